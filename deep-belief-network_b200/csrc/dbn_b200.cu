@@ -1,0 +1,477 @@
+// dbn_b200.cu -- C-ABI entry points (include/dbn_b200.h) of the B200-native CD-k / backprop path.
+// Host-side glue only: argument checks, workspace carving and kernel launches.  All arithmetic
+// lives in simt_gemm.cuh (strict FP32), umma_gemm.cuh (tcgen05 BF16) and misc_kernels.cuh.
+#include "dbn_common.cuh"
+#include "epilogue.cuh"
+#include "simt_gemm.cuh"
+#include "umma_gemm.cuh"
+#include "misc_kernels.cuh"
+
+using namespace dbn;
+
+namespace {
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+inline dbn_mat make_mat(void* p, int ld, int dtype) {
+  dbn_mat m;
+  m.ptr = p; m.ld = ld; m.dtype = dtype;
+  return m;
+}
+inline dbn_mat null_mat() { return make_mat(nullptr, 0, DBN_F32); }
+inline size_t elt_size(int dtype) { return dtype == DBN_F32 ? 4 : 2; }
+inline dbn_mat offset_cols(const dbn_mat& m, int cols) {
+  dbn_mat r = m;
+  if (r.ptr) r.ptr = static_cast<char*>(r.ptr) + (size_t)cols * elt_size(r.dtype);
+  return r;
+}
+inline dbn_operands make_ops(const dbn_mat& A, int tA, int row0A, const dbn_mat& B, int tB, int row0B, int K) {
+  dbn_operands o;
+  o.A = A; o.B = B; o.transA = tA; o.transB = tB; o.K = K; o.row0_A = row0A; o.row0_B = row0B; o._pad = 0;
+  return o;
+}
+inline dbn_act_epilogue blank_act() {
+  dbn_act_epilogue e;
+  memset(&e, 0, sizeof(e));
+  e.rng.keep_p = 1.0f;
+  return e;
+}
+inline dbn_update_epilogue blank_upd() {
+  dbn_update_epilogue e;
+  memset(&e, 0, sizeof(e));
+  e.decay = 1.0f;
+  return e;
+}
+
+int g_device_count = -1;
+int device_count_cached() {
+  if (g_device_count < 0) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { n = 0; (void)cudaGetLastError(); }
+    int ok = 0;
+    for (int d = 0; d < n; ++d) {
+      int major = 0;
+      if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10) ++ok;
+    }
+    g_device_count = ok;
+  }
+  return g_device_count;
+}
+#define DBN_NEED_DEVICE()                                                                           \
+  do {                                                                                              \
+    if (device_count_cached() <= 0)                                                                 \
+      return ::dbn::fail(DBN_ERR_NO_DEVICE, "%s: no sm_100 CUDA device (this library has no CPU fallback)%s", __func__, ""); \
+  } while (0)
+
+// bf16 row pitch: room for the ones column, multiple of 8 elements (16 B) as TMA requires.
+inline int bf16_pitch(int cols) { return (int)align_up((size_t)cols + 1, 8); }
+
+struct RbmWorkspace {
+  dbn_mat P0, Hs, Vt, Pk;
+};
+size_t rbm_ws_layout(int precision, int Bmax, int V, int H, char* base, RbmWorkspace* ws) {
+  const int dt = precision == DBN_PREC_BF16 ? DBN_BF16 : DBN_F32;
+  const int ldH = precision == DBN_PREC_BF16 ? bf16_pitch(H) : H;
+  const int ldV = precision == DBN_PREC_BF16 ? bf16_pitch(V) : V;
+  size_t off = 0;
+  auto carve = [&](int ld) {
+    dbn_mat m = make_mat(base ? base + off : nullptr, ld, dt);
+    off = align_up(off + (size_t)Bmax * ld * elt_size(dt), 1024);
+    return m;
+  };
+  RbmWorkspace w;
+  w.P0 = carve(ldH); w.Hs = carve(ldH); w.Vt = carve(ldV); w.Pk = carve(ldH);
+  if (ws) *ws = w;
+  return off;
+}
+
+struct MlpWorkspace {
+  dbn_mat a0;                         // masked input (dropout only)
+  dbn_mat act[DBN_MAX_LAYERS];        // a_1..a_L
+  dbn_mat delta[DBN_MAX_LAYERS];      // delta_1..delta_L
+  dbn_mat Z, dO;                      // head scores/outputs, head delta (fp32)
+};
+size_t mlp_ws_layout(int precision, int Bmax, int n_in, const int32_t* dims, int L, int n_out, char* base,
+                     MlpWorkspace* ws) {
+  const int dt = precision == DBN_PREC_BF16 ? DBN_BF16 : DBN_F32;
+  size_t off = 0;
+  auto carve = [&](int cols, int dtype, bool ones) {
+    const int ld = (dtype == DBN_BF16) ? bf16_pitch(cols) : cols;
+    (void)ones;
+    dbn_mat m = make_mat(base ? base + off : nullptr, ld, dtype);
+    off = align_up(off + (size_t)Bmax * ld * elt_size(dtype), 1024);
+    return m;
+  };
+  MlpWorkspace w;
+  w.a0 = carve(n_in, dt, true);
+  for (int l = 0; l < L; ++l) w.act[l] = carve(dims[l], dt, true);
+  for (int l = 0; l < L; ++l) w.delta[l] = carve(dims[l], dt, false);
+  w.Z = carve(n_out, DBN_F32, false);
+  w.dO = carve(n_out, DBN_F32, false);
+  if (ws) *ws = w;
+  return off;
+}
+
+int copy2d(cudaStream_t st, const dbn_mat& dst, const dbn_mat& src, int rows, int cols) {
+  if (dst.dtype == src.dtype) {
+    DBN_CUDA_OK(cudaMemcpy2DAsync(dst.ptr, (size_t)dst.ld * elt_size(dst.dtype), src.ptr,
+                                  (size_t)src.ld * elt_size(src.dtype), (size_t)cols * elt_size(src.dtype), rows,
+                                  cudaMemcpyDeviceToDevice, st));
+    return DBN_OK;
+  }
+  dbn_rng none;
+  memset(&none, 0, sizeof(none));
+  gather_rows_kernel<<<min(rows, 1184), 256, 0, st>>>(src, nullptr, rows, cols, dst, -1, none);
+  DBN_LAUNCH_CHECK();
+  return DBN_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dbn_abi_version(void) { return DBN_B200_ABI_VERSION; }
+const char* dbn_last_error(void) { return last_error_ref().c_str(); }
+int dbn_device_count(void) { return device_count_cached(); }
+uint64_t dbn_launch_count(void) { return launch_counter().load(); }
+size_t dbn_struct_size(int which) {
+  switch (which) {
+    case 0: return sizeof(dbn_mat);
+    case 1: return sizeof(dbn_rng);
+    case 2: return sizeof(dbn_operands);
+    case 3: return sizeof(dbn_act_epilogue);
+    case 4: return sizeof(dbn_update_epilogue);
+    case 5: return sizeof(dbn_rbm_step_args);
+    case 6: return sizeof(dbn_mlp_step_args);
+    default: return 0;
+  }
+}
+
+int dbn_philox_uniforms_host(uint64_t seed, uint32_t stream, uint32_t epoch, uint32_t row0, int rows, int cols,
+                             float* out_host) {
+  DBN_REQUIRE(out_host && rows >= 0 && cols >= 0, "bad argument");
+  for (int r = 0; r < rows; ++r)
+    for (int q = 0; q * 4 < cols; ++q) {
+      uint32_t o[4];
+      philox4x32_10(row0 + (uint32_t)r, (uint32_t)q, epoch, stream, (uint32_t)seed, (uint32_t)(seed >> 32), o);
+      for (int j = 0; j < 4 && q * 4 + j < cols; ++j) out_host[(size_t)r * cols + q * 4 + j] = u01_from_bits(o[j]);
+    }
+  return DBN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+int dbn_gemm_act(void* stream, int precision, int M, int N, const dbn_operands* ops, int n_ops,
+                 const dbn_act_epilogue* epi) {
+  DBN_NEED_DEVICE();
+  DBN_REQUIRE(ops && epi && (n_ops == 1 || n_ops == 2), "bad operands");
+  DBN_REQUIRE(M > 0 && N > 0, "empty output");
+  if (precision == DBN_PREC_BF16 && umma_gemm_supported(M, N, ops, n_ops))
+    return umma_gemm_act(as_stream(stream), M, N, ops, n_ops, *epi);
+  return simt_gemm_act(as_stream(stream), M, N, ops, n_ops, *epi);
+}
+
+int dbn_gemm_update(void* stream, int precision, int M, int N, int augM, int augN, const dbn_operands* ops,
+                    int n_ops, const dbn_update_epilogue* epi) {
+  DBN_NEED_DEVICE();
+  DBN_REQUIRE(ops && epi && (n_ops == 1 || n_ops == 2), "bad operands");
+  DBN_REQUIRE(M > 0 && N > 0, "empty output");
+  if (precision == DBN_PREC_BF16 && umma_gemm_supported(M + augM, N + augN, ops, n_ops))
+    return umma_gemm_update(as_stream(stream), M, N, augM, augN, ops, n_ops, *epi);
+  return simt_gemm_update(as_stream(stream), M, N, augM, augN, ops, n_ops, *epi);
+}
+
+// ------------------------------------------------------------------------------------------------
+int dbn_rbm_hidden_means(void* stream, int precision, const dbn_mat* X, int row0, int B, int V, int H,
+                         const dbn_mat* W, const float* c, int act, const dbn_mat* out) {
+  DBN_REQUIRE(X && W && out && out->ptr, "null argument");
+  dbn_operands o = make_ops(*X, 0, row0, *W, 0, 0, V);
+  dbn_act_epilogue e = blank_act();
+  e.bias = c; e.act = act; e.out = *out;
+  return dbn_gemm_act(stream, precision, B, H, &o, 1, &e);
+}
+
+int dbn_rbm_visible_means(void* stream, int precision, const dbn_mat* Hm, int B, int V, int H, const dbn_mat* W,
+                          const float* b, int act, const dbn_mat* out) {
+  DBN_REQUIRE(Hm && W && out && out->ptr, "null argument");
+  dbn_operands o = make_ops(*Hm, 0, 0, *W, 1, 0, H);
+  dbn_act_epilogue e = blank_act();
+  e.bias = b; e.act = act; e.out = *out;
+  return dbn_gemm_act(stream, precision, B, V, &o, 1, &e);
+}
+
+size_t dbn_rbm_workspace_bytes(int precision, int Bmax, int V, int H) {
+  return rbm_ws_layout(precision, Bmax, V, H, nullptr, nullptr);
+}
+
+int dbn_rbm_workspace_init(void* stream, int precision, int Bmax, int V, int H, void* workspace) {
+  DBN_NEED_DEVICE();
+  RbmWorkspace ws;
+  size_t bytes = rbm_ws_layout(precision, Bmax, V, H, static_cast<char*>(workspace), &ws);
+  DBN_CUDA_OK(cudaMemsetAsync(workspace, 0, bytes, as_stream(stream)));
+  if (precision == DBN_PREC_BF16) {
+    DBN_TRY(dbn_fill_ones_column(stream, &ws.P0, Bmax, H));
+    DBN_TRY(dbn_fill_ones_column(stream, &ws.Pk, Bmax, H));
+    DBN_TRY(dbn_fill_ones_column(stream, &ws.Vt, Bmax, V));
+  }
+  return DBN_OK;
+}
+
+int dbn_rbm_cd_step(void* stream, const dbn_rbm_step_args* a) {
+  DBN_NEED_DEVICE();
+  DBN_REQUIRE(a != nullptr, "null args");
+  DBN_REQUIRE(a->B > 0 && a->V > 0 && a->H > 0 && a->k >= 0, "bad shape");
+  DBN_REQUIRE(a->act == DBN_ACT_SIGMOID || a->act == DBN_ACT_RELU, "Invalid activation function.");
+  DBN_REQUIRE(a->workspace_bytes >= dbn_rbm_workspace_bytes(a->precision, a->B, a->V, a->H), "workspace too small");
+  const bool tc = a->precision == DBN_PREC_BF16;
+  DBN_REQUIRE(!tc || (a->Wb.ptr && a->X.dtype == DBN_BF16), "BF16 mode needs bf16 X and the bf16 shadow of W");
+  if (a->k == 0) return DBN_OK;  // v_k == v_0: all deltas are zero (dbn/models.py:134 loop is empty)
+  RbmWorkspace ws;
+  rbm_ws_layout(a->precision, a->B, a->V, a->H, static_cast<char*>(a->workspace), &ws);
+  const dbn_mat Wop = tc ? a->Wb : make_mat(a->W, a->ldw, DBN_F32);
+  const int B = a->B, V = a->V, H = a->H;
+
+  for (int t = 0; t < a->k; ++t) {
+    // h_t ~ P(h | v_t): dbn/models.py:135 -> :148-155
+    dbn_operands o = (t == 0) ? make_ops(a->X, 0, a->row0, Wop, 0, 0, V) : make_ops(ws.Vt, 0, 0, Wop, 0, 0, V);
+    dbn_act_epilogue e = blank_act();
+    e.bias = a->c; e.act = a->act;
+    e.rng = a->rng;
+    e.rng.mode = DBN_RNG_SAMPLE;
+    e.rng.stream = a->rng.stream + (uint32_t)t;
+    if (a->rng.injected.ptr) e.rng.injected = offset_cols(a->rng.injected, t * H);
+    e.out = (t == 0) ? ws.P0 : ws.Pk;  // only the t = 0 means are kept (== h_0 of :140)
+    if (t == 0) e.out2 = a->P0;
+    e.sample = ws.Hs;
+    DBN_TRY(dbn_gemm_act(stream, a->precision, B, H, &o, 1, &e));
+    if (t == 0 && a->H0s.ptr) DBN_TRY(copy2d(as_stream(stream), a->H0s, ws.Hs, B, H));
+    // v_{t+1} = mean visible: dbn/models.py:136 -> :185-201
+    dbn_operands o2 = make_ops(ws.Hs, 0, 0, Wop, 1, 0, H);
+    dbn_act_epilogue e2 = blank_act();
+    e2.bias = a->b; e2.act = a->act; e2.out = ws.Vt;
+    if (t == a->k - 1) e2.out2 = a->Vk;
+    DBN_TRY(dbn_gemm_act(stream, a->precision, B, V, &o2, 1, &e2));
+  }
+  {  // h_k = P(h | v_k): dbn/models.py:141
+    dbn_operands o = make_ops(ws.Vt, 0, 0, Wop, 0, 0, V);
+    dbn_act_epilogue e = blank_act();
+    e.bias = a->c; e.act = a->act; e.out = ws.Pk; e.out2 = a->Pk;
+    DBN_TRY(dbn_gemm_act(stream, a->precision, B, H, &o, 1, &e));
+  }
+  {  // dW = h_0^T v_0 - h_k^T v_k, db, dc (dbn/models.py:142-144) + update (:117-119)
+    dbn_operands o[2];
+    o[0] = make_ops(ws.P0, 1, 0, a->X, 1, a->row0, B);
+    o[1] = make_ops(ws.Pk, 1, 0, ws.Vt, 1, 0, B);
+    dbn_update_epilogue u = blank_upd();
+    u.W = a->W; u.ldw = a->ldw; u.Wb = tc ? a->Wb : null_mat();
+    u.vecM = a->c; u.vecN = a->b; u.decay = 1.0f; u.scale = a->lr_over_bs; u.raw = a->raw_delta;
+    DBN_TRY(dbn_gemm_update(stream, a->precision, H, V, 1, 1, o, 2, &u));
+  }
+  return DBN_OK;
+}
+
+int dbn_rbm_fit_epoch(void* stream, const dbn_rbm_step_args* tmpl, int n_rows, int batch_size) {
+  DBN_REQUIRE(tmpl && n_rows >= 0 && batch_size > 0, "bad argument");
+  for (int s = 0; s < n_rows; s += batch_size) {  // batch_generator: dbn/utils.py:14-22 (short last batch)
+    dbn_rbm_step_args a = *tmpl;
+    a.B = std::min(batch_size, n_rows - s);
+    a.row0 = tmpl->row0 + s;
+    a.rng.row0 = tmpl->rng.row0 + (uint32_t)s;
+    if (a.rng.injected.ptr)
+      a.rng.injected.ptr = static_cast<char*>(a.rng.injected.ptr) + (size_t)s * a.rng.injected.ld * sizeof(float);
+    DBN_TRY(dbn_rbm_cd_step(stream, &a));
+  }
+  return DBN_OK;
+}
+
+int dbn_rbm_apply_delta(void* stream, int V, int H, float scale, const float* raw, int ld, float* W, int ldw,
+                        float* b, float* c, const dbn_mat* Wb) {
+  DBN_NEED_DEVICE();
+  DBN_REQUIRE(raw && W && b && c, "null argument");
+  const long total = (long)(H + 1) * ((V + 4) / 4);
+  const int blocks = (int)std::min<long>((total + 255) / 256, 148L * 8);
+  apply_delta_kernel<<<blocks, 256, 0, as_stream(stream)>>>(V, H, scale, raw, ld, W, ldw, b, c,
+                                                           Wb ? *Wb : null_mat());
+  DBN_LAUNCH_CHECK();
+  return DBN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+size_t dbn_mlp_workspace_bytes(int precision, int Bmax, int n_in, const int32_t* dims, int n_layers, int n_out) {
+  return mlp_ws_layout(precision, Bmax, n_in, dims, n_layers, n_out, nullptr, nullptr);
+}
+
+int dbn_mlp_workspace_init(void* stream, int precision, int Bmax, int n_in, const int32_t* dims, int n_layers,
+                           int n_out, void* workspace) {
+  DBN_NEED_DEVICE();
+  DBN_REQUIRE(n_layers >= 1 && n_layers <= DBN_MAX_LAYERS, "bad layer count");
+  MlpWorkspace ws;
+  size_t bytes = mlp_ws_layout(precision, Bmax, n_in, dims, n_layers, n_out, static_cast<char*>(workspace), &ws);
+  DBN_CUDA_OK(cudaMemsetAsync(workspace, 0, bytes, as_stream(stream)));
+  if (precision == DBN_PREC_BF16) {
+    DBN_TRY(dbn_fill_ones_column(stream, &ws.a0, Bmax, n_in));
+    for (int l = 0; l < n_layers; ++l) DBN_TRY(dbn_fill_ones_column(stream, &ws.act[l], Bmax, dims[l]));
+  }
+  return DBN_OK;
+}
+
+int dbn_mlp_train_step(void* stream, const dbn_mlp_step_args* a) {
+  DBN_NEED_DEVICE();
+  DBN_REQUIRE(a != nullptr, "null args");
+  const int L = a->n_layers, B = a->B;
+  DBN_REQUIRE(L >= 1 && L <= DBN_MAX_LAYERS && B > 0 && a->n_in > 0 && a->n_out > 0, "bad shape");
+  DBN_REQUIRE(a->act == DBN_ACT_SIGMOID || a->act == DBN_ACT_RELU, "Invalid activation function.");
+  DBN_REQUIRE(a->workspace_bytes >= dbn_mlp_workspace_bytes(a->precision, B, a->n_in, a->dims, L, a->n_out),
+              "workspace too small");
+  const bool tc = a->precision == DBN_PREC_BF16;
+  const bool dropout = a->keep_p < 1.0f;
+  const bool raw = a->raw_grads[0].ptr != nullptr;
+  cudaStream_t st = as_stream(stream);
+  MlpWorkspace ws;
+  mlp_ws_layout(a->precision, B, a->n_in, a->dims, L, a->n_out, static_cast<char*>(a->workspace), &ws);
+  auto Wop = [&](int l) { return tc ? a->Wb[l] : make_mat(a->W[l], a->ldw[l], DBN_F32); };
+  const int prime = a->act == DBN_ACT_SIGMOID ? DBN_MUL_PRIME_SIGMOID : DBN_MUL_PRIME_RELU;
+
+  // ---- forward (dbn/models.py:394-417) ----
+  dbn_mat in0 = a->X;
+  int in0_row0 = a->row0;
+  if (dropout) {  // input_data *= Binomial(1, p): dbn/models.py:401-403
+    dbn_rng r = a->rng;
+    r.mode = DBN_RNG_MASK; r.keep_p = a->keep_p; r.stream = a->rng.stream + 0u; r.injected = a->masks[0];
+    dbn_mat src = a->X;
+    src.ptr = static_cast<char*>(src.ptr) + (size_t)a->row0 * src.ld * elt_size(src.dtype);
+    gather_rows_kernel<<<min(B, 1184), 256, 0, st>>>(src, nullptr, B, a->n_in, ws.a0, -1, r);
+    DBN_LAUNCH_CHECK();
+    in0 = ws.a0;
+    in0_row0 = 0;
+  }
+  for (int l = 0; l < L; ++l) {
+    const int K = l == 0 ? a->n_in : a->dims[l - 1];
+    dbn_operands o = make_ops(l == 0 ? in0 : ws.act[l - 1], 0, l == 0 ? in0_row0 : 0, Wop(l), 0, 0, K);
+    dbn_act_epilogue e = blank_act();
+    e.bias = a->c[l]; e.act = a->act; e.out = ws.act[l];
+    if (dropout) {  // dbn/models.py:408-411
+      e.rng = a->rng;
+      e.rng.mode = DBN_RNG_MASK; e.rng.keep_p = a->keep_p; e.rng.stream = a->rng.stream + (uint32_t)(l + 1);
+      e.rng.injected = a->masks[l + 1];
+    }
+    DBN_TRY(dbn_gemm_act(stream, a->precision, B, a->dims[l], &o, 1, &e));
+  }
+  const int HL = a->dims[L - 1];
+  const dbn_mat WoM = make_mat(a->Wo, a->ldwo, DBN_F32);
+  {  // head scores (dbn/models.py:601 / :703), strict FP32: the head is tiny (n_out columns)
+    dbn_operands o = make_ops(ws.act[L - 1], 0, 0, WoM, 0, 0, HL);
+    dbn_act_epilogue e = blank_act();
+    e.bias = a->bo; e.act = DBN_ACT_IDENTITY; e.out = ws.Z;
+    DBN_TRY(simt_gemm_act(st, B, a->n_out, &o, 1, e));
+  }
+  DBN_TRY(dbn_head_delta(stream, a->head, static_cast<float*>(ws.Z.ptr), ws.Z.ld, a->Y + (size_t)a->row0 * a->ldy,
+                         a->ldy, B, a->n_out, static_cast<float*>(ws.dO.ptr), ws.dO.ld, a->loss_rows));
+  if (a->out.ptr) DBN_TRY(copy2d(st, a->out, ws.Z, B, a->n_out));
+
+  // ---- backward deltas (dbn/models.py:489-501), all with the pre-update weights ----
+  {
+    dbn_operands o = make_ops(ws.dO, 0, 0, WoM, 1, 0, a->n_out);
+    dbn_act_epilogue e = blank_act();
+    e.act = DBN_ACT_IDENTITY; e.mul = prime; e.aux = ws.act[L - 1]; e.out = ws.delta[L - 1];
+    DBN_TRY(simt_gemm_act(st, B, HL, &o, 1, e));
+  }
+  for (int l = L - 2; l >= 0; --l) {
+    dbn_operands o = make_ops(ws.delta[l + 1], 0, 0, Wop(l + 1), 1, 0, a->dims[l + 1]);
+    dbn_act_epilogue e = blank_act();
+    e.act = DBN_ACT_IDENTITY; e.mul = prime; e.aux = ws.act[l]; e.out = ws.delta[l];
+    DBN_TRY(dbn_gemm_act(stream, a->precision, B, a->dims[l], &o, 1, &e));
+  }
+
+  // ---- gradients + decayed SGD update (dbn/models.py:508-513, :454-465) ----
+  {
+    dbn_operands o = make_ops(ws.dO, 1, 0, ws.act[L - 1], 1, 0, B);
+    dbn_update_epilogue u = blank_upd();
+    u.W = a->Wo; u.ldw = a->ldwo; u.vecM = a->bo; u.decay = a->decay; u.scale = -a->lr_over_bs;
+    if (raw) u.raw = a->raw_grads[L];
+    DBN_TRY(simt_gemm_update(st, a->n_out, HL, 0, 1, &o, 1, u));
+  }
+  for (int l = L - 1; l >= 0; --l) {
+    const int K_in = l == 0 ? a->n_in : a->dims[l - 1];
+    dbn_operands o = make_ops(ws.delta[l], 1, 0, l == 0 ? in0 : ws.act[l - 1], 1, l == 0 ? in0_row0 : 0, B);
+    dbn_update_epilogue u = blank_upd();
+    u.W = a->W[l]; u.ldw = a->ldw[l]; u.Wb = tc ? a->Wb[l] : null_mat();
+    u.vecM = a->c[l]; u.decay = a->decay; u.scale = -a->lr_over_bs;
+    if (raw) u.raw = a->raw_grads[l];
+    DBN_TRY(dbn_gemm_update(stream, a->precision, a->dims[l], K_in, 0, 1, &o, 1, &u));
+  }
+  return DBN_OK;
+}
+
+int dbn_mlp_fit_epoch(void* stream, const dbn_mlp_step_args* tmpl, int n_rows, int batch_size) {
+  DBN_REQUIRE(tmpl && n_rows >= 0 && batch_size > 0, "bad argument");
+  for (int s = 0; s < n_rows; s += batch_size) {
+    dbn_mlp_step_args a = *tmpl;
+    a.B = std::min(batch_size, n_rows - s);
+    a.row0 = tmpl->row0 + s;
+    a.rng.row0 = tmpl->rng.row0 + (uint32_t)s;
+    if (a.loss_rows) a.loss_rows += s;
+    for (int j = 0; j <= a.n_layers; ++j)
+      if (a.masks[j].ptr)
+        a.masks[j].ptr = static_cast<char*>(a.masks[j].ptr) + (size_t)s * a.masks[j].ld * sizeof(float);
+    DBN_TRY(dbn_mlp_train_step(stream, &a));
+  }
+  return DBN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+int dbn_gather_rows(void* stream, const dbn_mat* src, const int32_t* idx, int n_rows, int n_cols, const dbn_mat* dst,
+                    int ones_col, const dbn_rng* input_dropout) {
+  DBN_NEED_DEVICE();
+  DBN_REQUIRE(src && dst && src->ptr && dst->ptr, "null argument");
+  if (n_rows <= 0) return DBN_OK;
+  dbn_rng r;
+  memset(&r, 0, sizeof(r));
+  if (input_dropout) r = *input_dropout;
+  gather_rows_kernel<<<std::min(n_rows, 148 * 16), 256, 0, as_stream(stream)>>>(*src, idx, n_rows, n_cols, *dst,
+                                                                              ones_col, r);
+  DBN_LAUNCH_CHECK();
+  return DBN_OK;
+}
+
+int dbn_scale_cast(void* stream, const float* src, int lds, int rows, int cols, float scale, const dbn_mat* dst) {
+  DBN_NEED_DEVICE();
+  DBN_REQUIRE(src && dst && dst->ptr, "null argument");
+  const long total = (long)rows * ((cols + 3) / 4);
+  if (total <= 0) return DBN_OK;
+  const int blocks = (int)std::min<long>((total + 255) / 256, 148L * 8);
+  scale_cast_kernel<<<blocks, 256, 0, as_stream(stream)>>>(src, lds, rows, cols, scale, *dst);
+  DBN_LAUNCH_CHECK();
+  return DBN_OK;
+}
+
+int dbn_fill_ones_column(void* stream, const dbn_mat* m, int rows, int col) {
+  DBN_NEED_DEVICE();
+  DBN_REQUIRE(m && m->ptr && col < m->ld, "bad matrix");
+  fill_ones_column_kernel<<<ceil_div(rows, 256), 256, 0, as_stream(stream)>>>(*m, rows, col);
+  DBN_LAUNCH_CHECK();
+  return DBN_OK;
+}
+
+int dbn_sum_sq_diff(void* stream, const dbn_mat* A, const dbn_mat* B, int row0_B, int rows, int cols, float inv_denom,
+                    float* out) {
+  DBN_NEED_DEVICE();
+  DBN_REQUIRE(A && B && out, "null argument");
+  const long total = (long)rows * ((cols + 3) / 4);
+  if (total <= 0) return DBN_OK;
+  const int blocks = (int)std::min<long>((total + 255) / 256, 148L * 4);
+  sum_sq_diff_kernel<<<blocks, 256, 0, as_stream(stream)>>>(*A, *B, row0_B, rows, cols, inv_denom, out);
+  DBN_LAUNCH_CHECK();
+  return DBN_OK;
+}
+
+int dbn_head_delta(void* stream, int head, float* Z, int ldz, const float* Y, int ldy, int B, int C, float* delta,
+                   int ldd, float* loss_rows) {
+  DBN_NEED_DEVICE();
+  DBN_REQUIRE(Z && B > 0 && C > 0, "bad argument");
+  head_delta_kernel<<<ceil_div(B * 32, 128), 128, 0, as_stream(stream)>>>(head, Z, ldz, Y, ldy, B, C, delta, ldd,
+                                                                        loss_rows);
+  DBN_LAUNCH_CHECK();
+  return DBN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,154 @@
+// misc_kernels.cuh -- the memory-bound helpers around the contractions: row gather (epoch
+// shuffle), scale/cast (p-rescale, bf16 shadows), ones columns, reconstruction error, output head.
+#pragma once
+#include "epilogue.cuh"
+
+namespace dbn {
+
+// dst[i, :] = src[idx ? idx[i] : i, :] (optionally * Bernoulli(keep_p) input dropout), dst[i, ones_col] = 1.
+// One warp-row per block row: 256 threads stride over the columns of `rows_per_block` rows.
+__global__ void __launch_bounds__(256) gather_rows_kernel(dbn_mat src, const int32_t* __restrict__ idx, int n_rows,
+                                                          int n_cols, dbn_mat dst, int ones_col, dbn_rng rng) {
+  const uint32_t epoch = rng.epoch + (rng.epoch_ptr ? *rng.epoch_ptr : 0u);
+  const int quads = (n_cols + 3) >> 2;
+  for (int i = blockIdx.x; i < n_rows; i += gridDim.x) {
+    const int s = idx ? idx[i] : i;
+    for (int q = threadIdx.x; q < quads; q += blockDim.x) {
+      const int c = q << 2;
+      const int nv = min(4, n_cols - c);
+      float v[4];
+      mat_load4(src, s, c, v, nv);
+      if (rng.mode == DBN_RNG_MASK) {
+        float u[4];
+        if (rng.injected.ptr) {
+          mat_load4(rng.injected, i, c, u, nv);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) v[j] = (u[j] != 0.0f) ? v[j] : 0.0f;
+        } else {
+          rng_uniform4(rng, epoch, i, c, u);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) v[j] = (u[j] < rng.keep_p) ? v[j] : 0.0f;
+        }
+      }
+      mat_store4(dst, i, c, v, nv);
+    }
+    if (ones_col >= 0 && threadIdx.x == 0) mat_store(dst, i, ones_col, 1.0f);
+  }
+}
+
+__global__ void __launch_bounds__(256) scale_cast_kernel(const float* __restrict__ src, int lds, int rows, int cols,
+                                                         float scale, dbn_mat dst) {
+  const int quads = (cols + 3) >> 2;
+  const long total = (long)rows * quads;
+  dbn_mat s;
+  s.ptr = const_cast<float*>(src); s.ld = lds; s.dtype = DBN_F32;
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    const int r = (int)(t / quads), c = (int)(t % quads) << 2;
+    const int nv = min(4, cols - c);
+    float v[4];
+    mat_load4(s, r, c, v, nv);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] *= scale;
+    mat_store4(dst, r, c, v, nv);
+  }
+}
+
+__global__ void fill_ones_column_kernel(dbn_mat m, int rows, int col) {
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += gridDim.x * blockDim.x) mat_store(m, r, col, 1.0f);
+}
+
+// out[0] += inv_denom * sum (A[r,c] - B[row0_B + r, c])^2
+__global__ void __launch_bounds__(256) sum_sq_diff_kernel(dbn_mat A, dbn_mat B, int row0_B, int rows, int cols,
+                                                          float inv_denom, float* out) {
+  const int quads = (cols + 3) >> 2;
+  const long total = (long)rows * quads;
+  float acc = 0.0f;
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    const int r = (int)(t / quads), c = (int)(t % quads) << 2;
+    const int nv = min(4, cols - c);
+    float a[4], b[4];
+    mat_load4(A, r, c, a, nv);
+    mat_load4(B, row0_B + r, c, b, nv);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float d = (j < nv) ? (a[j] - b[j]) : 0.0f;
+      acc = fmaf(d, d, acc);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __shared__ float warp_sums[8];
+  if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.0f;
+    for (int w = 0; w < 8; ++w) s += warp_sums[w];
+    atomicAdd(out, s * inv_denom);
+  }
+}
+
+// One warp per sample row.  softmax (max-shifted; equal to the reference's un-shifted form
+// dbn/models.py:603-605 within rounding) or identity; delta = out - y (dbn/models.py:617-626,
+// :713-720); loss = -log p[label] (:673-680) or sum_t (pred - y)^2 (:733-741).
+__global__ void __launch_bounds__(128) head_delta_kernel(int head, float* Z, int ldz, const float* __restrict__ Y,
+                                                         int ldy, int B, int C, float* delta, int ldd,
+                                                         float* loss_rows) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= B) return;
+  float* z = Z + (size_t)warp * ldz;
+  const bool train = (Y != nullptr) && (delta != nullptr);  // inference: outputs only
+  const float* y = train ? Y + (size_t)warp * ldy : nullptr;
+  float* d = train ? delta + (size_t)warp * ldd : nullptr;
+  float loss = 0.0f;
+  if (head == DBN_HEAD_SOFTMAX) {
+    float mx = -INFINITY;
+    for (int j = lane; j < C; j += 32) mx = fmaxf(mx, z[j]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.0f;
+    for (int j = lane; j < C; j += 32) sum += expf(z[j] - mx);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float inv = 1.0f / sum;
+    float py = 0.0f;
+    for (int j = lane; j < C; j += 32) {
+      const float p = expf(z[j] - mx) * inv;
+      z[j] = p;
+      if (train) {
+        d[j] = p - y[j];
+        py = fmaf(p, y[j], py);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) py += __shfl_xor_sync(0xffffffffu, py, o);
+    loss = -logf(py);
+  } else if (train) {
+    for (int j = lane; j < C; j += 32) {
+      const float e = z[j] - y[j];
+      d[j] = e;
+      loss = fmaf(e, e, loss);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) loss += __shfl_xor_sync(0xffffffffu, loss, o);
+  }
+  if (train && loss_rows != nullptr && lane == 0) loss_rows[warp] = loss;
+}
+
+// W += s * dW, b += s * db (last row), c += s * dc (last column) from a raw [(H+1), ld] delta buffer.
+__global__ void __launch_bounds__(256) apply_delta_kernel(int V, int H, float scale, const float* __restrict__ raw,
+                                                          int ld, float* W, int ldw, float* b, float* c, dbn_mat Wb) {
+  const int quads = (V + 1 + 3) >> 2;
+  const long total = (long)(H + 1) * quads;
+  dbn_update_epilogue e;
+  e.W = W; e.ldw = ldw; e.Wb = Wb; e.vecM = c; e.vecN = b; e.decay = 1.0f; e.scale = scale;
+  e.raw.ptr = nullptr; e.raw.ld = 0; e.raw.dtype = DBN_F32;
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    const int m = (int)(t / quads), n4 = (int)(t % quads) << 2;
+    float acc[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[j] = (n4 + j <= V) ? raw[(size_t)m * ld + n4 + j] : 0.0f;
+    upd_epilogue_quad(e, m, n4, acc, H, V, 1, 1);
+  }
+}
+
+}  // namespace dbn

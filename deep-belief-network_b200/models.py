@@ -1,0 +1,351 @@
+"""scikit-learn style estimators of the B200 backend -- the host-side mirror of the reference's
+backend interface (`dbn/models.py`; the TF backend `dbn/tensorflow/models.py` is the precedent for
+what a backend overrides).  Same four classes, constructor arguments, defaults, fitted attributes,
+method signatures and error behaviour; the training loops run on the device through
+libdbn_b200.so (see engine.py) instead of per-sample NumPy.
+
+Fitted parameters are exposed exactly like the reference's NumPy backend: `W (H,V)`, `b (V,)`,
+`c (H,)` float64 ndarrays on the estimator (so pickles are plain NumPy and interoperate), head
+`W (out,H_last)`, `b (out,)` on the supervised estimators.
+
+Two extra, optional constructor arguments exist on every class (defaults keep the reference's
+behaviour): `precision` in {'auto','fp32','bf16'} selects the strict-FP32 FFMA kernels or the
+tcgen05 BF16 kernels, and `rng` in {'philox','numpy'} selects in-kernel Philox draws or a replay of
+the reference's `np.random` uniform / binomial stream (parity runs).
+"""
+from __future__ import annotations
+
+import pickle
+
+import numpy as np
+from scipy.stats import truncnorm
+from sklearn.base import BaseEstimator, ClassifierMixin, RegressorMixin, TransformerMixin
+
+from . import engine as E
+from .activations import ReLUActivationFunction, SigmoidActivationFunction
+
+
+def _device():
+    import torch
+    E.require_device()
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _to_device_f32(X):
+    import torch
+    X = np.ascontiguousarray(np.asarray(X), dtype=np.float32)
+    return torch.from_numpy(X).to(_device())
+
+
+def _draw_seed():
+    """Philox key drawn from the global np.random stream, so `np.random.seed(...)` stays the
+    user-facing reproducibility knob (reference: example_classification.py:3)."""
+    return int(np.random.randint(0, 2 ** 31 - 1)) | (int(np.random.randint(0, 2 ** 31 - 1)) << 32)
+
+
+class BaseModel(object):
+    """save / load by pickling the estimator (reference: dbn/models.py:11-23)."""
+
+    def save(self, save_path):
+        with open(save_path, "wb") as fp:
+            pickle.dump(self, fp)
+
+    @classmethod
+    def load(cls, load_path):
+        with open(load_path, "rb") as fp:
+            return pickle.load(fp)
+
+
+class BinaryRBM(BaseEstimator, TransformerMixin, BaseModel):
+    """Binary restricted Boltzmann machine trained with CD-k (reference: dbn/models.py:26-220)."""
+
+    def __init__(self, n_hidden_units=100, activation_function='sigmoid', optimization_algorithm='sgd',
+                 learning_rate=1e-3, n_epochs=10, contrastive_divergence_iter=1, batch_size=32, verbose=True,
+                 precision='auto', rng='philox'):
+        self.n_hidden_units = n_hidden_units
+        self.activation_function = activation_function
+        self.optimization_algorithm = optimization_algorithm
+        self.learning_rate = learning_rate
+        self.n_epochs = n_epochs
+        self.contrastive_divergence_iter = contrastive_divergence_iter
+        self.batch_size = batch_size
+        self.verbose = verbose
+        self.precision = precision
+        self.rng = rng
+
+    # ---- parameter initialisation: same draws, same order as dbn/models.py:55-69 ----
+    def _init_params(self, n_visible):
+        self.n_visible_units = n_visible
+        h, s = self.n_hidden_units, np.sqrt(n_visible)
+        if self.activation_function == 'sigmoid':
+            self.W = np.random.randn(h, n_visible) / s
+            self.c = np.random.randn(h) / s
+            self.b = np.random.randn(n_visible) / s
+            self._activation_function_class = SigmoidActivationFunction
+        elif self.activation_function == 'relu':
+            self.W = truncnorm.rvs(-0.2, 0.2, size=[h, n_visible]) / s
+            self.c = np.full(h, 0.1) / s
+            self.b = np.full(n_visible, 0.1) / s
+            self._activation_function_class = ReLUActivationFunction
+        else:
+            raise ValueError("Invalid activation function.")
+
+    def _resolved_precision(self):
+        return E.resolve_precision(self.precision, self.n_visible_units, self.n_hidden_units, self.batch_size)
+
+    def _device_layer(self, precision=None):
+        return E.DeviceRbm(self.W, self.b, self.c, self.activation_function,
+                           precision or self._resolved_precision(), _device())
+
+    def _fit_device(self, Xd, dp=None):
+        """Initialise and train on a device-resident fp32 dataset; returns the DeviceRbm so a
+        stacked DBN can keep transforming on the device."""
+        self._init_params(int(Xd.shape[1]))
+        if self.optimization_algorithm != 'sgd':
+            raise ValueError("Invalid optimization algorithm.")
+        layer = self._device_layer()
+        seed = _draw_seed()
+        cb = None
+        if self.verbose:
+            cb = lambda it, err: print(">> Epoch %d finished \tRBM Reconstruction error %f" % (it, err))
+        layer.fit(Xd, self.n_epochs, self.batch_size, self.contrastive_divergence_iter, self.learning_rate, seed,
+                  rng_mode=self.rng, verbose=cb, dp=dp)
+        self.W, self.b, self.c = layer.export()
+        return layer
+
+    def fit(self, X):
+        """Fit the RBM to X (n_samples, n_features).  Returns self (dbn/models.py:49-75)."""
+        self._fit_device(_to_device_f32(X))
+        return self
+
+    def transform(self, X):
+        """Hidden-unit means of X; a 1-D sample gives a 1-D result (dbn/models.py:77-86)."""
+        X = np.asarray(X)
+        single = X.ndim == 1
+        Xd = _to_device_f32(X[None, :] if single else X)
+        out = self._device_layer().transform(Xd).double().cpu().numpy()
+        return out[0] if single else out
+
+    def _reconstruct(self, transformed_data):
+        """Visible means given hidden values (dbn/models.py:88-94)."""
+        import torch
+        layer = self._device_layer('fp32')
+        Hd = _to_device_f32(transformed_data)
+        out = torch.empty(Hd.shape[0], layer.V, dtype=torch.float32, device=Hd.device)
+        layer.visible_means(Hd, int(Hd.shape[0]), out)
+        return out.double().cpu().numpy()
+
+    def _compute_reconstruction_error(self, data):
+        """mean over samples of the squared reconstruction distance (dbn/models.py:212-220)."""
+        return self._device_layer().reconstruction_error(_to_device_f32(data))
+
+
+class UnsupervisedDBN(BaseEstimator, TransformerMixin, BaseModel):
+    """Greedy layer-wise stack of RBMs (reference: dbn/models.py:223-287)."""
+
+    def __init__(self, hidden_layers_structure=[100, 100], activation_function='sigmoid',
+                 optimization_algorithm='sgd', learning_rate_rbm=1e-3, n_epochs_rbm=10,
+                 contrastive_divergence_iter=1, batch_size=32, verbose=True, precision='auto', rng='philox'):
+        self.hidden_layers_structure = hidden_layers_structure
+        self.activation_function = activation_function
+        self.optimization_algorithm = optimization_algorithm
+        self.learning_rate_rbm = learning_rate_rbm
+        self.n_epochs_rbm = n_epochs_rbm
+        self.contrastive_divergence_iter = contrastive_divergence_iter
+        self.batch_size = batch_size
+        self.rbm_layers = None
+        self.verbose = verbose
+        self.precision = precision
+        self.rng = rng
+        self.rbm_class = BinaryRBM
+
+    def _fit_device(self, Xd):
+        self.rbm_layers = [
+            self.rbm_class(n_hidden_units=h, activation_function=self.activation_function,
+                           optimization_algorithm=self.optimization_algorithm, learning_rate=self.learning_rate_rbm,
+                           n_epochs=self.n_epochs_rbm, contrastive_divergence_iter=self.contrastive_divergence_iter,
+                           batch_size=self.batch_size, verbose=self.verbose, precision=self.precision, rng=self.rng)
+            for h in self.hidden_layers_structure]
+        if self.verbose:
+            print("[START] Pre-training step:")
+        data = Xd
+        for rbm in self.rbm_layers:      # strictly sequential: layer l+1 sees layer l's final features
+            layer = rbm._fit_device(data)
+            data = layer.transform(data)  # stays in HBM between layers
+        if self.verbose:
+            print("[END] Pre-training step")
+        return self
+
+    def fit(self, X, y=None):
+        """Pre-train every layer on the previous layer's features (dbn/models.py:248-276)."""
+        return self._fit_device(_to_device_f32(X))
+
+    def _transform_device(self, Xd):
+        for rbm in self.rbm_layers:
+            Xd = rbm._device_layer().transform(Xd)
+        return Xd
+
+    def transform(self, X):
+        """Stacked transform (dbn/models.py:278-287)."""
+        X = np.asarray(X)
+        single = X.ndim == 1
+        out = self._transform_device(_to_device_f32(X[None, :] if single else X)).double().cpu().numpy()
+        return out[0] if single else out
+
+
+class AbstractSupervisedDBN(BaseEstimator, BaseModel):
+    """Pre-train + fine-tune driver shared by the classifier and the regressor
+    (reference: dbn/models.py:290-382 and the NumPy specialisation :385-559)."""
+
+    _head = None  # 'softmax' | 'linear'
+
+    def __init__(self, hidden_layers_structure=[100, 100], activation_function='sigmoid',
+                 optimization_algorithm='sgd', learning_rate=1e-3, learning_rate_rbm=1e-3, n_iter_backprop=100,
+                 l2_regularization=1.0, n_epochs_rbm=10, contrastive_divergence_iter=1, batch_size=32, dropout_p=0,
+                 verbose=True, precision='auto', rng='philox'):
+        self.hidden_layers_structure = hidden_layers_structure
+        self.activation_function = activation_function
+        self.optimization_algorithm = optimization_algorithm
+        self.learning_rate = learning_rate
+        self.learning_rate_rbm = learning_rate_rbm
+        self.n_iter_backprop = n_iter_backprop
+        self.l2_regularization = l2_regularization
+        self.n_epochs_rbm = n_epochs_rbm
+        self.contrastive_divergence_iter = contrastive_divergence_iter
+        self.batch_size = batch_size
+        self.dropout_p = dropout_p
+        self.verbose = verbose
+        self.precision = precision
+        self.rng = rng
+        self.unsupervised_dbn_class = UnsupervisedDBN
+        self.unsupervised_dbn = UnsupervisedDBN(
+            hidden_layers_structure=hidden_layers_structure, activation_function=activation_function,
+            optimization_algorithm=optimization_algorithm, learning_rate_rbm=learning_rate_rbm,
+            n_epochs_rbm=n_epochs_rbm, contrastive_divergence_iter=contrastive_divergence_iter,
+            batch_size=batch_size, verbose=verbose, precision=precision, rng=rng)
+        self.p = 1 - self.dropout_p
+
+    # ---- public API (dbn/models.py:327-362) ----
+    def fit(self, X, y=None, pre_train=True):
+        Xd = _to_device_f32(X)
+        if pre_train:
+            self.unsupervised_dbn._fit_device(Xd)
+        self._fine_tuning(Xd, np.asarray(y))
+        return self
+
+    def pre_train(self, X):
+        self.unsupervised_dbn.fit(X)
+        return self
+
+    def transform(self, *args):
+        return self.unsupervised_dbn.transform(*args)
+
+    def predict(self, X):
+        X = np.asarray(X)
+        if X.ndim == 1:
+            X = X[None, :]
+        return self._forward(_to_device_f32(X)).double().cpu().numpy()
+
+    def _compute_output_units_matrix(self, matrix_visible_units):
+        """Head outputs for already-transformed features (dbn/models.py:607-615, :705-711)."""
+        A = np.asarray(matrix_visible_units, dtype=np.float64)
+        Z = A @ self.W.T + self.b[None, :]
+        if self._head == 'softmax':
+            Ez = np.exp(Z - Z.max(axis=1, keepdims=True))
+            return Ez / Ez.sum(axis=1, keepdims=True)
+        return Z
+
+    # ---- device plumbing ----
+    def _ft_precision(self):
+        rbms = self.unsupervised_dbn.rbm_layers
+        widths = [rbms[0].n_visible_units] + [r.n_hidden_units for r in rbms]
+        return E.resolve_precision(self.precision, min(widths), min(widths), self.batch_size)
+
+    def _device_mlp(self, precision):
+        dev = _device()
+        layers = [E.DeviceRbm(r.W, r.b, r.c, r.activation_function, precision, dev)
+                  for r in self.unsupervised_dbn.rbm_layers]
+        return E.DeviceMlp(layers, self.W, self.b, self.unsupervised_dbn.activation_function, self._head,
+                           precision, dev)
+
+    def _forward(self, Xd):
+        return self._device_mlp(self._ft_precision()).forward(Xd)
+
+    def _fine_tuning(self, Xd, _labels):
+        """Head init, 1/p pre-scale, SGD, p post-scale (dbn/models.py:517-551)."""
+        rbms = self.unsupervised_dbn.rbm_layers
+        self.num_classes = self._determine_num_output_neurons(_labels)
+        h_last = rbms[-1].n_hidden_units
+        self.W = np.random.randn(self.num_classes, h_last) / np.sqrt(h_last)
+        self.b = np.random.randn(self.num_classes) / np.sqrt(h_last)
+        labels = np.asarray(self._transform_labels_to_network_format(_labels), dtype=np.float64)
+        if labels.ndim == 1:
+            labels = labels[:, None]
+        if self.unsupervised_dbn.optimization_algorithm != 'sgd':
+            raise ValueError("Invalid optimization algorithm.")
+        mlp = self._device_mlp(self._ft_precision())
+        for layer in mlp.layers:
+            layer.scale_hidden(1.0 / self.p)
+        if self.verbose:
+            print("[START] Fine tuning step:")
+        cb = None
+        if self.verbose:
+            cb = lambda it, err: print(">> Epoch %d finished \tANN training loss %f" % (it, err))
+        mlp.fit(Xd, _to_device_f32(labels), self.n_iter_backprop, self.batch_size, self.learning_rate,
+                self.l2_regularization, self.dropout_p, _draw_seed(), rng_mode=self.rng, verbose=cb)
+        for layer in mlp.layers:
+            layer.scale_hidden(self.p)
+        for rbm, layer in zip(rbms, mlp.layers):
+            rbm.W, _b, rbm.c = layer.export()   # rbm.b is not touched by backprop (dbn/models.py:454-460)
+        self.W, self.b = mlp.export_head()
+        if self.verbose:
+            print("[END] Fine tuning step")
+
+
+class SupervisedDBNClassification(AbstractSupervisedDBN, ClassifierMixin):
+    """DBN + softmax classifier (reference: dbn/models.py:562-680)."""
+
+    _head = 'softmax'
+
+    def _transform_labels_to_network_format(self, labels):
+        """One-hot rows with a first-appearance label->index map (dbn/models.py:568-584)."""
+        self.label_to_idx_map, self.idx_to_label_map = {}, {}
+        onehot = np.zeros((len(labels), self.num_classes))
+        for i, label in enumerate(labels):
+            if label not in self.label_to_idx_map:
+                j = len(self.label_to_idx_map)
+                self.label_to_idx_map[label] = j
+                self.idx_to_label_map[j] = label
+            onehot[i, self.label_to_idx_map[label]] = 1
+        return onehot
+
+    def _transform_network_format_to_labels(self, indexes):
+        return [self.idx_to_label_map[i] for i in indexes]
+
+    def _determine_num_output_neurons(self, labels):
+        return len(np.unique(labels))
+
+    def predict_proba(self, X):
+        """Class probabilities (n_samples, n_classes) (dbn/models.py:628-634)."""
+        return super(SupervisedDBNClassification, self).predict(X)
+
+    def predict_proba_dict(self, X):
+        """One {label: probability} dict per sample (dbn/models.py:636-658)."""
+        probs = self.predict_proba(X)
+        return [{self.idx_to_label_map[j]: row[j] for j in range(probs.shape[1])} for row in probs]
+
+    def predict(self, X):
+        """List of original labels (dbn/models.py:660-663)."""
+        return self._transform_network_format_to_labels(np.argmax(self.predict_proba(X), axis=1))
+
+
+class SupervisedDBNRegression(AbstractSupervisedDBN, RegressorMixin):
+    """DBN + linear regression head (reference: dbn/models.py:683-741)."""
+
+    _head = 'linear'
+
+    def _transform_labels_to_network_format(self, labels):
+        return labels
+
+    def _determine_num_output_neurons(self, labels):
+        return 1 if np.ndim(labels) == 1 else np.shape(labels)[1]

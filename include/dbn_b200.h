@@ -1,0 +1,292 @@
+/*
+ * dbn_b200.h -- C-ABI of the B200-native CD-k / backprop hot path.
+ *
+ * Drop-in boundary for the training hot path of albertbup/deep-belief-network (reference 1.0.5).
+ * The reference is pure Python; its "backend seam" is the set of methods a backend module
+ * overrides (see dbn/tensorflow/models.py:78-95, :199-236 and the abstract hooks at
+ * dbn/models.py:364-382).  Every entry point below names the reference function(s) it replaces
+ * (paths relative to the reference root).  The Python estimators in
+ * deep-belief-network_b200/models.py are the only callers; INTEGRATION.md shows the ctypes stub
+ * a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no C++/torch types cross the boundary.
+ *   - Every pointer is a DEVICE pointer unless its name ends in `_host`.
+ *   - Matrices are row-major; `ld` is the leading dimension in ELEMENTS.
+ *   - All calls are asynchronous on `stream` (a cudaStream_t passed as void*), never allocate
+ *     device memory and never synchronise, unless stated.  The caller owns every buffer.
+ *   - Return value: 0 = ok, non-zero = error (DBN_ERR_*); dbn_last_error() returns the message of
+ *     the calling thread's last failure.  Nothing throws across the boundary.
+ *   - There is no CPU fallback: on a machine without an sm_100 device every compute call returns
+ *     DBN_ERR_NO_DEVICE.
+ */
+#ifndef DBN_B200_H
+#define DBN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DBN_B200_ABI_VERSION 1
+
+/* ---- status codes ---------------------------------------------------------------------- */
+enum {
+  DBN_OK = 0,
+  DBN_ERR_INVALID_ARG = 1,
+  DBN_ERR_CUDA = 2,
+  DBN_ERR_NO_DEVICE = 3,
+  DBN_ERR_UNSUPPORTED = 4
+};
+
+/* ---- enums ------------------------------------------------------------------------------ */
+/* activation_function strings of the reference: 'sigmoid' / 'relu' (dbn/models.py:57-69;
+ * dbn/activations.py:23-38, :43-58).  IDENTITY is the linear regression head (dbn/models.py:696). */
+enum { DBN_ACT_IDENTITY = 0, DBN_ACT_SIGMOID = 1, DBN_ACT_RELU = 2 };
+
+/* element types of a dbn_mat */
+enum { DBN_F32 = 0, DBN_BF16 = 1 };
+
+/* arithmetic of the contraction: strict FP32 FFMA (1e-5 parity mode) or tcgen05 BF16 with FP32
+ * accumulation in TMEM (2e-3 parity mode). */
+enum { DBN_PREC_FP32 = 0, DBN_PREC_BF16 = 1 };
+
+/* multiplicative term of the activation epilogue: the activation derivative evaluated on the
+ * (post-dropout) activation, dbn/activations.py:38 `a*(1-a)` and :58 `(a>0)`. */
+enum { DBN_MUL_NONE = 0, DBN_MUL_PRIME_SIGMOID = 1, DBN_MUL_PRIME_RELU = 2 };
+
+/* random use in the activation epilogue */
+enum {
+  DBN_RNG_NONE = 0,
+  DBN_RNG_SAMPLE = 1, /* s = (u < p), strict '<'   -- dbn/models.py:155                 */
+  DBN_RNG_MASK = 2    /* a *= Bernoulli(keep_p), no 1/p rescale -- dbn/models.py:401-411 */
+};
+
+/* output head: softmax + cross-entropy (dbn/models.py:594-626) or linear + squared error
+ * (dbn/models.py:696-720) */
+enum { DBN_HEAD_SOFTMAX = 0, DBN_HEAD_LINEAR = 1 };
+
+/* ---- plain structs ------------------------------------------------------------------------ */
+typedef struct dbn_mat {
+  void* ptr;     /* device pointer (may be NULL = absent) */
+  int32_t ld;    /* leading dimension, elements           */
+  int32_t dtype; /* DBN_F32 / DBN_BF16                    */
+} dbn_mat;
+
+/* Counter-based randomness.  Uniforms are Philox4x32-10 with key = seed and counter =
+ * (row0 + m, n / 4, *epoch_ptr + epoch, stream): a draw depends only on the GLOBAL row index of
+ * the sample inside the epoch, the unit index, the epoch and the purpose -- not on the batch
+ * split or the number of GPUs.  u = (x >> 8) * 2^-24, so every uniform is exact in fp32.
+ * If `injected.ptr` is non-NULL the values are read from it instead (fp32, [M, ld]): uniforms for
+ * DBN_RNG_SAMPLE, {0,1} keep-masks for DBN_RNG_MASK.  This is how the parity tests feed the
+ * reference's draws (np.random.random_sample / np.random.binomial) to the kernels. */
+typedef struct dbn_rng {
+  int32_t mode;              /* DBN_RNG_*                         */
+  float keep_p;              /* DBN_RNG_MASK: p = 1 - dropout_p   */
+  uint64_t seed;
+  uint32_t stream;           /* purpose id (Gibbs step / layer)   */
+  uint32_t epoch;            /* added to *epoch_ptr               */
+  const uint32_t* epoch_ptr; /* device counter or NULL            */
+  uint32_t row0;             /* global row index of row m = 0     */
+  uint32_t _pad;
+  dbn_mat injected;
+} dbn_rng;
+
+/* One operand pair of a contraction  acc[m,n] += sign * sum_k A(m,k) * B(n,k).
+ * transX = 0: X is stored [rows = M or N, cols = K] (K contiguous);
+ * transX = 1: X is stored [rows = K, cols = M or N] (M/N contiguous).
+ * row0_X offsets the stored ROW index (slices of an epoch-sized array without pointer math that
+ * would break TMA alignment). */
+typedef struct dbn_operands {
+  dbn_mat A;
+  dbn_mat B;
+  int32_t transA, transB;
+  int32_t K;
+  int32_t row0_A, row0_B;
+  int32_t _pad;
+} dbn_operands;
+
+/* Activation-type epilogue:
+ *     x = acc + bias[n];  a = act(x);  a *= prime(aux[m,n]);  a *= mask;   out = a
+ *     sample = (u < a)
+ * Replaces the element-wise tails of _compute_hidden_units_matrix (dbn/models.py:176-183),
+ * _compute_visible_units_matrix (:195-201), _sample_hidden_units (:148-155), the dropout lines
+ * of _compute_activations (:401-411) and the delta line of _backpropagation (:498-499). */
+typedef struct dbn_act_epilogue {
+  const float* bias; /* [N] or NULL */
+  int32_t act;       /* DBN_ACT_*   */
+  int32_t mul;       /* DBN_MUL_*   */
+  dbn_mat aux;       /* activation a_l for DBN_MUL_PRIME_* */
+  dbn_rng rng;
+  dbn_mat out;       /* value, may be NULL          */
+  dbn_mat out2;      /* second copy (other dtype), may be NULL */
+  dbn_mat sample;    /* {0,1} sample, may be NULL   */
+} dbn_act_epilogue;
+
+/* Update-type epilogue over an (M+augM) x (N+augN) accumulator whose optional extra row / column
+ * hold the contraction with a vector of ones (bias statistics):
+ *     W[m,n]  = decay * W[m,n] + scale * acc[m,n]          (m < M, n < N)
+ *     vecN[n] = vecN[n]        + scale * acc[M,n]          (augM: visible-bias statistics)
+ *     vecM[m] = vecM[m]        + scale * acc[m,N]          (augN: hidden-bias statistics)
+ * or, if `raw.ptr` != NULL, acc is written unmodified to raw [(M+augM), ld] and nothing is updated
+ * (parity tests, multi-GPU all-reduce).
+ * Replaces dbn/models.py:114-119 (RBM accumulate + update) and :445-465 (fine-tune accumulate,
+ * L2 decay and SGD update). */
+typedef struct dbn_update_epilogue {
+  float* W;      /* fp32 master [M, ldw]  */
+  int32_t ldw;
+  int32_t _pad;
+  dbn_mat Wb;    /* bf16 shadow of W (tensor-core operand), may be NULL */
+  float* vecM;   /* [M] or NULL */
+  float* vecN;   /* [N] or NULL */
+  float decay;
+  float scale;
+  dbn_mat raw;   /* fp32, may be NULL */
+} dbn_update_epilogue;
+
+/* ---- library / device ------------------------------------------------------------------- */
+int dbn_abi_version(void);
+const char* dbn_last_error(void);
+/* Number of sm_100 devices visible; 0 on a CPU-only box (no CUDA call fails). */
+int dbn_device_count(void);
+/* Counts kernels launched by this library since load (bench.py's `gpu_launches`). */
+uint64_t dbn_launch_count(void);
+/* sizeof() of the structs above as compiled (0 dbn_mat, 1 dbn_rng, 2 dbn_operands, 3 dbn_act_epilogue,
+ * 4 dbn_update_epilogue, 5 dbn_rbm_step_args, 6 dbn_mlp_step_args): lets a binding check its layout. */
+size_t dbn_struct_size(int which);
+
+/* The uniforms the kernels draw (see dbn_rng) computed on the HOST into out_host[rows*cols]: lets a
+ * caller or a test reproduce the device's Philox stream without a GPU. */
+int dbn_philox_uniforms_host(uint64_t seed, uint32_t stream, uint32_t epoch, uint32_t row0, int rows,
+                             int cols, float* out_host);
+
+/* ---- fused contractions (building blocks of every path-level call) ----------------------- */
+/* acc = ops[0] - ops[1] (n_ops = 1 or 2), M x N output, activation epilogue.
+ * precision = DBN_PREC_FP32: operands fp32, SIMT FFMA kernel.
+ * precision = DBN_PREC_BF16: operands bf16, TMA + tcgen05.mma kernel (ld % 8 == 0, 16B-aligned). */
+int dbn_gemm_act(void* stream, int precision, int M, int N, const dbn_operands* ops, int n_ops,
+                 const dbn_act_epilogue* epi);
+
+/* Same contraction with the update epilogue.  augM / augN (0/1) append the ones row / column:
+ * for DBN_PREC_FP32 they are virtual; for DBN_PREC_BF16 the caller's operand buffers must hold
+ * 1.0 in column M of A-storage / column N of B-storage (see dbn_fill_ones_column). */
+int dbn_gemm_update(void* stream, int precision, int M, int N, int augM, int augN,
+                    const dbn_operands* ops, int n_ops, const dbn_update_epilogue* epi);
+
+/* ---- RBM: BinaryRBM hot path ---------------------------------------------------------------- */
+/* _compute_hidden_units_matrix (dbn/models.py:176-183): out[B,H] = act(X W^T + c). */
+int dbn_rbm_hidden_means(void* stream, int precision, const dbn_mat* X, int row0, int B, int V, int H,
+                         const dbn_mat* W, const float* c, int act, const dbn_mat* out);
+/* _compute_visible_units_matrix (dbn/models.py:195-201): out[B,V] = act(Hm W + b). */
+int dbn_rbm_visible_means(void* stream, int precision, const dbn_mat* Hm, int B, int V, int H,
+                          const dbn_mat* W, const float* b, int act, const dbn_mat* out);
+
+/* Workspace of one CD-k step for a batch of up to Bmax rows (bytes). */
+size_t dbn_rbm_workspace_bytes(int precision, int Bmax, int V, int H);
+/* Zero the workspace and (BF16 mode) write the ones columns the bias statistics ride on.  Call once
+ * after allocating the workspace, before the first dbn_rbm_cd_step. */
+int dbn_rbm_workspace_init(void* stream, int precision, int Bmax, int V, int H, void* workspace);
+
+typedef struct dbn_rbm_step_args {
+  int32_t precision, act;
+  int32_t B, V, H, k;      /* B rows in this mini-batch                              */
+  float lr_over_bs;        /* learning_rate / configured batch_size (models.py:117-119) */
+  int32_t row0;            /* first row of the mini-batch inside X                   */
+  dbn_mat X;               /* [rows, ldx] fp32 (FP32) / bf16 with ones column V (BF16) */
+  float* W;                /* fp32 master (H, ldw) */
+  int32_t ldw, _pad;
+  float* b;                /* (V,) */
+  float* c;                /* (H,) */
+  dbn_mat Wb;              /* bf16 shadow of W (BF16 mode), else NULL               */
+  dbn_rng rng;             /* mode ignored; .injected = U[B, k*H] or NULL; stream = Gibbs step is added */
+  void* workspace;         /* >= dbn_rbm_workspace_bytes */
+  size_t workspace_bytes;
+  /* optional outputs (parity tests): */
+  dbn_mat P0;              /* fp32 [B,H]  hidden means at t=0  (h_0, models.py:140)   */
+  dbn_mat Vk;              /* fp32 [B,V]                                            */
+  dbn_mat Pk;              /* fp32 [B,H]  (h_k, models.py:141)                       */
+  dbn_mat H0s;             /* fp32 [B,H]  first hidden sample (models.py:155)        */
+  dbn_mat raw_delta;       /* fp32 [(H+1), ld>=V+1]: dW | dc column ; db row. If set, W/b/c are NOT updated */
+} dbn_rbm_step_args;
+
+/* One mini-batch of BinaryRBM._stochastic_gradient_descent (dbn/models.py:108-119) ==
+ * batched _contrastive_divergence (:124-146) + parameter update. */
+int dbn_rbm_cd_step(void* stream, const dbn_rbm_step_args* args);
+
+/* One epoch's mini-batch loop (dbn/models.py:108-119 with dbn/utils.py:14-22): rows
+ * [tmpl->row0, tmpl->row0 + n_rows) of tmpl->X in steps of batch_size, last batch short.  The
+ * template's optional outputs must be NULL.  Pure launches: capture it in a CUDA graph. */
+int dbn_rbm_fit_epoch(void* stream, const dbn_rbm_step_args* tmpl, int n_rows, int batch_size);
+
+/* W/b/c update from an (all-reduced) raw delta buffer: W += s*dW, b += s*db, c += s*dc, and
+ * refresh of the bf16 shadow.  raw is [(H+1), ld]. */
+int dbn_rbm_apply_delta(void* stream, int V, int H, float scale, const float* raw, int ld,
+                        float* W, int ldw, float* b, float* c, const dbn_mat* Wb);
+
+/* ---- supervised fine-tune: _backpropagation + SGD update ------------------------------------ */
+#define DBN_MAX_LAYERS 16
+
+typedef struct dbn_mlp_step_args {
+  int32_t precision, act, head;     /* DBN_PREC_*, DBN_ACT_*, DBN_HEAD_*             */
+  int32_t n_layers;                 /* hidden layers L                               */
+  int32_t B, n_in, n_out;           /* rows in this mini-batch, input width, head width */
+  int32_t dims[DBN_MAX_LAYERS];     /* hidden widths H_1..H_L                        */
+  float* W[DBN_MAX_LAYERS];         /* fp32 masters (H_l, ldw[l])                    */
+  int32_t ldw[DBN_MAX_LAYERS];
+  float* c[DBN_MAX_LAYERS];         /* hidden biases                                 */
+  dbn_mat Wb[DBN_MAX_LAYERS];       /* bf16 shadows (BF16 mode)                      */
+  float* Wo; int32_t ldwo, _pad0;   /* head (n_out, ldwo) fp32                       */
+  float* bo;
+  dbn_mat X;  int32_t row0, _pad1;  /* inputs [rows, ld] (fp32 / bf16+ones column)   */
+  const float* Y; int32_t ldy, _pad2; /* targets in network format [rows, ldy] fp32 (one-hot / regression), row0 applies */
+  float lr_over_bs;                 /* learning_rate / batch_size  (models.py:458-465) */
+  float decay;                      /* 1 - lr*l2/N                 (models.py:456-457) */
+  float keep_p;                     /* 1 - dropout_p; 1 = no dropout                 */
+  int32_t _pad3;
+  dbn_rng rng;                      /* dropout: .injected unused here; see masks[]   */
+  dbn_mat masks[DBN_MAX_LAYERS + 1];/* injected keep-masks fp32 (input, H_1..H_L) or NULL ptr -> Philox */
+  void* workspace; size_t workspace_bytes;
+  float* loss_rows;                 /* optional [B]: -log p[label] or sum_t (pred-y)^2 */
+  dbn_mat out;                      /* optional fp32 [B, n_out] head outputs          */
+  dbn_mat raw_grads[DBN_MAX_LAYERS + 1]; /* optional fp32 [(out_l), in_l + 1] raw gradient | bias column; if raw_grads[0].ptr set nothing is updated */
+} dbn_mlp_step_args;
+
+size_t dbn_mlp_workspace_bytes(int precision, int Bmax, int n_in, const int32_t* dims, int n_layers,
+                               int n_out);
+int dbn_mlp_workspace_init(void* stream, int precision, int Bmax, int n_in, const int32_t* dims,
+                           int n_layers, int n_out, void* workspace);
+
+/* One mini-batch of NumPyAbstractSupervisedDBN._stochastic_gradient_descent
+ * (dbn/models.py:439-465) == batched _compute_activations (:394-417) + _backpropagation
+ * (:471-515) + output head (:594-626 / :696-720) + decayed SGD update. */
+int dbn_mlp_train_step(void* stream, const dbn_mlp_step_args* args);
+
+/* One iteration's mini-batch loop (dbn/models.py:439-465). loss_rows (if set) is [n_rows]. */
+int dbn_mlp_fit_epoch(void* stream, const dbn_mlp_step_args* tmpl, int n_rows, int batch_size);
+
+/* ---- small helpers the host loops need -------------------------------------------------------- */
+/* dst[i, :] = src[idx[i], :] with optional dtype conversion and dropout on the input
+ * (permutation + batch_generator of the reference: dbn/models.py:106-107, dbn/utils.py:11-13).
+ * If ones_col >= 0, dst[i, ones_col] = 1 (bias-statistics column for the tensor-core path). */
+int dbn_gather_rows(void* stream, const dbn_mat* src, const int32_t* idx, int n_rows, int n_cols,
+                    const dbn_mat* dst, int ones_col, const dbn_rng* input_dropout);
+/* dst = scale * src (fp32 -> fp32 / bf16) -- the /p and *p rescale of dbn/models.py:533-535, :546-548
+ * and the refresh of bf16 shadows. */
+int dbn_scale_cast(void* stream, const float* src, int lds, int rows, int cols, float scale,
+                   const dbn_mat* dst);
+/* column `col` of a [rows, ld] matrix := 1.0 */
+int dbn_fill_ones_column(void* stream, const dbn_mat* m, int rows, int col);
+/* out[0] += sum_rows sum_cols (A - B)^2 / denom   (reconstruction error, dbn/models.py:212-220) */
+int dbn_sum_sq_diff(void* stream, const dbn_mat* A, const dbn_mat* B, int row0_B, int rows, int cols,
+                    float inv_denom, float* out);
+/* softmax / identity of head scores in place + delta + loss (dbn/models.py:594-626, :696-720).
+ * Y == NULL or delta == NULL: outputs only (predict, dbn/models.py:607-615 / :705-711). */
+int dbn_head_delta(void* stream, int head, float* Z, int ldz, const float* Y, int ldy, int B, int C,
+                   float* delta, int ldd, float* loss_rows);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DBN_B200_H */

@@ -1,0 +1,238 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) against (1) outputs of the unmodified
+reference (tests/golden/) and (2) the float64 oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): probabilities and deltas within 1e-5 relative in
+strict-FP32 mode and 2e-3 in BF16 tensor-core mode; sampled binary states bit-exact given identical
+uniforms (uniforms guard-banded away from p by more than the arithmetic error)."""
+import os
+
+import numpy as np
+import pytest
+
+import gpu_harness as G
+from oracle import dbn_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp32": 1e-5, "bf16": 2e-3}
+BAND = {"fp32": 2e-5, "bf16": 2e-2}
+
+
+def load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name + ".npz"), allow_pickle=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# fused contraction building blocks against NumPy
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("M,N,K,tA,tB", [(70, 50, 33, 0, 0), (64, 64, 64, 0, 1), (130, 257, 96, 1, 1),
+                                         (256, 512, 384, 0, 0), (256, 384, 512, 0, 1), (384, 520, 256, 1, 1),
+                                         (1, 1, 1, 0, 0), (300, 9, 1000, 0, 0)])
+def test_gemm_act_matches_numpy(precision, M, N, K, tA, tB):
+    import ctypes as C
+    import torch
+    from dbn_b200 import _lib as L, engine as E
+    rng = np.random.default_rng(M * 7 + N * 3 + K)
+    A = rng.standard_normal((M, K)).astype(np.float32)
+    B = rng.standard_normal((N, K)).astype(np.float32) / np.sqrt(K)
+    bias = rng.standard_normal(N).astype(np.float32)
+    dt = torch.float32 if precision == "fp32" else torch.bfloat16
+
+    def put(X, trans):
+        X = X.T if trans else X
+        r, c = X.shape
+        ld = c if precision == "fp32" else E.bf16_pitch(c)
+        t = torch.zeros(r, ld, dtype=dt, device="cuda")
+        t[:, :c] = torch.as_tensor(np.ascontiguousarray(X)).cuda().to(dt)
+        return t
+
+    Ad, Bd = put(A, tA), put(B, tB)
+    Aq = Ad[:, :(M if tA else K)].float().cpu().numpy().astype(np.float64)
+    Bq = Bd[:, :(N if tB else K)].float().cpu().numpy().astype(np.float64)
+    Aq = Aq.T if tA else Aq
+    Bq = Bq.T if tB else Bq
+    ref = 1.0 / (1.0 + np.exp(-(Aq @ Bq.T + bias[None, :])))
+    out = torch.zeros(M, N, device="cuda")
+    ops = L.Operands()
+    ops.A, ops.B, ops.transA, ops.transB, ops.K = E.mat(Ad), E.mat(Bd), tA, tB, K
+    epi = L.ActEpilogue()
+    bd = torch.as_tensor(bias).cuda()
+    epi.bias, epi.act = bd.data_ptr(), L.ACT_SIGMOID
+    epi.rng.keep_p = 1.0
+    epi.out = E.mat(out)
+    L.check(G.lib().dbn_gemm_act(E.stream_ptr(), E.PREC_IDS[precision], M, N, C.byref(ops), 1, C.byref(epi)))
+    torch.cuda.synchronize()
+    got = out.double().cpu().numpy()
+    # operands were quantised identically for the reference, so only accumulation order differs
+    assert np.max(np.abs(got - ref)) < 2e-6 * max(1.0, np.sqrt(K) / 8)
+
+
+# ---------------------------------------------------------------------------------------------------
+# CD-k: golden vectors produced by the reference's own _contrastive_divergence
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["cd_step_sigmoid_k1", "cd_step_sigmoid_k4", "cd_step_relu_k1", "cd_step_relu_k10"])
+def test_cd_step_against_reference_golden(golden_dir, name):
+    g = load(golden_dir, name)
+    k, act = int(g["k"]), str(g["act"])
+    res = G.run_cd_step(g["W"], g["b"], g["c"], g["V0"], k, act, "fp32", U=g["U"], raw=True)
+    assert np.max(np.abs(res["P0"] - g["P0"])) < 1e-5
+    # the fixture's uniforms are not guard-banded: make sure no draw sits on the fp32 rounding edge
+    ch = orc.cd_chain(g["W"], g["b"], g["c"], g["V0"], g["U"], k, act)
+    assert G.count_flips(res["H0s"], ch["samples"][0], g["U"][:, 0, :], ch["P0"], 1e-6) == 0
+    assert G.relF(res["dW"], g["dW"]) < 1e-5
+    assert np.max(np.abs(res["db"] - g["db"])) < 1e-5 * max(1.0, np.max(np.abs(g["db"])))
+    assert np.max(np.abs(res["dc"] - g["dc"])) < 1e-5 * max(1.0, np.max(np.abs(g["dc"])))
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("B,V,H,k,act", [(256, 784, 500, 1, "sigmoid"),    # config 2, layer 1
+                                         (96, 500, 2000, 1, "sigmoid"),    # config 2, layer 3, short last batch
+                                         (32, 64, 256, 1, "relu"),         # config 1, layer 1
+                                         (16, 13, 100, 10, "relu"),        # config 4
+                                         (200, 130, 70, 3, "sigmoid")])    # ragged everything
+def test_cd_step_against_oracle(precision, B, V, H, k, act):
+    rng = np.random.default_rng(B + V + H + k)
+    tol, band = TOL[precision], BAND[precision]
+    if act == "sigmoid":
+        W = rng.standard_normal((H, V)) / np.sqrt(V)
+        V0 = (rng.random((B, V)) < 0.13).astype(np.float64)
+    else:
+        W = rng.uniform(-0.2, 0.2, (H, V)) / np.sqrt(V)
+        V0 = (rng.integers(0, 17, (B, V)) / 16.0)
+    b = rng.standard_normal(V) * 0.1
+    c = rng.standard_normal(H) * 0.1
+    if precision == "bf16":  # identical inputs: parameters representable in the operand type
+        import torch
+        W = torch.as_tensor(W).to(torch.bfloat16).double().numpy()
+    U = rng.random((B, k, H), dtype=np.float32)
+    # guard-band the uniforms along the oracle's own chain so every comparison is decided
+    for t in range(k):
+        ch = orc.cd_chain(W, b, c, V0, U.astype(np.float64), k, act)
+        Vt = V0 if t == 0 else orc.visible_means(W, b, ch["samples"][t - 1], act)
+        Pt = orc.hidden_means(W, c, Vt, act)
+        U[:, t, :] = G.guard_band_uniforms(U[:, t, :], Pt, band, rng)
+    U64 = U.astype(np.float64)
+    lr_over_bs = 0.01 / 256
+    res = G.run_cd_step(W, b, c, V0, k, act, precision, U=U, raw=True)
+    dW, db, dc, ch = orc.cd_deltas(W, b, c, V0, U64, k, act)
+    scale = max(1.0, float(np.max(np.abs(ch["P0"]))))
+    assert np.max(np.abs(res["P0"] - ch["P0"])) < tol * scale
+    assert np.array_equal(res["H0s"], ch["samples"][0]), "sampled hidden states must be bit-exact"
+    assert np.max(np.abs(res["Vk"] - ch["Vk"])) < tol * max(1.0, float(np.max(np.abs(ch["Vk"])))) * (1 if k == 1 else 10)
+    assert np.max(np.abs(res["Pk"] - ch["Pk"])) < tol * scale * (1 if k == 1 else 10)
+    # dW is a difference of two like-sized products: norm-wise relative error, halves checked too
+    pos = ch["P0"].T @ V0
+    assert np.linalg.norm(res["dW"] - dW) < tol * np.linalg.norm(pos) * (1 if k == 1 else 10)
+    assert np.max(np.abs(res["db"] - db)) < tol * B * (1 if k == 1 else 10)
+    assert np.max(np.abs(res["dc"] - dc)) < tol * B * scale * (1 if k == 1 else 10)
+    # in-place update path (dbn/models.py:117-119)
+    res2 = G.run_cd_step(W, b, c, V0, k, act, precision, U=U, raw=False, lr_over_bs=lr_over_bs)
+    W2, b2, c2 = W.copy(), b.copy(), c.copy()
+    orc.cd_step(W2, b2, c2, V0, U64, k, act, 0.01, 256)
+    assert G.relF(res2["W"] - W, W2 - W) < 10 * tol + 1e-3 * (precision == "bf16") or np.linalg.norm(W2 - W) < 1e-9
+    assert np.max(np.abs(res2["W"] - W2)) < 1e-6
+    assert np.max(np.abs(res2["b"] - b2)) < 1e-6 and np.max(np.abs(res2["c"] - c2)) < 1e-6
+    if precision == "bf16":
+        import torch
+        assert np.array_equal(res2["Wb"], torch.as_tensor(res2["W"]).float().to(torch.bfloat16).double().numpy())
+
+
+def test_philox_samples_match_host_stream():
+    """In-kernel Philox mode: regenerate the uniforms on the host and require bit-exact samples."""
+    rng = np.random.default_rng(5)
+    B, V, H = 128, 96, 160
+    W = rng.standard_normal((H, V)) / np.sqrt(V)
+    b = rng.standard_normal(V) * 0.1
+    c = rng.standard_normal(H) * 0.1
+    V0 = (rng.random((B, V)) < 0.3).astype(np.float64)
+    seed, epoch, row0 = 0xABCDEF0123456789, 3, 4096
+    res = G.run_cd_step(W, b, c, V0, 1, "sigmoid", "fp32", seed=seed, raw=True, epoch=epoch, row0=row0)
+    U = G.philox_uniforms(seed, 0, epoch, row0, B, H).astype(np.float64)
+    P0 = orc.hidden_means(W, c, V0, "sigmoid")
+    assert G.count_flips(res["H0s"], (U < P0).astype(np.float64), U, P0, 2e-5) == 0
+    assert abs(res["H0s"].mean() - P0.mean()) < 0.02
+
+
+def test_gpu_count_invariance_of_one_step():
+    """Rows split over 'ranks' (each with its global row0) give the same samples and, summed, the same
+    raw deltas as the whole mini-batch: what data-parallel training relies on."""
+    rng = np.random.default_rng(9)
+    B, V, H = 256, 200, 136
+    W = rng.standard_normal((H, V)) / np.sqrt(V)
+    b = rng.standard_normal(V) * 0.1
+    c = rng.standard_normal(H) * 0.1
+    V0 = (rng.random((B, V)) < 0.4).astype(np.float64)
+    full = G.run_cd_step(W, b, c, V0, 1, "sigmoid", "fp32", seed=11, raw=True, row0=512)
+    parts = [G.run_cd_step(W, b, c, V0[s:s + 64], 1, "sigmoid", "fp32", seed=11, raw=True, row0=512 + s)
+             for s in range(0, B, 64)]
+    assert np.array_equal(np.concatenate([p["H0s"] for p in parts]), full["H0s"])
+    assert G.relF(sum(p["dW"] for p in parts), full["dW"]) < 1e-5
+    assert np.max(np.abs(sum(p["dc"] for p in parts) - full["dc"])) < 1e-3
+
+
+# ---------------------------------------------------------------------------------------------------
+# fine-tune step
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["ft_step_clf_sigmoid", "ft_step_clf_relu_dropout", "ft_step_reg_relu",
+                                  "ft_step_reg_sigmoid_dropout"])
+def test_finetune_step_against_reference_golden(golden_dir, name):
+    g = load(golden_dir, name)
+    L_ = len(g["hs"])
+    layers = [(g["W%d" % l], g["c%d" % l]) for l in range(L_)]
+    head = "softmax" if str(g["kind"]) == "clf" else "linear"
+    dropout = float(g["dropout"])
+    masks = [g["M%d" % j] for j in range(L_ + 1)] if dropout > 0 else None
+    res = G.run_mlp_step(layers, g["Wo"], g["bo"], g["X"], g["Y"], str(g["act"]), head, "fp32", masks=masks,
+                         keep_p=1 - dropout, raw=True)
+    assert np.max(np.abs(res["out"] - g["out"])) < 1e-5
+    for l in range(L_ + 1):
+        gW, gb = res["grads"][l]
+        assert np.linalg.norm(gW - g["gW%d" % l]) < 1e-5 * max(1.0, np.linalg.norm(g["gW%d" % l]))
+        assert np.max(np.abs(gb - g["gb%d" % l])) < 1e-5 * max(1.0, np.max(np.abs(g["gb%d" % l])))
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("B,n_in,hs,n_out,act,head,dropout", [
+    (256, 784, (500, 500, 2000), 10, "sigmoid", "softmax", 0.0),   # config 3
+    (32, 64, (256, 256), 10, "relu", "softmax", 0.2),             # config 1
+    (16, 13, (100,), 1, "relu", "linear", 0.0),                   # config 4
+    (75, 130, (200, 136), 3, "sigmoid", "linear", 0.5)])
+def test_finetune_step_against_oracle(precision, B, n_in, hs, n_out, act, head, dropout):
+    import torch
+    rng = np.random.default_rng(B + n_in + n_out)
+    tol = TOL[precision]
+    q = (lambda a: torch.as_tensor(a).to(torch.bfloat16).double().numpy()) if precision == "bf16" else (lambda a: a)
+    layers, prev = [], n_in
+    for h in hs:
+        layers.append((q(rng.standard_normal((h, prev)) / np.sqrt(prev)), rng.standard_normal(h) * 0.1))
+        prev = h
+    Wo = rng.standard_normal((n_out, prev)) / np.sqrt(prev)
+    bo = rng.standard_normal(n_out) * 0.1
+    X = q(rng.integers(0, 17, (B, n_in)) / 16.0)
+    Y = np.eye(n_out)[rng.integers(0, n_out, B)] if head == "softmax" else rng.standard_normal((B, n_out))
+    masks = None
+    if dropout > 0:
+        masks = [(rng.random((B, w)) < 1 - dropout).astype(np.float64) for w in [n_in] + list(hs)]
+    res = G.run_mlp_step(layers, Wo, bo, X, Y, act, head, precision, masks=masks, keep_p=1 - dropout, raw=True)
+    gW, gb, out, acts, deltas = orc.finetune_grads(layers, Wo, bo, X, Y, masks, act, head)
+    assert np.max(np.abs(res["out"] - out)) < tol * max(1.0, np.max(np.abs(out)))
+    assert np.max(np.abs(res["loss"] - orc.sample_loss(out, Y, head).sum(axis=1) / (n_out if head == "softmax" else 1))) \
+        < tol * 10 * max(1.0, np.max(np.abs(out)) ** 2)
+    for l in range(len(hs) + 1):
+        rW, rb = res["grads"][l]
+        scale = np.linalg.norm(np.abs(deltas[l]).T @ np.abs(acts[l]))  # size of the terms being summed
+        assert np.linalg.norm(rW - gW[l]) < tol * max(scale, 1e-12) * 3, "layer %d weight gradient" % l
+        assert np.max(np.abs(rb - gb[l])) < tol * max(1.0, np.abs(deltas[l]).sum(axis=0).max()) * 3
+    # decayed SGD update (dbn/models.py:454-465)
+    lr, l2, N, bs = 0.1, 1.0, 1000, max(B, 16)
+    res2 = G.run_mlp_step(layers, Wo, bo, X, Y, act, head, precision, masks=masks, keep_p=1 - dropout,
+                          lr_over_bs=lr / bs, decay=1 - lr * l2 / N)
+    lay = [[W.copy(), c.copy()] for (W, c) in layers]
+    Wo2, bo2, _ = orc.finetune_step(lay, Wo.copy(), bo.copy(), X, Y, masks, act, head, lr, l2, N, bs)
+    for l in range(len(hs)):
+        step = np.linalg.norm(lay[l][0] - layers[l][0])
+        assert np.linalg.norm(res2["layers"][l][0] - lay[l][0]) < max(3 * tol * step, 2e-6 * np.linalg.norm(lay[l][0]))
+        assert np.max(np.abs(res2["layers"][l][1] - lay[l][1])) < 1e-4
+    assert np.linalg.norm(res2["Wo"] - Wo2) < 3 * tol * np.linalg.norm(Wo2 - Wo) + 1e-6
+    assert np.max(np.abs(res2["bo"] - bo2)) < 1e-4

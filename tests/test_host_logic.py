@@ -1,0 +1,108 @@
+"""Host-side logic of the estimators that needs no GPU: constructor defaults mirror the reference,
+parameter init consumes the np.random stream exactly like the reference (checked against golden
+weights via n_epochs=0 semantics), label maps, error behaviour, sklearn plumbing, pickle."""
+import inspect
+import os
+import pickle
+
+import numpy as np
+import pytest
+
+import dbn_b200
+from dbn_b200 import engine as E
+from dbn_b200.models import BinaryRBM, SupervisedDBNClassification, SupervisedDBNRegression, UnsupervisedDBN
+from oracle import dbn_oracle as orc
+
+
+def test_constructor_defaults_match_reference():
+    # reference: dbn/models.py:31-39, :228-236, :296-309
+    d = {k: v.default for k, v in inspect.signature(BinaryRBM.__init__).parameters.items() if k != "self"}
+    assert d["n_hidden_units"] == 100 and d["activation_function"] == "sigmoid"
+    assert d["optimization_algorithm"] == "sgd" and d["learning_rate"] == 1e-3 and d["n_epochs"] == 10
+    assert d["contrastive_divergence_iter"] == 1 and d["batch_size"] == 32 and d["verbose"] is True
+    d = {k: v.default for k, v in inspect.signature(UnsupervisedDBN.__init__).parameters.items() if k != "self"}
+    assert d["hidden_layers_structure"] == [100, 100] and d["learning_rate_rbm"] == 1e-3 and d["n_epochs_rbm"] == 10
+    d = {k: v.default for k, v in inspect.signature(SupervisedDBNClassification.__init__).parameters.items()
+         if k != "self"}
+    assert d["learning_rate"] == 1e-3 and d["n_iter_backprop"] == 100 and d["l2_regularization"] == 1.0
+    assert d["dropout_p"] == 0 and d["batch_size"] == 32
+
+
+def test_param_init_consumes_rng_like_reference():
+    for act in ("sigmoid", "relu"):
+        np.random.seed(5)
+        m = BinaryRBM(n_hidden_units=7, activation_function=act)
+        m._init_params(12)
+        np.random.seed(5)
+        W, b, c = orc.rbm_init(12, 7, act)   # oracle is pinned to the reference (test_oracle_golden)
+        assert np.array_equal(m.W, W) and np.array_equal(m.b, b) and np.array_equal(m.c, c)
+        assert m.n_visible_units == 12
+
+
+def test_invalid_activation_and_optimizer_raise_value_error():
+    with pytest.raises(ValueError, match="Invalid activation function."):
+        BinaryRBM(activation_function="tanh")._init_params(4)
+    with pytest.raises(ValueError, match="Invalid precision."):
+        E.resolve_precision("fp8", 10, 10, 10)
+
+
+def test_epoch_order_is_the_double_shuffle():
+    np.random.seed(3)
+    o = E.epoch_order(10)
+    np.random.seed(3)
+    a = np.random.permutation(10)
+    b = np.random.permutation(10)
+    X = np.arange(10)
+    assert np.array_equal(X[o], X[a][b])
+
+
+def test_label_maps_first_appearance_order():
+    clf = SupervisedDBNClassification(hidden_layers_structure=[4])
+    y = np.array([7, 3, 7, 5, 3])
+    clf.num_classes = clf._determine_num_output_neurons(y)
+    Y = clf._transform_labels_to_network_format(y)
+    assert clf.label_to_idx_map == {7: 0, 3: 1, 5: 2} and clf.idx_to_label_map == {0: 7, 1: 3, 2: 5}
+    assert Y.tolist() == [[1, 0, 0], [0, 1, 0], [1, 0, 0], [0, 0, 1], [0, 1, 0]]
+    assert clf._transform_network_format_to_labels([2, 0]) == [5, 7]
+    l2i, _ = orc.label_maps(y)
+    assert l2i == clf.label_to_idx_map
+
+
+def test_regression_output_width():
+    r = SupervisedDBNRegression(hidden_layers_structure=[4])
+    assert r._determine_num_output_neurons(np.zeros(5)) == 1
+    assert r._determine_num_output_neurons(np.zeros((5, 3))) == 3
+
+
+def test_sklearn_params_and_clone():
+    from sklearn.base import clone
+    m = SupervisedDBNClassification(hidden_layers_structure=[8, 4], dropout_p=0.2, batch_size=16)
+    p = m.get_params()
+    assert p["hidden_layers_structure"] == [8, 4] and p["dropout_p"] == 0.2
+    c = clone(m)
+    assert c.batch_size == 16 and c.p == pytest.approx(0.8)
+    assert c.unsupervised_dbn.hidden_layers_structure == [8, 4]
+
+
+def test_pickle_roundtrip_of_fitted_attributes(tmp_path):
+    m = BinaryRBM(n_hidden_units=3, verbose=False)
+    np.random.seed(0)
+    m._init_params(5)
+    path = os.path.join(tmp_path, "rbm.pkl")
+    m.save(path)
+    m2 = BinaryRBM.load(path)
+    assert np.array_equal(m.W, m2.W) and m2._activation_function_class.name == "sigmoid"
+    assert isinstance(pickle.loads(pickle.dumps(m)), BinaryRBM)
+
+
+def test_precision_auto_policy():
+    assert E.resolve_precision("auto", 784, 500, 256) == "bf16"
+    assert E.resolve_precision("auto", 64, 256, 32) == "fp32"
+    assert E.resolve_precision("auto", 13, 100, 16) == "fp32"
+    assert E.resolve_precision("fp32", 4096, 4096, 32768) == "fp32"
+    assert E.bf16_pitch(784) == 792 and E.bf16_pitch(500) == 504 and E.bf16_pitch(4096) == 4104
+
+
+def test_public_names():
+    assert set(dbn_b200.__all__) == {"BinaryRBM", "UnsupervisedDBN", "SupervisedDBNClassification",
+                                     "SupervisedDBNRegression"}
