@@ -1,7 +1,436 @@
+// umma_gemm.cuh -- BF16 contraction on the 5th-generation tensor cores (sm_100a):
+// TMA (cp.async.bulk.tensor) -> 128B-swizzled shared memory -> tcgen05.mma with FP32 accumulation
+// in TMEM -> tcgen05.ld -> fused epilogue (epilogue.cuh).
+//
+//   acc[m,n] = sum_k A0(m,k) B0(n,k)  -  sum_k A1(m,k) B1(n,k)        (second pair optional, negated
+//                                                                        by the instruction descriptor)
+//
+// Every operand may be K-major (stored [M|N, K]) or MN-major (stored [K, M|N]); the same bf16 W
+// shadow therefore serves v->h (K-major B), h->v (MN-major B) and, with the activations, the
+// dW = P0^T V0 - Pk^T Vk contraction (MN-major A and B) without any transposed copy in HBM.
+//
+// Kernel shape: persistent, one CTA per SM, 6 warps:
+//   warp 0    TMA producer (one elected lane)         -- ring of S smem stages, mbarrier full/empty
+//   warp 1    TMEM allocator + tcgen05.mma issuer      -- one elected lane issues 4 MMAs (K=16) per stage
+//   warps 2-5 epilogue (one TMEM lane quarter each)    -- double-buffered accumulator (2 x BN columns)
+// Tile 128 x BN x 64 (BN in {64,128,256}); ragged edges are zero-filled by TMA and masked in the
+// epilogue, so no operand is ever padded to a tile multiple.
 #pragma once
+#include <cuda.h>
+
 #include "epilogue.cuh"
+
 namespace dbn {
-inline bool umma_gemm_supported(int, int, const dbn_operands*, int) { return false; }
-inline int umma_gemm_act(cudaStream_t, int, int, const dbn_operands*, int, const dbn_act_epilogue&) { return DBN_ERR_UNSUPPORTED; }
-inline int umma_gemm_update(cudaStream_t, int, int, int, int, const dbn_operands*, int, const dbn_update_epilogue&) { return DBN_ERR_UNSUPPORTED; }
+
+constexpr int UG_BM = 128;
+constexpr int UG_BK = 64;   // bf16 elements per stage along K = one 128-byte swizzle row
+constexpr int UG_UK = 16;   // K of one tcgen05.mma.kind::f16
+constexpr int UG_THREADS = 192;
+constexpr int UG_SMEM_BUDGET = 196608;  // operand ring; + 1 KB barriers/alignment  (<= 227 KB per CTA)
+constexpr int UG_A_BYTES = UG_BM * UG_BK * 2;
+
+struct UmmaGemmParams {
+  CUtensorMap tmA[2];
+  CUtensorMap tmB[2];
+  int n_ops;
+  int K[2];
+  int transA[2], transB[2];
+  int rowA[2], rowB[2];
+  int M, N;  // accumulator extent (incl. the ones row / column)
+  int tiles_m, tiles_n, group_m;
+};
+
+// ---- PTX wrappers -------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Bounded wait: a protocol bug traps (kernel error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!done && spin > (1u << 24)) {
+      printf("dbn_b200: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x, bar,
+             parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t v[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor (sm_100 "version 1"), 128-byte swizzle.
+//   bits [0,14) start address >> 4 | [16,30) leading byte offset >> 4 | [32,46) stride byte offset >> 4
+//   bits [46,48) = 1 (Blackwell) | [61,64) layout type = 2 (SWIZZLE_128B)
+// K-major operand  : rows of 128 B (64 bf16 along K); 8-row groups 1024 B apart (SBO); LBO unused (=1).
+// MN-major operand : rows of 128 B (64 bf16 along M/N) indexed by k; 8-k groups 1024 B apart (SBO);
+//                    64-wide M/N chunks 8192 B apart (LBO).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// Instruction descriptor of tcgen05.mma.kind::f16: D = F32, A = B = BF16.
+//   [4,6) D format (1 = F32) | [7,10) A format (1 = BF16) | [10,13) B format | 13 negate A | 15 A MN-major
+//   16 B MN-major | [17,23) N >> 3 | [24,29) M >> 4
+__device__ __forceinline__ uint32_t make_idesc(int bn, int transA, int transB, int negA) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)negA << 13) | ((uint32_t)transA << 15) |
+         ((uint32_t)transB << 16) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(UG_BM >> 4) << 24);
+}
+
+__device__ __forceinline__ void tile_coords(const UmmaGemmParams& p, int tile, int& mb, int& nb) {
+  // grouped raster: `group_m` row-blocks x all column-blocks form an L2-resident super-tile
+  const int per_group = p.group_m * p.tiles_n;
+  const int g = tile / per_group;
+  const int first_m = g * p.group_m;
+  const int gm = min(p.group_m, p.tiles_m - first_m);
+  const int r = tile - g * per_group;
+  mb = first_m + r % gm;
+  nb = r / gm;
+}
+
+template <int BN, class Epi>
+__global__ void __launch_bounds__(UG_THREADS, 1)
+umma_gemm_kernel(const __grid_constant__ UmmaGemmParams p, const __grid_constant__ Epi epi_args, int coreM, int coreN,
+                 int augM, int augN) {
+  constexpr int B_BYTES = BN * UG_BK * 2;
+  constexpr int STAGE_BYTES = UG_A_BYTES + B_BYTES;
+  constexpr int STAGES = UG_SMEM_BUDGET / STAGE_BYTES;
+  constexpr int TMEM_COLS = 2 * BN;
+  static_assert(STAGES >= 3, "pipeline too shallow");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  // bars[0..S) full, [S..2S) empty, [2S..2S+2) tmem_full, [2S+2..2S+4) tmem_empty
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t bar_base = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles = p.tiles_m * p.tiles_n;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 4);  // one arrive per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        int mb, nb;
+        tile_coords(p, tile, mb, nb);
+        for (int pass = 0; pass < p.n_ops; ++pass) {
+          const int nkb = (p.K[pass] + UG_BK - 1) / UG_BK;
+          for (int kb = 0; kb < nkb; ++kb, ++it) {
+            const int s = it % STAGES;
+            const uint32_t ph = (it / STAGES) & 1u;
+            mbar_wait(empty_bar(s), ph ^ 1u);
+            mbar_expect_tx(full_bar(s), STAGE_BYTES);
+            const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + UG_A_BYTES;
+            if (!p.transA[pass]) {
+              tma_load_2d(sa, &p.tmA[pass], full_bar(s), kb * UG_BK, p.rowA[pass] + mb * UG_BM);
+            } else {
+#pragma unroll
+              for (int ch = 0; ch < UG_BM / 64; ++ch)
+                tma_load_2d(sa + ch * 8192, &p.tmA[pass], full_bar(s), mb * UG_BM + ch * 64, p.rowA[pass] + kb * UG_BK);
+            }
+            if (!p.transB[pass]) {
+              tma_load_2d(sb, &p.tmB[pass], full_bar(s), kb * UG_BK, p.rowB[pass] + nb * BN);
+            } else {
+#pragma unroll
+              for (int ch = 0; ch < BN / 64; ++ch)
+                tma_load_2d(sb + ch * 8192, &p.tmB[pass], full_bar(s), nb * BN + ch * 64, p.rowB[pass] + kb * UG_BK);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      uint32_t it = 0, tl = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
+        const int as = tl & 1;
+        const uint32_t aph = (tl >> 1) & 1u;
+        mbar_wait(tempty_bar(as), aph ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+        uint32_t accumulate = 0;
+        for (int pass = 0; pass < p.n_ops; ++pass) {
+          const int nkb = (p.K[pass] + UG_BK - 1) / UG_BK;
+          const int tA = p.transA[pass], tB = p.transB[pass];
+          const uint32_t idesc = make_idesc(BN, tA, tB, pass == 1);
+          for (int kb = 0; kb < nkb; ++kb, ++it) {
+            const int s = it % STAGES;
+            const uint32_t ph = (it / STAGES) & 1u;
+            mbar_wait(full_bar(s), ph);
+            tc_fence_after();
+            const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + UG_A_BYTES;
+#pragma unroll
+            for (int k4 = 0; k4 < UG_BK / UG_UK; ++k4) {
+              const uint64_t da = tA ? make_smem_desc(sa + k4 * 2048, 8192, 1024) : make_smem_desc(sa + k4 * 32, 16, 1024);
+              const uint64_t db = tB ? make_smem_desc(sb + k4 * 2048, 8192, 1024) : make_smem_desc(sb + k4 * 32, 16, 1024);
+              tc_mma_bf16(tmem_d, da, db, idesc, accumulate);
+              accumulate = 1;
+            }
+            tc_commit(empty_bar(s));  // frees the smem stage once these MMAs have read it
+          }
+        }
+        tc_commit(tfull_bar(as));  // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ===================== epilogue warps (TMEM lane quarter = warp % 4) =====================
+    const int q = warp & 3;
+    uint32_t epoch = 0;
+    if constexpr (!Epi::kIsUpdate) epoch = epi_args.e.rng.epoch + (epi_args.e.rng.epoch_ptr ? *epi_args.e.rng.epoch_ptr : 0u);
+    uint32_t tl = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tl) {
+      int mb, nb;
+      tile_coords(p, tile, mb, nb);
+      const int as = tl & 1;
+      const uint32_t aph = (tl >> 1) & 1u;
+      mbar_wait(tfull_bar(as), aph);
+      tc_fence_after();
+      const int m = mb * UG_BM + q * 32 + lane;
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
+#pragma unroll 1
+      for (int ch = 0; ch < BN / 32; ++ch) {
+        const int n0 = nb * BN + ch * 32;
+        if (n0 >= p.N) break;  // warp-uniform
+        uint32_t v[32];
+        tc_ld32(trow + ch * 32, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float acc[4] = {__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                          __uint_as_float(v[4 * j + 3])};
+          epi_args.apply(epoch, m, n0 + 4 * j, acc, coreM, coreN, augM, augN);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(as));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+  }
+}
+
+struct UmmaActEpi {
+  static constexpr bool kIsUpdate = false;
+  dbn_act_epilogue e;
+  __device__ __forceinline__ void apply(uint32_t epoch, int m, int n4, const float acc[4], int M, int N, int, int) const {
+    act_epilogue_quad(e, epoch, m, n4, acc, M, N);
+  }
+};
+struct UmmaUpdEpi {
+  static constexpr bool kIsUpdate = true;
+  dbn_update_epilogue e;
+  __device__ __forceinline__ void apply(uint32_t, int m, int n4, const float acc[4], int M, int N, int augM, int augN) const {
+    upd_epilogue_quad(e, m, n4, acc, M, N, augM, augN);
+  }
+};
+
+// ---- host side ---------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+// Tensor map over a bf16 operand stored [rows, ld].  valid_cols / valid_rows bound the region TMA may
+// read; everything outside is zero-filled, which is what makes ragged shapes and short batches exact.
+inline int make_operand_map(CUtensorMap* map, const dbn_mat& X, uint64_t valid_cols, uint64_t valid_rows, uint32_t box_rows) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return fail(DBN_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available%s%s");
+  cuuint64_t gdim[2] = {valid_cols, valid_rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)X.ld * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, X.ptr, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[64];
+    snprintf(buf, sizeof(buf), "%d", (int)r);
+    return fail(DBN_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %s%s", buf);
+  }
+  return DBN_OK;
+}
+
+inline bool umma_operand_ok(const dbn_mat& X) {
+  return X.ptr != nullptr && X.dtype == DBN_BF16 && (X.ld % 8) == 0 && (reinterpret_cast<uintptr_t>(X.ptr) % 16) == 0;
+}
+
+// The tensor-core path takes bf16 operands with 16-byte aligned rows and is worth its 128 x BN tiles
+// only for contractions that fill at least part of one; everything else runs on the FP32 SIMT kernel.
+inline bool umma_gemm_supported(int M, int N, const dbn_operands* ops, int n_ops) {
+  for (int i = 0; i < n_ops; ++i) {
+    if (!umma_operand_ok(ops[i].A) || !umma_operand_ok(ops[i].B)) return false;
+    if (ops[i].K < 32) return false;
+  }
+  return M >= 64 && N >= 32;
+}
+
+inline int umma_num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int BN, class Epi>
+inline int umma_launch(cudaStream_t st, UmmaGemmParams& p, const Epi& epi, int coreM, int coreN, int augM, int augN) {
+  constexpr int B_BYTES = BN * UG_BK * 2;
+  constexpr int STAGE_BYTES = UG_A_BYTES + B_BYTES;
+  constexpr int STAGES = UG_SMEM_BUDGET / STAGE_BYTES;
+  constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + (2 * STAGES + 4) * 8 + 16;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DBN_CUDA_OK(cudaFuncSetAttribute(umma_gemm_kernel<BN, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    attr_set = true;
+  }
+  p.tiles_m = ceil_div(p.M, UG_BM);
+  p.tiles_n = ceil_div(p.N, BN);
+  // super-tile of group_m row blocks: A slab (group_m * 128 rows) + all of B stay L2-resident
+  p.group_m = std::max(1, std::min(p.tiles_m, 16));
+  const int n_tiles = p.tiles_m * p.tiles_n;
+  const int grid = std::min(n_tiles, umma_num_sms());
+  umma_gemm_kernel<BN, Epi><<<grid, UG_THREADS, SMEM, st>>>(p, epi, coreM, coreN, augM, augN);
+  DBN_LAUNCH_CHECK();
+  return DBN_OK;
+}
+
+template <class Epi>
+inline int umma_gemm_run(cudaStream_t st, int M, int N, int augM, int augN, const dbn_operands* ops, int n_ops,
+                         const Epi& epi) {
+  UmmaGemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.n_ops = n_ops;
+  p.M = M + augM;
+  p.N = N + augN;
+  // tile width: widest tile that still gives every SM work
+  const int sms = umma_num_sms();
+  const int tm = ceil_div(p.M, UG_BM);
+  int bn = 64;
+  if (tm * ceil_div(p.N, 256) >= sms) bn = 256;
+  else if (tm * ceil_div(p.N, 128) >= sms) bn = 128;
+  for (int i = 0; i < n_ops; ++i) {
+    const dbn_operands& o = ops[i];
+    p.K[i] = o.K;
+    p.transA[i] = o.transA; p.transB[i] = o.transB;
+    p.rowA[i] = o.row0_A; p.rowB[i] = o.row0_B;
+    if (!o.transA) DBN_TRY(make_operand_map(&p.tmA[i], o.A, o.K, (uint64_t)o.row0_A + p.M, UG_BM));
+    else           DBN_TRY(make_operand_map(&p.tmA[i], o.A, p.M, (uint64_t)o.row0_A + o.K, 64));
+    if (!o.transB) DBN_TRY(make_operand_map(&p.tmB[i], o.B, o.K, (uint64_t)o.row0_B + p.N, bn));
+    else           DBN_TRY(make_operand_map(&p.tmB[i], o.B, p.N, (uint64_t)o.row0_B + o.K, 64));
+  }
+  if (bn == 256) return umma_launch<256, Epi>(st, p, epi, M, N, augM, augN);
+  if (bn == 128) return umma_launch<128, Epi>(st, p, epi, M, N, augM, augN);
+  return umma_launch<64, Epi>(st, p, epi, M, N, augM, augN);
+}
+
+inline int umma_gemm_act(cudaStream_t st, int M, int N, const dbn_operands* ops, int n_ops, const dbn_act_epilogue& e) {
+  UmmaActEpi epi;
+  epi.e = e;
+  return umma_gemm_run(st, M, N, 0, 0, ops, n_ops, epi);
+}
+inline int umma_gemm_update(cudaStream_t st, int M, int N, int augM, int augN, const dbn_operands* ops, int n_ops,
+                            const dbn_update_epilogue& e) {
+  UmmaUpdEpi epi;
+  epi.e = e;
+  return umma_gemm_run(st, M, N, augM, augN, ops, n_ops, epi);
+}
+
+}  // namespace dbn

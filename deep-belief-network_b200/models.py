@@ -104,7 +104,7 @@ class BinaryRBM(BaseEstimator, TransformerMixin, BaseModel):
         if self.optimization_algorithm != 'sgd':
             raise ValueError("Invalid optimization algorithm.")
         layer = self._device_layer()
-        seed = _draw_seed()
+        seed = _draw_seed() if self.rng == 'philox' else 0   # 'numpy' replays the reference stream untouched
         cb = None
         if self.verbose:
             cb = lambda it, err: print(">> Epoch %d finished \tRBM Reconstruction error %f" % (it, err))
@@ -292,7 +292,8 @@ class AbstractSupervisedDBN(BaseEstimator, BaseModel):
         if self.verbose:
             cb = lambda it, err: print(">> Epoch %d finished \tANN training loss %f" % (it, err))
         mlp.fit(Xd, _to_device_f32(labels), self.n_iter_backprop, self.batch_size, self.learning_rate,
-                self.l2_regularization, self.dropout_p, _draw_seed(), rng_mode=self.rng, verbose=cb)
+                self.l2_regularization, self.dropout_p, _draw_seed() if self.rng == 'philox' else 0,
+                rng_mode=self.rng, verbose=cb)
         for layer in mlp.layers:
             layer.scale_hidden(self.p)
         for rbm, layer in zip(rbms, mlp.layers):

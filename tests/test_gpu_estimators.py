@@ -28,7 +28,6 @@ def test_rbm_fit_replays_reference(golden_dir, name):
     m = BinaryRBM(n_hidden_units=h, activation_function=str(g["act"]), learning_rate=float(g["lr"]),
                   n_epochs=epochs, contrastive_divergence_iter=k, batch_size=bs, verbose=False,
                   precision="fp32", rng="numpy")
-    # the Philox seed draw must not disturb the replayed stream: it is taken after init
     m.fit(g["X"])
     assert m.W.dtype == np.float64 and m.W.shape == (h, v)
     assert np.max(np.abs(m.W - g["W"])) < 5e-5
@@ -70,16 +69,15 @@ def test_supervised_fit_replays_reference(golden_dir, name):
         assert P.shape == g["pred"].shape and np.max(np.abs(P - g["pred"])) < 5e-4
 
 
-def test_seed_replay_is_exact_through_philox_seed_draw():
-    """The stream positions consumed by the fit must be the reference's plus exactly the two
-    randint draws of the Philox key (documented deviation)."""
+def test_numpy_replay_consumes_exactly_the_reference_stream():
+    """rng='numpy': the fit consumes the reference's draws and nothing else (the Philox key is only
+    drawn in rng='philox' mode, after parameter init)."""
     X = (np.random.default_rng(0).random((40, 12)) < 0.4).astype(np.float32)
     np.random.seed(3)
     BinaryRBM(n_hidden_units=5, n_epochs=2, batch_size=8, verbose=False, precision="fp32", rng="numpy").fit(X)
     after_ours = np.random.random_sample()
     np.random.seed(3)
     orc.rbm_init(12, 5, "sigmoid")
-    np.random.randint(0, 2 ** 31 - 1); np.random.randint(0, 2 ** 31 - 1)
     for _ in range(2):
         np.random.permutation(40); np.random.permutation(40); np.random.random_sample((40, 5))
     assert after_ours == np.random.random_sample()

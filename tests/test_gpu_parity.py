@@ -131,8 +131,9 @@ def test_cd_step_against_oracle(precision, B, V, H, k, act):
     W2, b2, c2 = W.copy(), b.copy(), c.copy()
     orc.cd_step(W2, b2, c2, V0, U64, k, act, 0.01, 256)
     assert G.relF(res2["W"] - W, W2 - W) < 10 * tol + 1e-3 * (precision == "bf16") or np.linalg.norm(W2 - W) < 1e-9
-    assert np.max(np.abs(res2["W"] - W2)) < 1e-6
-    assert np.max(np.abs(res2["b"] - b2)) < 1e-6 and np.max(np.abs(res2["c"] - c2)) < 1e-6
+    step = 3 * tol * lr_over_bs * B          # size of one update x relative tolerance
+    assert np.max(np.abs(res2["W"] - W2)) < 1e-6 + step
+    assert np.max(np.abs(res2["b"] - b2)) < 1e-6 + step and np.max(np.abs(res2["c"] - c2)) < 1e-6 + step
     if precision == "bf16":
         import torch
         assert np.array_equal(res2["Wb"], torch.as_tensor(res2["W"]).float().to(torch.bfloat16).double().numpy())
@@ -216,14 +217,19 @@ def test_finetune_step_against_oracle(precision, B, n_in, hs, n_out, act, head, 
         masks = [(rng.random((B, w)) < 1 - dropout).astype(np.float64) for w in [n_in] + list(hs)]
     res = G.run_mlp_step(layers, Wo, bo, X, Y, act, head, precision, masks=masks, keep_p=1 - dropout, raw=True)
     gW, gb, out, acts, deltas = orc.finetune_grads(layers, Wo, bo, X, Y, masks, act, head)
-    assert np.max(np.abs(res["out"] - out)) < tol * max(1.0, np.max(np.abs(out)))
+    # The tolerance is per contraction; a forward/backward chain through L layers + head compounds it.
+    # BF16 + relu additionally flips the gate (a > 0) of units whose pre-activation is within the bf16
+    # rounding of 0 -- the backprop analogue of a sample flip -- so that case gets twice the margin.
+    depth = len(hs) + 1
+    gate = 2.0 if (precision == "bf16" and act == "relu") else 1.0
+    assert np.max(np.abs(res["out"] - out)) < depth * tol * max(1.0, np.max(np.abs(out)))
     assert np.max(np.abs(res["loss"] - orc.sample_loss(out, Y, head).sum(axis=1) / (n_out if head == "softmax" else 1))) \
         < tol * 10 * max(1.0, np.max(np.abs(out)) ** 2)
     for l in range(len(hs) + 1):
         rW, rb = res["grads"][l]
         scale = np.linalg.norm(np.abs(deltas[l]).T @ np.abs(acts[l]))  # size of the terms being summed
-        assert np.linalg.norm(rW - gW[l]) < tol * max(scale, 1e-12) * 3, "layer %d weight gradient" % l
-        assert np.max(np.abs(rb - gb[l])) < tol * max(1.0, np.abs(deltas[l]).sum(axis=0).max()) * 3
+        assert np.linalg.norm(rW - gW[l]) < tol * max(scale, 1e-12) * depth * gate, "layer %d weight gradient" % l
+        assert np.max(np.abs(rb - gb[l])) < tol * max(1.0, np.abs(deltas[l]).sum(axis=0).max()) * depth * gate
     # decayed SGD update (dbn/models.py:454-465)
     lr, l2, N, bs = 0.1, 1.0, 1000, max(B, 16)
     res2 = G.run_mlp_step(layers, Wo, bo, X, Y, act, head, precision, masks=masks, keep_p=1 - dropout,
@@ -232,7 +238,7 @@ def test_finetune_step_against_oracle(precision, B, n_in, hs, n_out, act, head, 
     Wo2, bo2, _ = orc.finetune_step(lay, Wo.copy(), bo.copy(), X, Y, masks, act, head, lr, l2, N, bs)
     for l in range(len(hs)):
         step = np.linalg.norm(lay[l][0] - layers[l][0])
-        assert np.linalg.norm(res2["layers"][l][0] - lay[l][0]) < max(3 * tol * step, 2e-6 * np.linalg.norm(lay[l][0]))
+        assert np.linalg.norm(res2["layers"][l][0] - lay[l][0]) < max(depth * gate * tol * step, 2e-6 * np.linalg.norm(lay[l][0]))
         assert np.max(np.abs(res2["layers"][l][1] - lay[l][1])) < 1e-4
-    assert np.linalg.norm(res2["Wo"] - Wo2) < 3 * tol * np.linalg.norm(Wo2 - Wo) + 1e-6
+    assert np.linalg.norm(res2["Wo"] - Wo2) < depth * gate * tol * np.linalg.norm(Wo2 - Wo) + 1e-6
     assert np.max(np.abs(res2["bo"] - bo2)) < 1e-4
