@@ -20,6 +20,7 @@ PREC_FP32, PREC_BF16 = 0, 1
 MUL_NONE, MUL_PRIME_SIGMOID, MUL_PRIME_RELU = 0, 1, 2
 RNG_NONE, RNG_SAMPLE, RNG_MASK = 0, 1, 2
 HEAD_SOFTMAX, HEAD_LINEAR = 0, 1
+STEP_SKIP_UPDATE = 1
 MAX_LAYERS = 16
 
 
@@ -51,7 +52,7 @@ class UpdateEpilogue(C.Structure):
 class RbmStepArgs(C.Structure):
     _fields_ = [("precision", C.c_int32), ("act", C.c_int32), ("B", C.c_int32), ("V", C.c_int32),
                 ("H", C.c_int32), ("k", C.c_int32), ("lr_over_bs", C.c_float), ("row0", C.c_int32),
-                ("X", Mat), ("W", C.c_void_p), ("ldw", C.c_int32), ("_pad", C.c_int32), ("b", C.c_void_p),
+                ("X", Mat), ("W", C.c_void_p), ("ldw", C.c_int32), ("flags", C.c_int32), ("b", C.c_void_p),
                 ("c", C.c_void_p), ("Wb", Mat), ("rng", Rng), ("workspace", C.c_void_p),
                 ("workspace_bytes", C.c_size_t), ("P0", Mat), ("Vk", Mat), ("Pk", Mat), ("H0s", Mat),
                 ("raw_delta", Mat)]
@@ -92,8 +93,9 @@ SYMBOLS = {
     "dbn_rbm_workspace_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "dbn_rbm_cd_step": (C.c_int, [C.c_void_p, _P(RbmStepArgs)]),
     "dbn_rbm_fit_epoch": (C.c_int, [C.c_void_p, _P(RbmStepArgs), C.c_int, C.c_int]),
-    "dbn_rbm_apply_delta": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_int, C.c_void_p,
-                                      C.c_int, C.c_void_p, C.c_void_p, _P(Mat)]),
+    "dbn_rbm_delta_rows": (C.c_int, [C.c_void_p, _P(RbmStepArgs), C.c_int, C.c_int]),
+    "dbn_rbm_apply_delta": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p,
+                                      C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, _P(Mat)]),
     "dbn_mlp_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, _P(C.c_int32), C.c_int, C.c_int]),
     "dbn_mlp_workspace_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, _P(C.c_int32), C.c_int, C.c_int,
                                          C.c_void_p]),

@@ -257,6 +257,7 @@ int dbn_rbm_cd_step(void* stream, const dbn_rbm_step_args* a) {
     e.bias = a->c; e.act = a->act; e.out = ws.Pk; e.out2 = a->Pk;
     DBN_TRY(dbn_gemm_act(stream, a->precision, B, H, &o, 1, &e));
   }
+  if (a->flags & DBN_STEP_SKIP_UPDATE) return DBN_OK;
   {  // dW = h_0^T v_0 - h_k^T v_k, db, dc (dbn/models.py:142-144) + update (:117-119)
     dbn_operands o[2];
     o[0] = make_ops(ws.P0, 1, 0, a->X, 1, a->row0, B);
@@ -283,13 +284,33 @@ int dbn_rbm_fit_epoch(void* stream, const dbn_rbm_step_args* tmpl, int n_rows, i
   return DBN_OK;
 }
 
-int dbn_rbm_apply_delta(void* stream, int V, int H, float scale, const float* raw, int ld, float* W, int ldw,
-                        float* b, float* c, const dbn_mat* Wb) {
+int dbn_rbm_delta_rows(void* stream, const dbn_rbm_step_args* a, int h0, int h1) {
+  DBN_NEED_DEVICE();
+  DBN_REQUIRE(a && a->raw_delta.ptr, "needs args with a raw_delta buffer");
+  DBN_REQUIRE(h0 >= 0 && h0 < h1 && h1 <= a->H && (h0 % 8) == 0, "bad row range");
+  if (a->k == 0) return DBN_OK;
+  const bool tc = a->precision == DBN_PREC_BF16;
+  RbmWorkspace ws;
+  rbm_ws_layout(a->precision, a->B, a->V, a->H, static_cast<char*>(a->workspace), &ws);
+  dbn_operands o[2];
+  o[0] = make_ops(offset_cols(ws.P0, h0), 1, 0, a->X, 1, a->row0, a->B);
+  o[1] = make_ops(offset_cols(ws.Pk, h0), 1, 0, ws.Vt, 1, 0, a->B);
+  dbn_update_epilogue u = blank_upd();
+  u.raw = a->raw_delta;
+  u.raw.ptr = static_cast<char*>(u.raw.ptr) + (size_t)h0 * u.raw.ld * sizeof(float);
+  (void)tc;
+  return dbn_gemm_update(stream, a->precision, h1 - h0, a->V, h1 == a->H ? 1 : 0, 1, o, 2, &u);
+}
+
+int dbn_rbm_apply_delta(void* stream, int V, int H, int h0, int h1, float scale, const float* raw, int ld, float* W,
+                        int ldw, float* b, float* c, const dbn_mat* Wb) {
   DBN_NEED_DEVICE();
   DBN_REQUIRE(raw && W && b && c, "null argument");
-  const long total = (long)(H + 1) * ((V + 4) / 4);
+  DBN_REQUIRE(h0 >= 0 && h0 < h1 && h1 <= H, "bad row range");
+  const int rows = (h1 - h0) + (h1 == H ? 1 : 0);
+  const long total = (long)rows * ((V + 4) / 4);
   const int blocks = (int)std::min<long>((total + 255) / 256, 148L * 8);
-  apply_delta_kernel<<<blocks, 256, 0, as_stream(stream)>>>(V, H, scale, raw, ld, W, ldw, b, c,
+  apply_delta_kernel<<<blocks, 256, 0, as_stream(stream)>>>(V, H, h0, rows, scale, raw, ld, W, ldw, b, c,
                                                            Wb ? *Wb : null_mat());
   DBN_LAUNCH_CHECK();
   return DBN_OK;

@@ -134,16 +134,18 @@ __global__ void __launch_bounds__(128) head_delta_kernel(int head, float* Z, int
   if (train && loss_rows != nullptr && lane == 0) loss_rows[warp] = loss;
 }
 
-// W += s * dW, b += s * db (last row), c += s * dc (last column) from a raw [(H+1), ld] delta buffer.
-__global__ void __launch_bounds__(256) apply_delta_kernel(int V, int H, float scale, const float* __restrict__ raw,
-                                                          int ld, float* W, int ldw, float* b, float* c, dbn_mat Wb) {
+// W += s * dW, b += s * db (row H), c += s * dc (last column) from a raw [(H+1), ld] delta buffer,
+// rows [h0, h0 + rows).
+__global__ void __launch_bounds__(256) apply_delta_kernel(int V, int H, int h0, int rows, float scale,
+                                                          const float* __restrict__ raw, int ld, float* W, int ldw,
+                                                          float* b, float* c, dbn_mat Wb) {
   const int quads = (V + 1 + 3) >> 2;
-  const long total = (long)(H + 1) * quads;
+  const long total = (long)rows * quads;
   dbn_update_epilogue e;
   e.W = W; e.ldw = ldw; e.Wb = Wb; e.vecM = c; e.vecN = b; e.decay = 1.0f; e.scale = scale;
   e.raw.ptr = nullptr; e.raw.ld = 0; e.raw.dtype = DBN_F32;
   for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
-    const int m = (int)(t / quads), n4 = (int)(t % quads) << 2;
+    const int m = h0 + (int)(t / quads), n4 = (int)(t % quads) << 2;
     float acc[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[j] = (n4 + j <= V) ? raw[(size_t)m * ld + n4 + j] : 0.0f;

@@ -400,12 +400,19 @@ inline int umma_gemm_run(cudaStream_t st, int M, int N, int augM, int augN, cons
   p.n_ops = n_ops;
   p.M = M + augM;
   p.N = N + augN;
-  // tile width: widest tile that still gives every SM work
+  // Tile width by a two-term cost model: waves over the SMs x cycles per K=16 slice of one tile, the
+  // latter = max(tcgen05 floor 128*BN/256, smem operand read (128 + BN) * 32 B / 128 B/clk).
   const int sms = umma_num_sms();
   const int tm = ceil_div(p.M, UG_BM);
   int bn = 64;
-  if (tm * ceil_div(p.N, 256) >= sms) bn = 256;
-  else if (tm * ceil_div(p.N, 128) >= sms) bn = 128;
+  long best = -1;
+  for (int cand : {256, 128, 64}) {
+    const long tiles = (long)tm * ceil_div(p.N, cand);
+    const long waves = (tiles + sms - 1) / sms;
+    const long cyc = std::max(cand / 2, 32 + cand / 4);
+    const long cost = waves * cyc;
+    if (best < 0 || cost < best) { best = cost; bn = cand; }
+  }
   for (int i = 0; i < n_ops; ++i) {
     const dbn_operands& o = ops[i];
     p.K[i] = o.K;

@@ -66,6 +66,17 @@ def require_device():
     return lib
 
 
+def dp_context():
+    """(rank, world) when the process runs under torch.distributed with DBN_B200_DATA_PARALLEL=1,
+    else None.  One process per GPU (torchrun); replicas-only configs simply leave the flag unset."""
+    if os.environ.get("DBN_B200_DATA_PARALLEL", "0") != "1":
+        return None
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return None
+    return dist.get_rank(), dist.get_world_size()
+
+
 def epoch_order(n):
     """Composed double shuffle of the reference (dbn/models.py:106 then dbn/utils.py:12), drawn
     from the global np.random stream in the same order."""
@@ -160,10 +171,11 @@ class DeviceRbm:
         L.check(self.lib.dbn_rbm_visible_means(stream_ptr(), self.prec, mat(Hop), n, self.V, self.H,
                                                self.w_operand(), ptr(self.b), self.act, mat(out)))
 
-    def transform(self, Xd):
+    def transform(self, Xd, out=None):
         """fp32 [N,V] device tensor -> fp32 [N,H] hidden means (BinaryRBM.transform, :77-86)."""
         n = int(Xd.shape[0])
-        out = torch.empty(n, self.H, dtype=torch.float32, device=self.device)
+        if out is None:
+            out = torch.empty(n, self.H, dtype=torch.float32, device=self.device)
         for s in range(0, n, _CHUNK):
             m = min(_CHUNK, n - s)
             xs = Xd[s:s + m]
@@ -221,84 +233,147 @@ class DeviceRbm:
             return
         if dp is not None and dp[1] > 1:
             return self._fit_dp(Xd, n_epochs, batch_size, k, lr, seed, verbose, dp)
-        feeder = _IndexFeeder(n, self.device)
-        Xp = self.stage(Xd)  # allocates the epoch array; contents rewritten every epoch
-        ws = self.make_workspace(min(batch_size, n))
-        epoch_ctr = torch.zeros(1, dtype=torch.int32, device=self.device)
-        U = None
-        if rng_mode == "numpy":
-            U = torch.empty(n, k * self.H, dtype=torch.float32, device=self.device)
-        args = self._step_args(Xp, k, lr / batch_size, ws, seed, epoch_ctr, U)
-        # warm-up launch of every kernel of the step outside graph capture (lr = 0: parameters unchanged)
-        warm = self._step_args(Xp, k, 0.0, ws, seed, epoch_ctr, U)
-        warm.B, warm.row0 = min(batch_size, n), 0
-        self.stage(Xd[:warm.B], out=Xp[:warm.B])
-        if U is not None:
-            U[:warm.B].fill_(0.5)
-        L.check(self.lib.dbn_rbm_cd_step(stream_ptr(), C.byref(warm)))
-        torch.cuda.current_stream().synchronize()
-
-        graph = None
-
-        def run_epoch():
-            self.stage(Xd, idx=feeder.dev, out=Xp)
-            L.check(self.lib.dbn_rbm_fit_epoch(stream_ptr(), C.byref(args), n, batch_size))
-            epoch_ctr.add_(1)
-
+        runner = RbmEpochRunner(self, Xd, batch_size, k, lr, seed, rng_mode)
         for epoch in range(1, n_epochs + 1):
-            feeder.push(epoch_order(n))
-            if U is not None:  # replay the reference's uniform stream
-                U.copy_(torch.from_numpy(np.random.random_sample((n, k * self.H)).astype(np.float32)))
-            if _use_graphs():
-                if graph is None:
-                    graph = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(graph):
-                        run_epoch()
-                graph.replay()
-            else:
-                run_epoch()
+            runner.run()
             if verbose is not None:
                 verbose(epoch, self.reconstruction_error(Xd))
         torch.cuda.current_stream().synchronize()
 
     def _fit_dp(self, Xd, n_epochs, batch_size, k, lr, seed, verbose, dp):
-        """Data-parallel epoch loop: every rank holds the full dataset and the same shuffle; rank r
-        computes rows [r*bl, (r+1)*bl) of each global mini-batch (bl = batch_size / world), writes
-        raw deltas, sum-all-reduces them (NCCL) and applies the identical update.  Philox counters use
-        the global row index, so samples are independent of the GPU count."""
-        import torch.distributed as dist
-        rank, world = dp
-        n = int(Xd.shape[0])
-        if batch_size % world != 0 or n % batch_size != 0:
-            raise ValueError("data-parallel fit needs batch_size % world == 0 and N % batch_size == 0")
-        bl = batch_size // world
-        steps = n // batch_size
-        n_local = steps * bl
-        feeder = _IndexFeeder(n_local, self.device)
-        Xp = self.stage(Xd[:n_local])
-        ws = self.make_workspace(bl)
-        epoch_ctr = torch.zeros(1, dtype=torch.int32, device=self.device)
-        ldr = (self.V + 1 + 3) // 4 * 4
-        raw = torch.zeros(self.H + 1, ldr, dtype=torch.float32, device=self.device)
-        args = self._step_args(Xp, k, lr / batch_size, ws, seed, epoch_ctr)
-        args.raw_delta = mat(raw)
-        args.B = bl
+        runner = DpRbmEpochRunner(self, Xd, batch_size, k, lr, seed, dp)
         for epoch in range(1, n_epochs + 1):
-            order = epoch_order(n).reshape(steps, world, bl)[:, rank, :].reshape(-1)
-            feeder.push(order)
-            self.stage(Xd, idx=feeder.dev, out=Xp)
-            for s in range(steps):
-                args.row0 = s * bl
-                args.rng.row0 = s * batch_size + rank * bl
-                L.check(self.lib.dbn_rbm_cd_step(stream_ptr(), C.byref(args)))
-                dist.all_reduce(raw, op=dist.ReduceOp.SUM)
-                L.check(self.lib.dbn_rbm_apply_delta(stream_ptr(), self.V, self.H, lr / batch_size, ptr(raw), ldr,
-                                                     ptr(self.W), self.V, ptr(self.b), ptr(self.c),
-                                                     C.byref(mat(self.Wb))))
-            epoch_ctr.add_(1)
+            runner.run()
             if verbose is not None:
                 verbose(epoch, self.reconstruction_error(Xd))
         torch.cuda.current_stream().synchronize()
+
+
+class RbmEpochRunner:
+    """One RBM layer + one dataset prepared for epoch-at-a-time training: the epoch array, the
+    workspace, the warm-up launch and the captured CUDA graph (gather + every mini-batch CD-k step).
+    `run()` = one epoch of dbn/models.py:105-119."""
+
+    def __init__(self, layer, Xd, batch_size, k, lr, seed, rng_mode="philox"):
+        self.layer, self.Xd = layer, Xd
+        self.n, self.bs, self.k = int(Xd.shape[0]), int(batch_size), int(k)
+        n, lib = self.n, layer.lib
+        self.feeder = _IndexFeeder(n, layer.device)
+        self.Xp = layer.stage(Xd)  # allocates the epoch array; rewritten by the gather every epoch
+        self.ws = layer.make_workspace(min(self.bs, n))
+        self.epoch_ctr = torch.zeros(1, dtype=torch.int32, device=layer.device)
+        self.U = None
+        if rng_mode == "numpy":
+            self.U = torch.empty(n, k * layer.H, dtype=torch.float32, device=layer.device)
+        self.args = layer._step_args(self.Xp, k, lr / batch_size, self.ws, seed, self.epoch_ctr, self.U)
+        # warm-up launch of every kernel of the step outside graph capture (lr = 0: parameters unchanged)
+        warm = layer._step_args(self.Xp, k, 0.0, self.ws, seed, self.epoch_ctr, self.U)
+        warm.B, warm.row0 = min(self.bs, n), 0
+        if self.U is not None:
+            self.U[:warm.B].fill_(0.5)
+        L.check(lib.dbn_rbm_cd_step(stream_ptr(), C.byref(warm)))
+        torch.cuda.current_stream().synchronize()
+        self.graph = None
+        self.launches_per_epoch = 0
+        self.epochs_run = 0
+
+    def _enqueue(self):
+        lib = self.layer.lib
+        self.layer.stage(self.Xd, idx=self.feeder.dev, out=self.Xp)
+        L.check(lib.dbn_rbm_fit_epoch(stream_ptr(), C.byref(self.args), self.n, self.bs))
+        self.epoch_ctr.add_(1)
+
+    def run(self, order=None):
+        """One epoch.  `order` defaults to the reference's double shuffle drawn from np.random."""
+        layer = self.layer
+        self.feeder.push(epoch_order(self.n) if order is None else order)
+        if self.U is not None:  # replay the reference's uniform stream (SURVEY A.3)
+            self.U.copy_(torch.from_numpy(np.random.random_sample((self.n, self.k * layer.H)).astype(np.float32)))
+        if _use_graphs():
+            if self.graph is None:
+                before = layer.lib.dbn_launch_count()
+                self.graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph):
+                    self._enqueue()
+                self.launches_per_epoch = int(layer.lib.dbn_launch_count() - before)
+            self.graph.replay()
+        else:
+            before = layer.lib.dbn_launch_count()
+            self._enqueue()
+            self.launches_per_epoch = int(layer.lib.dbn_launch_count() - before)
+        self.epochs_run += 1
+
+
+class DpRbmEpochRunner:
+    """Data-parallel epoch of one RBM layer (BASELINE.json config 5).
+
+    Every rank holds the dataset and draws the same shuffle; rank r computes rows
+    [r*bl, (r+1)*bl) of each global mini-batch (bl = batch_size / world).  Philox counters are keyed
+    by the GLOBAL row index, so the sampled states do not depend on the GPU count.  Per step the
+    Gibbs chain runs locally, then the raw delta [(H+1) x (V+1)] = dW | dc ; db is produced in
+    `n_chunks` row blocks: block i is all-reduced (NCCL sum over NVLink) and applied on a side stream
+    while the tensor cores produce block i+1, so only the last block's exchange is exposed."""
+
+    def __init__(self, layer, Xd, batch_size, k, lr, seed, dp, n_chunks=8):
+        import torch.distributed as dist
+        self.dist = dist
+        self.layer, self.Xd = layer, Xd
+        self.rank, self.world = dp
+        self.n, self.bs, self.k = int(Xd.shape[0]), int(batch_size), int(k)
+        if self.bs % self.world != 0 or self.n % self.bs != 0:
+            raise ValueError("data-parallel fit needs batch_size % world == 0 and N % batch_size == 0")
+        self.bl = self.bs // self.world
+        self.steps = self.n // self.bs
+        self.n_local = self.steps * self.bl
+        self.scale = lr / batch_size
+        H, V = layer.H, layer.V
+        self.feeder = _IndexFeeder(self.n_local, layer.device)
+        self.Xp = layer.stage(Xd[:self.n_local])
+        self.ws = layer.make_workspace(self.bl)
+        self.epoch_ctr = torch.zeros(1, dtype=torch.int32, device=layer.device)
+        self.ldr = (V + 1 + 3) // 4 * 4
+        self.raw = torch.zeros(H + 1, self.ldr, dtype=torch.float32, device=layer.device)
+        self.args = layer._step_args(self.Xp, k, self.scale, self.ws, seed, self.epoch_ctr)
+        self.args.raw_delta = mat(self.raw)
+        self.args.B = self.bl
+        self.args.flags = L.STEP_SKIP_UPDATE
+        rows = max(128, (H + n_chunks - 1) // n_chunks // 128 * 128)
+        self.chunks = [(h0, min(H, h0 + rows)) for h0 in range(0, H, rows)]
+        self.comm = torch.cuda.Stream(device=layer.device)
+        self.ev_ready = [torch.cuda.Event() for _ in self.chunks]
+        self.ev_done = torch.cuda.Event()
+        self.launches_per_epoch = 0
+
+    def step(self, s):
+        layer, lib, a = self.layer, self.layer.lib, self.args
+        a.row0 = s * self.bl
+        a.rng.row0 = s * self.bs + self.rank * self.bl
+        main = torch.cuda.current_stream()
+        L.check(lib.dbn_rbm_cd_step(stream_ptr(), C.byref(a)))          # Gibbs chain only
+        for i, (h0, h1) in enumerate(self.chunks):
+            L.check(lib.dbn_rbm_delta_rows(stream_ptr(), C.byref(a), h0, h1))
+            self.ev_ready[i].record(main)
+            with torch.cuda.stream(self.comm):
+                self.comm.wait_event(self.ev_ready[i])
+                blk = self.raw[h0:(h1 + 1 if h1 == layer.H else h1)]
+                self.dist.all_reduce(blk, op=self.dist.ReduceOp.SUM)
+                L.check(lib.dbn_rbm_apply_delta(stream_ptr(), layer.V, layer.H, h0, h1, self.scale, ptr(self.raw),
+                                                self.ldr, ptr(layer.W), layer.V, ptr(layer.b), ptr(layer.c),
+                                                C.byref(mat(layer.Wb))))
+        self.ev_done.record(self.comm)
+        main.wait_event(self.ev_done)
+
+    def run(self, order=None):
+        before = self.layer.lib.dbn_launch_count()
+        if order is None:
+            order = epoch_order(self.n)
+        local = order.reshape(self.steps, self.world, self.bl)[:, self.rank, :].reshape(-1)
+        self.feeder.push(local)
+        self.layer.stage(self.Xd, idx=self.feeder.dev, out=self.Xp)
+        for s in range(self.steps):
+            self.step(s)
+        self.epoch_ctr.add_(1)
+        self.launches_per_epoch = int(self.layer.lib.dbn_launch_count() - before)
 
 
 class DeviceMlp:
@@ -364,56 +439,12 @@ class DeviceMlp:
         n = int(Xd.shape[0])
         if n == 0 or n_iter <= 0:
             return
-        keep_p = 1.0 - dropout_p
-        first = self.layers[0]
-        feeder = _IndexFeeder(n, self.device)
-        Xp = first.stage(Xd)
-        Yp = torch.empty(n, self.n_out, dtype=torch.float32, device=self.device)
-        ws = self.make_workspace(min(batch_size, n))
-        iter_ctr = torch.zeros(1, dtype=torch.int32, device=self.device)
-        loss_rows = torch.zeros(n, dtype=torch.float32, device=self.device)
-        masks = None
-        if rng_mode == "numpy" and dropout_p > 0:
-            masks = [torch.empty(n, w, dtype=torch.float32, device=self.device) for w in [self.n_in] + self.dims]
-        decay = 1.0 - (lr * l2) / n
-        args = self.step_args(Xp, Yp, lr / batch_size, decay, keep_p, ws, seed, iter_ctr, loss_rows, masks)
-        warm = self.step_args(Xp, Yp, 0.0, 1.0, keep_p, ws, seed, iter_ctr, loss_rows, masks)
-        warm.B, warm.row0 = min(batch_size, n), 0
-        first.stage(Xd[:warm.B], out=Xp[:warm.B])
-        Yp[:warm.B].copy_(Yd[:warm.B])
-        if masks is not None:
-            for m in masks:
-                m[:warm.B].fill_(1.0)
-        L.check(self.lib.dbn_mlp_train_step(stream_ptr(), C.byref(warm)))
-        torch.cuda.current_stream().synchronize()
-        graph = None
-
-        def run_iter():
-            first.stage(Xd, idx=feeder.dev, out=Xp)
-            L.check(self.lib.dbn_gather_rows(stream_ptr(), mat(Yd), ptr(feeder.dev), n, self.n_out, mat(Yp), -1, None))
-            L.check(self.lib.dbn_mlp_fit_epoch(stream_ptr(), C.byref(args), n, batch_size))
-            iter_ctr.add_(1)
-
-        widths = [self.n_in] + self.dims
+        runner = MlpIterRunner(self, Xd, Yd, batch_size, lr, l2, dropout_p, seed, rng_mode)
         for it in range(1, n_iter + 1):
-            feeder.push(epoch_order(n))
-            if masks is not None:  # reference draw order: per row, V then H_1.. (dbn/models.py:402, :409)
-                flat = np.random.binomial(1, keep_p, (n, sum(widths))).astype(np.float32)
-                o = 0
-                for m, w in zip(masks, widths):
-                    m.copy_(torch.from_numpy(np.ascontiguousarray(flat[:, o:o + w])))
-                    o += w
-            if _use_graphs():
-                if graph is None:
-                    graph = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(graph):
-                        run_iter()
-                graph.replay()
-            else:
-                run_iter()
+            runner.run()
             if verbose is not None:
                 scale = self.n_out if self.head == L.HEAD_SOFTMAX else 1.0  # dbn/models.py:450,468 quirk
-                verbose(it, float(loss_rows.sum().item()) / n * scale)
+                verbose(it, float(runner.loss_rows.sum().item()) / n * scale)
         torch.cuda.current_stream().synchronize()
 
     def forward(self, Xd):
@@ -435,3 +466,65 @@ class DeviceMlp:
             L.check(self.lib.dbn_head_delta(stream_ptr(), self.head, ptr(out), self.n_out, None, 0, n, self.n_out,
                                             None, 0, None))
         return out
+
+
+class MlpIterRunner:
+    """One fine-tune problem prepared for iteration-at-a-time training: gathered inputs / targets,
+    workspace, warm-up launch and the captured CUDA graph of one iteration (dbn/models.py:434-465)."""
+
+    def __init__(self, mlp, Xd, Yd, batch_size, lr, l2, dropout_p, seed, rng_mode="philox"):
+        self.mlp, self.Xd, self.Yd = mlp, Xd, Yd
+        self.n, self.bs = int(Xd.shape[0]), int(batch_size)
+        n, dev, lib = self.n, mlp.device, mlp.lib
+        self.keep_p = 1.0 - dropout_p
+        self.first = mlp.layers[0]
+        self.feeder = _IndexFeeder(n, dev)
+        self.Xp = self.first.stage(Xd)
+        self.Yp = Yd.clone()
+        self.ws = mlp.make_workspace(min(self.bs, n))
+        self.iter_ctr = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.loss_rows = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.widths = [mlp.n_in] + mlp.dims
+        self.masks = None
+        if rng_mode == "numpy" and dropout_p > 0:
+            self.masks = [torch.ones(n, w, dtype=torch.float32, device=dev) for w in self.widths]
+        decay = 1.0 - (lr * l2) / n
+        self.args = mlp.step_args(self.Xp, self.Yp, lr / batch_size, decay, self.keep_p, self.ws, seed, self.iter_ctr,
+                                  self.loss_rows, self.masks)
+        warm = mlp.step_args(self.Xp, self.Yp, 0.0, 1.0, self.keep_p, self.ws, seed, self.iter_ctr, self.loss_rows,
+                             self.masks)
+        warm.B, warm.row0 = min(self.bs, n), 0
+        L.check(lib.dbn_mlp_train_step(stream_ptr(), C.byref(warm)))
+        torch.cuda.current_stream().synchronize()
+        self.graph = None
+        self.launches_per_iter = 0
+
+    def _enqueue(self):
+        lib = self.mlp.lib
+        self.first.stage(self.Xd, idx=self.feeder.dev, out=self.Xp)
+        L.check(lib.dbn_gather_rows(stream_ptr(), mat(self.Yd), ptr(self.feeder.dev), self.n, self.mlp.n_out,
+                                    mat(self.Yp), -1, None))
+        L.check(lib.dbn_mlp_fit_epoch(stream_ptr(), C.byref(self.args), self.n, self.bs))
+        self.iter_ctr.add_(1)
+
+    def run(self, order=None):
+        lib = self.mlp.lib
+        self.feeder.push(epoch_order(self.n) if order is None else order)
+        if self.masks is not None:  # reference draw order: per row, V then H_1.. (dbn/models.py:402, :409)
+            flat = np.random.binomial(1, self.keep_p, (self.n, sum(self.widths))).astype(np.float32)
+            o = 0
+            for m, w in zip(self.masks, self.widths):
+                m.copy_(torch.from_numpy(np.ascontiguousarray(flat[:, o:o + w])))
+                o += w
+        if _use_graphs():
+            if self.graph is None:
+                before = lib.dbn_launch_count()
+                self.graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph):
+                    self._enqueue()
+                self.launches_per_iter = int(lib.dbn_launch_count() - before)
+            self.graph.replay()
+        else:
+            before = lib.dbn_launch_count()
+            self._enqueue()
+            self.launches_per_iter = int(lib.dbn_launch_count() - before)

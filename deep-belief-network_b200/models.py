@@ -115,7 +115,7 @@ class BinaryRBM(BaseEstimator, TransformerMixin, BaseModel):
 
     def fit(self, X):
         """Fit the RBM to X (n_samples, n_features).  Returns self (dbn/models.py:49-75)."""
-        self._fit_device(_to_device_f32(X))
+        self._fit_device(_to_device_f32(X), dp=E.dp_context())
         return self
 
     def transform(self, X):

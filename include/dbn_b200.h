@@ -183,6 +183,9 @@ int dbn_rbm_hidden_means(void* stream, int precision, const dbn_mat* X, int row0
 int dbn_rbm_visible_means(void* stream, int precision, const dbn_mat* Hm, int B, int V, int H,
                           const dbn_mat* W, const float* b, int act, const dbn_mat* out);
 
+/* dbn_rbm_step_args.flags */
+#define DBN_STEP_SKIP_UPDATE 1 /* run the Gibbs chain only; deltas are produced later by dbn_rbm_delta_rows */
+
 /* Workspace of one CD-k step for a batch of up to Bmax rows (bytes). */
 size_t dbn_rbm_workspace_bytes(int precision, int Bmax, int V, int H);
 /* Zero the workspace and (BF16 mode) write the ones columns the bias statistics ride on.  Call once
@@ -196,7 +199,8 @@ typedef struct dbn_rbm_step_args {
   int32_t row0;            /* first row of the mini-batch inside X                   */
   dbn_mat X;               /* [rows, ldx] fp32 (FP32) / bf16 with ones column V (BF16) */
   float* W;                /* fp32 master (H, ldw) */
-  int32_t ldw, _pad;
+  int32_t ldw;
+  int32_t flags;           /* DBN_STEP_* */
   float* b;                /* (V,) */
   float* c;                /* (H,) */
   dbn_mat Wb;              /* bf16 shadow of W (BF16 mode), else NULL               */
@@ -220,9 +224,14 @@ int dbn_rbm_cd_step(void* stream, const dbn_rbm_step_args* args);
  * template's optional outputs must be NULL.  Pure launches: capture it in a CUDA graph. */
 int dbn_rbm_fit_epoch(void* stream, const dbn_rbm_step_args* tmpl, int n_rows, int batch_size);
 
-/* W/b/c update from an (all-reduced) raw delta buffer: W += s*dW, b += s*db, c += s*dc, and
- * refresh of the bf16 shadow.  raw is [(H+1), ld]. */
-int dbn_rbm_apply_delta(void* stream, int V, int H, float scale, const float* raw, int ld,
+/* Rows [h0, h1) of the raw delta (dW | dc) of the chain left in the workspace by a
+ * dbn_rbm_cd_step(flags = DBN_STEP_SKIP_UPDATE) with the same args; h1 == H also writes the db row H.
+ * h0 % 8 == 0.  Lets the caller pipeline delta production with the all-reduce of earlier rows. */
+int dbn_rbm_delta_rows(void* stream, const dbn_rbm_step_args* args, int h0, int h1);
+
+/* W/b/c update from an (all-reduced) raw delta buffer [(H+1), ld], rows [h0, h1) (+ the db row when
+ * h1 == H): W += s*dW, c += s*dc, b += s*db, and refresh of the bf16 shadow. */
+int dbn_rbm_apply_delta(void* stream, int V, int H, int h0, int h1, float scale, const float* raw, int ld,
                         float* W, int ldw, float* b, float* c, const dbn_mat* Wb);
 
 /* ---- supervised fine-tune: _backpropagation + SGD update ------------------------------------ */
