@@ -63,8 +63,9 @@ int device_count_cached() {
       return ::dbn::fail(DBN_ERR_NO_DEVICE, "%s: no sm_100 CUDA device (this library has no CPU fallback)%s", __func__, ""); \
   } while (0)
 
-// bf16 row pitch: room for the ones column, multiple of 8 elements (16 B) as TMA requires.
-inline int bf16_pitch(int cols) { return (int)align_up((size_t)cols + 1, 8); }
+// bf16 row pitch: room for the ones column, multiple of 64 elements so that every row starts on a
+// 128-byte line (TMA needs 16 B; line-aligned rows halve the L2 requests of a 128-byte box row).
+inline int bf16_pitch(int cols) { return (int)align_up((size_t)cols + 1, 64); }
 
 struct RbmWorkspace {
   dbn_mat P0, Hs, Vt, Pk;
@@ -134,6 +135,10 @@ int dbn_abi_version(void) { return DBN_B200_ABI_VERSION; }
 const char* dbn_last_error(void) { return last_error_ref().c_str(); }
 int dbn_device_count(void) { return device_count_cached(); }
 uint64_t dbn_launch_count(void) { return launch_counter().load(); }
+int dbn_debug_set_trace(void* device_buf) {
+  umma_trace_ptr() = static_cast<long long*>(device_buf);
+  return DBN_OK;
+}
 size_t dbn_struct_size(int which) {
   switch (which) {
     case 0: return sizeof(dbn_mat);

@@ -6,6 +6,9 @@
 #include <stdio.h>
 #include <atomic>
 #include <string>
+#include <string.h>
+#include <stdlib.h>
+#include <utility>
 
 #include "dbn_b200.h"
 
@@ -54,6 +57,40 @@ inline std::atomic<uint64_t>& launch_counter() {
   } while (0)
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------
+// Every contraction kernel is launched with programmatic stream serialization: it may start (and run
+// its prologue: barrier init, TMEM allocation, tensor-map prefetch) while its predecessor in the
+// stream is still executing, and touches global memory only after pdl_wait(), which returns once the
+// predecessor grid has completed and flushed.  At batch 256 the step is a chain of ~10 us kernels, so
+// hiding launch latency and prologue is worth ~25 % of the step.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+inline bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DBN_B200_PDL");
+    v = (e == nullptr || e[0] != '0') ? 1 : 0;
+  }
+  return v == 1;
+}
+
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+}
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // ---- typed matrix access ------------------------------------------------------------------------

@@ -10,24 +10,43 @@ namespace dbn {
 // float64 oracle (reference: dbn/activations.py:29  1/(1+exp(-x))).
 __device__ __forceinline__ float sigmoid_strict(float x) { return 1.0f / (1.0f + expf(-x)); }
 
+// BF16 tensor-core mode: ex2.approx + rcp (2 MUFU ops, ~1e-6 relative) -- far inside the 2e-3 budget
+// of that mode and ~6x fewer issue slots than expf + IEEE division, which matters because the
+// epilogue warps must keep up with the tcgen05 mainloop.
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float sigmoid_fast(float x) { return rcp_approx(1.0f + __expf(-x)); }
+
+template <bool kFast>
 __device__ __forceinline__ float apply_act(int act, float x) {
-  if (act == DBN_ACT_SIGMOID) return sigmoid_strict(x);
+  if (act == DBN_ACT_SIGMOID) return kFast ? sigmoid_fast(x) : sigmoid_strict(x);
   if (act == DBN_ACT_RELU) return fmaxf(x, 0.0f);  // dbn/activations.py:49
   return x;
 }
 
 // Activation epilogue on 4 columns.  M, N = logical output extent (stores are masked to it).
+template <bool kFast = false>
 __device__ __forceinline__ void act_epilogue_quad(const dbn_act_epilogue& e, uint32_t epoch, int m, int n4,
                                                   const float acc[4], int M, int N) {
   if (m >= M || n4 >= N) return;
   const int nvalid = min(4, N - n4);
   float a[4];
+  float bv[4] = {0.f, 0.f, 0.f, 0.f};
+  if (e.bias != nullptr) {
+    if (nvalid == 4 && (reinterpret_cast<uintptr_t>(e.bias + n4) & 15) == 0) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(e.bias + n4));
+      bv[0] = t.x; bv[1] = t.y; bv[2] = t.z; bv[3] = t.w;
+    } else {
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    float x = acc[j];
-    if (e.bias != nullptr && j < nvalid) x += e.bias[n4 + j];
-    a[j] = apply_act(e.act, x);
+      for (int j = 0; j < 4; ++j)
+        if (j < nvalid) bv[j] = __ldg(e.bias + n4 + j);
+    }
   }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) a[j] = apply_act<kFast>(e.act, acc[j] + bv[j]);
   if (e.mul != DBN_MUL_NONE) {
     float g[4];
     mat_load4(e.aux, m, n4, g, nvalid);
@@ -91,6 +110,152 @@ __device__ __forceinline__ void upd_epilogue_quad(const dbn_update_epilogue& e, 
     for (int j = 0; j < 4; ++j)
       if (n4 + j < N) e.vecN[n4 + j] += e.scale * acc[j];
   }
+}
+
+// ---- 32-column row segments (the tcgen05 epilogue: one thread = one accumulator row x 32 columns) ----
+// All loads are issued before any dependent math and all stores are 16-byte vectors, so the 32
+// independent element chains give the single epilogue warp per scheduler enough ILP; runtime switches
+// are hoisted to one branch per 32 columns.  Falls back to the generic quad path on ragged edges.
+__device__ __forceinline__ bool mat_vec_ok(const dbn_mat& m) {
+  if (m.ptr == nullptr) return true;
+  const int per16 = (m.dtype == DBN_F32) ? 4 : 8;
+  return (m.ld % per16) == 0 && (reinterpret_cast<uintptr_t>(m.ptr) & 15) == 0;
+}
+__device__ __forceinline__ void row32_load(const dbn_mat& m, int r, int c, float v[32]) {
+  const size_t i = (size_t)r * (size_t)m.ld + (size_t)c;
+  if (m.dtype == DBN_F32) {
+    const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(m.ptr) + i);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 t = p[j];
+      v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+    }
+  } else {
+    const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(m.ptr) + i);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint4 t = p[j];
+      const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[k]);
+        v[8 * j + 2 * k] = __low2float(h);
+        v[8 * j + 2 * k + 1] = __high2float(h);
+      }
+    }
+  }
+}
+__device__ __forceinline__ void row32_store(const dbn_mat& m, int r, int c, const float v[32]) {
+  const size_t i = (size_t)r * (size_t)m.ld + (size_t)c;
+  if (m.dtype == DBN_F32) {
+    float4* p = reinterpret_cast<float4*>(reinterpret_cast<float*>(m.ptr) + i);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) p[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  } else {
+    uint4* p = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(m.ptr) + i);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint32_t w[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const __nv_bfloat162 h = __floats2bfloat162_rn(v[8 * j + 2 * k], v[8 * j + 2 * k + 1]);
+        w[k] = *reinterpret_cast<const uint32_t*>(&h);
+      }
+      p[j] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+  }
+}
+
+template <bool kFast>
+__device__ __forceinline__ void act_epilogue_row32(const dbn_act_epilogue& e, uint32_t epoch, int m, int n0,
+                                                   const float acc[32], int M, int N) {
+  const bool inj = e.rng.injected.ptr != nullptr;
+  const bool vec = (m < M) && (n0 + 32 <= N) && mat_vec_ok(e.out) && mat_vec_ok(e.out2) && mat_vec_ok(e.sample) &&
+                   (e.mul == DBN_MUL_NONE || mat_vec_ok(e.aux)) && (!inj || mat_vec_ok(e.rng.injected)) &&
+                   (e.bias == nullptr || (reinterpret_cast<uintptr_t>(e.bias) & 15) == 0);
+  if (!vec) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) act_epilogue_quad<kFast>(e, epoch, m, n0 + 4 * j, acc + 4 * j, M, N);
+    return;
+  }
+  float a[32];
+  if (e.bias != nullptr) {
+    const float4* bp = reinterpret_cast<const float4*>(e.bias + n0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 t = __ldg(bp + j);
+      a[4 * j] = acc[4 * j] + t.x; a[4 * j + 1] = acc[4 * j + 1] + t.y;
+      a[4 * j + 2] = acc[4 * j + 2] + t.z; a[4 * j + 3] = acc[4 * j + 3] + t.w;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) a[j] = acc[j];
+  }
+  if (e.act == DBN_ACT_SIGMOID) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) a[j] = kFast ? sigmoid_fast(a[j]) : sigmoid_strict(a[j]);
+  } else if (e.act == DBN_ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) a[j] = fmaxf(a[j], 0.0f);
+  }
+  if (e.mul != DBN_MUL_NONE) {
+    float g[32];
+    row32_load(e.aux, m, n0, g);
+    if (e.mul == DBN_MUL_PRIME_SIGMOID) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) a[j] *= g[j] * (1.0f - g[j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) a[j] = (g[j] > 0.0f) ? a[j] : 0.0f;
+    }
+  }
+  float u[32];
+  if (e.rng.mode != DBN_RNG_NONE) {
+    if (inj) {
+      row32_load(e.rng.injected, m, n0, u);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) rng_uniform4(e.rng, epoch, m, n0 + 4 * j, u + 4 * j);
+    }
+    if (e.rng.mode == DBN_RNG_MASK) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const bool keep = inj ? (u[j] != 0.0f) : (u[j] < e.rng.keep_p);
+        a[j] = keep ? a[j] : 0.0f;
+      }
+    }
+  }
+  if (e.out.ptr != nullptr) row32_store(e.out, m, n0, a);
+  if (e.out2.ptr != nullptr) row32_store(e.out2, m, n0, a);
+  if (e.rng.mode == DBN_RNG_SAMPLE && e.sample.ptr != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) u[j] = (u[j] < a[j]) ? 1.0f : 0.0f;
+    row32_store(e.sample, m, n0, u);
+  }
+}
+
+__device__ __forceinline__ void upd_epilogue_row32(const dbn_update_epilogue& e, int m, int n0, const float acc[32],
+                                                   int M, int N, int augM, int augN) {
+  const bool core = (m < M) && (n0 + 32 <= N);
+  const bool vec = core && mat_vec_ok(e.raw) && mat_vec_ok(e.Wb) &&
+                   (e.raw.ptr != nullptr || ((e.ldw & 3) == 0 && (reinterpret_cast<uintptr_t>(e.W) & 15) == 0));
+  if (!vec) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) upd_epilogue_quad(e, m, n0 + 4 * j, acc + 4 * j, M, N, augM, augN);
+    return;
+  }
+  if (e.raw.ptr != nullptr) {
+    row32_store(e.raw, m, n0, acc);
+    return;
+  }
+  dbn_mat Wm;
+  Wm.ptr = e.W; Wm.ld = e.ldw; Wm.dtype = DBN_F32;
+  float w[32];
+  row32_load(Wm, m, n0, w);   // all 8 loads in flight before the first store
+#pragma unroll
+  for (int j = 0; j < 32; ++j) w[j] = fmaf(e.scale, acc[j], e.decay * w[j]);
+  row32_store(Wm, m, n0, w);
+  if (e.Wb.ptr != nullptr) row32_store(e.Wb, m, n0, w);
 }
 
 }  // namespace dbn

@@ -97,11 +97,15 @@ __device__ __forceinline__ void sg_run(const SimtGemmArgs& g, const Epi& epi_fn)
 }
 
 __global__ void __launch_bounds__(SG_THREADS) simt_gemm_act_kernel(SimtGemmArgs g, dbn_act_epilogue e) {
+  if (threadIdx.x == 0) pdl_launch_dependents();
+  pdl_wait();
   const uint32_t epoch = e.rng.epoch + (e.rng.epoch_ptr ? *e.rng.epoch_ptr : 0u);
   sg_run(g, [&](int m, int n4, const float* acc) { act_epilogue_quad(e, epoch, m, n4, acc, g.M, g.N); });
 }
 
 __global__ void __launch_bounds__(SG_THREADS) simt_gemm_update_kernel(SimtGemmArgs g, dbn_update_epilogue e) {
+  if (threadIdx.x == 0) pdl_launch_dependents();
+  pdl_wait();
   sg_run(g, [&](int m, int n4, const float* acc) { upd_epilogue_quad(e, m, n4, acc, g.M, g.N, g.augM, g.augN); });
 }
 
@@ -112,7 +116,7 @@ inline int simt_gemm_act(cudaStream_t st, int M, int N, const dbn_operands* ops,
   for (int i = 0; i < n_ops; ++i) g.ops[i] = ops[i];
   if (n_ops == 1) g.ops[1] = ops[0];
   dim3 grid(ceil_div(N, SG_BN), ceil_div(M, SG_BM));
-  simt_gemm_act_kernel<<<grid, SG_THREADS, 0, st>>>(g, e);
+  DBN_CUDA_OK(launch_pdl(simt_gemm_act_kernel, grid, dim3(SG_THREADS), 0, st, g, e));
   DBN_LAUNCH_CHECK();
   return DBN_OK;
 }
@@ -124,7 +128,7 @@ inline int simt_gemm_update(cudaStream_t st, int M, int N, int augM, int augN, c
   for (int i = 0; i < n_ops; ++i) g.ops[i] = ops[i];
   if (n_ops == 1) g.ops[1] = ops[0];
   dim3 grid(ceil_div(N + augN, SG_BN), ceil_div(M + augM, SG_BM));
-  simt_gemm_update_kernel<<<grid, SG_THREADS, 0, st>>>(g, e);
+  DBN_CUDA_OK(launch_pdl(simt_gemm_update_kernel, grid, dim3(SG_THREADS), 0, st, g, e));
   DBN_LAUNCH_CHECK();
   return DBN_OK;
 }

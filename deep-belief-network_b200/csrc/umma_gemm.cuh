@@ -25,7 +25,8 @@ namespace dbn {
 constexpr int UG_BM = 128;
 constexpr int UG_BK = 64;   // bf16 elements per stage along K = one 128-byte swizzle row
 constexpr int UG_UK = 16;   // K of one tcgen05.mma.kind::f16
-constexpr int UG_THREADS = 192;
+constexpr int UG_EPI_WARPS = 8;          // two warps per TMEM lane quarter, each takes half of the columns
+constexpr int UG_THREADS = 64 + 32 * UG_EPI_WARPS;
 constexpr int UG_SMEM_BUDGET = 196608;  // operand ring; + 1 KB barriers/alignment  (<= 227 KB per CTA)
 constexpr int UG_A_BYTES = UG_BM * UG_BK * 2;
 
@@ -38,7 +39,18 @@ struct UmmaGemmParams {
   int rowA[2], rowB[2];
   int M, N;  // accumulator extent (incl. the ones row / column)
   int tiles_m, tiles_n, group_m;
+  long long* trace;  // debug: per-CTA phase timestamps (dbn_debug_set_trace), normally NULL
 };
+
+// debug trace slots per CTA: 0 entry (globaltimer ns), 1..6 clock64 at: entry, setup done, first operands
+// landed, mainloop of first tile issued, accumulator of first tile ready, first tile's epilogue done, 7 exit
+__device__ __forceinline__ void trace_mark(const UmmaGemmParams& p, int slot) {
+  if (p.trace != nullptr) p.trace[(size_t)blockIdx.x * 8 + slot] = clock64();
+}
+inline long long*& umma_trace_ptr() {
+  static long long* t = nullptr;
+  return t;
+}
 
 // ---- PTX wrappers -------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -160,15 +172,25 @@ umma_gemm_kernel(const __grid_constant__ UmmaGemmParams p, const __grid_constant
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = p.tiles_m * p.tiles_n;
+  if (threadIdx.x == 0 && p.trace != nullptr) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+    p.trace[(size_t)blockIdx.x * 8 + 0] = (long long)gt;
+    trace_mark(p, 1);
+  }
 
   if (warp == 0 && lane == 0) {
+    for (int i = 0; i < p.n_ops; ++i) {   // hide the descriptor fetch behind the barrier / TMEM setup
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmA[i]) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmB[i]) : "memory");
+    }
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 4);  // one arrive per epilogue warp
+      mbar_init(tempty_bar(s), UG_EPI_WARPS);  // one arrive per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -183,6 +205,9 @@ umma_gemm_kernel(const __grid_constant__ UmmaGemmParams p, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) pdl_launch_dependents();
+  pdl_wait();   // nothing above touches global memory; everything below may
+  if (threadIdx.x == 0) trace_mark(p, 2);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -237,6 +262,7 @@ umma_gemm_kernel(const __grid_constant__ UmmaGemmParams p, const __grid_constant
             const uint32_t ph = (it / STAGES) & 1u;
             mbar_wait(full_bar(s), ph);
             tc_fence_after();
+            if (it == 0) trace_mark(p, 3);
             const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + UG_A_BYTES;
 #pragma unroll
             for (int k4 = 0; k4 < UG_BK / UG_UK; ++k4) {
@@ -249,6 +275,7 @@ umma_gemm_kernel(const __grid_constant__ UmmaGemmParams p, const __grid_constant
           }
         }
         tc_commit(tfull_bar(as));  // accumulator complete -> epilogue
+        if (tl == 0) trace_mark(p, 4);
       }
     }
   } else {
@@ -264,24 +291,26 @@ umma_gemm_kernel(const __grid_constant__ UmmaGemmParams p, const __grid_constant
       const uint32_t aph = (tl >> 1) & 1u;
       mbar_wait(tfull_bar(as), aph);
       tc_fence_after();
+      if (tl == 0 && warp == 2 && lane == 0) trace_mark(p, 5);
       const int m = mb * UG_BM + q * 32 + lane;
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
+      constexpr int CH_PER_WARP = (BN / 32) / (UG_EPI_WARPS / 4);
+      const int ch0 = ((warp - 2) >> 2) * CH_PER_WARP;   // which column half this warp drains
 #pragma unroll 1
-      for (int ch = 0; ch < BN / 32; ++ch) {
+      for (int ch = ch0; ch < ch0 + CH_PER_WARP; ++ch) {
         const int n0 = nb * BN + ch * 32;
         if (n0 >= p.N) break;  // warp-uniform
         uint32_t v[32];
         tc_ld32(trow + ch * 32, v);
+        float acc[32];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float acc[4] = {__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
-                          __uint_as_float(v[4 * j + 3])};
-          epi_args.apply(epoch, m, n0 + 4 * j, acc, coreM, coreN, augM, augN);
-        }
+        for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(v[j]);
+        epi_args.apply(epoch, m, n0, acc, coreM, coreN, augM, augN);
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(as));
+      if (tl == 0 && warp == 2 && lane == 0) trace_mark(p, 6);
     }
   }
 
@@ -292,20 +321,241 @@ umma_gemm_kernel(const __grid_constant__ UmmaGemmParams p, const __grid_constant
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
                  : "memory");
   }
+  if (threadIdx.x == 32) trace_mark(p, 7);
+}
+
+
+// =====================================================================================================
+// 2-CTA variant (cta_group::2): a cluster of two CTAs on one TPC computes a 256 x BN tile.  Each CTA
+// stages its own 128 rows of A and HALF of the B tile (BN/2 columns); tcgen05.mma.cta_group::2, issued
+// by the leader CTA only, reads both halves and writes each CTA's 128 x BN accumulator into that CTA's
+// own TMEM.  Operand bytes fetched from L2 per MAC drop by a third (BN = 256: 32 KB instead of 48 KB
+// per CTA and k-block), which is what bounds the single-CTA kernel on the 4096-wide layers.
+// =====================================================================================================
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  // the transaction bytes are credited to the LEADER CTA's barrier (peer bit cleared)
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_2sm(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+      "h"((uint16_t)3)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_2sm(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cta(uint32_t bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar),
+      "r"(cta)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t make_idesc_2sm(int bn, int transA, int transB, int negA) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)negA << 13) | ((uint32_t)transA << 15) |
+         ((uint32_t)transB << 16) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
+
+template <int BN, class Epi>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UG_THREADS, 1)
+umma_gemm2_kernel(const __grid_constant__ UmmaGemmParams p, const __grid_constant__ Epi epi_args, int coreM, int coreN,
+                  int augM, int augN) {
+  constexpr int HB = BN / 2;                     // B columns staged by each CTA
+  constexpr int B_BYTES = HB * UG_BK * 2;
+  constexpr int STAGE_BYTES = UG_A_BYTES + B_BYTES;
+  constexpr int STAGES = UG_SMEM_BUDGET / STAGE_BYTES;
+  constexpr int TMEM_COLS = 2 * BN;
+  static_assert(HB % 64 == 0, "MN-major B halves come in 64-column chunks");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t bar_base = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta = cluster_ctarank();
+  const bool leader = cta == 0;
+  const int n_tiles = p.tiles_m * p.tiles_n;     // tiles_m counts 256-row blocks here
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < p.n_ops; ++i) {   // hide the descriptor fetch behind the barrier / TMEM setup
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmA[i]) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmB[i]) : "memory");
+    }
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 2 * UG_EPI_WARPS);  // epilogue warps of both CTAs (used on the leader only)
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) pdl_launch_dependents();
+  pdl_wait();
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = cluster_id; tile < n_tiles; tile += n_clusters) {
+        int mb, nb;
+        tile_coords(p, tile, mb, nb);
+        const int m0 = mb * 256 + (int)cta * UG_BM;
+        const int n0 = nb * BN + (int)cta * HB;
+        for (int pass = 0; pass < p.n_ops; ++pass) {
+          const int nkb = (p.K[pass] + UG_BK - 1) / UG_BK;
+          for (int kb = 0; kb < nkb; ++kb, ++it) {
+            const int s = it % STAGES;
+            const uint32_t ph = (it / STAGES) & 1u;
+            mbar_wait(empty_bar(s), ph ^ 1u);
+            if (leader) mbar_expect_tx(full_bar(s), 2 * STAGE_BYTES);
+            const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + UG_A_BYTES;
+            if (!p.transA[pass]) {
+              tma_load_2d_2sm(sa, &p.tmA[pass], full_bar(s), kb * UG_BK, p.rowA[pass] + m0);
+            } else {
+#pragma unroll
+              for (int ch = 0; ch < UG_BM / 64; ++ch)
+                tma_load_2d_2sm(sa + ch * 8192, &p.tmA[pass], full_bar(s), m0 + ch * 64, p.rowA[pass] + kb * UG_BK);
+            }
+            if (!p.transB[pass]) {
+              tma_load_2d_2sm(sb, &p.tmB[pass], full_bar(s), kb * UG_BK, p.rowB[pass] + n0);
+            } else {
+#pragma unroll
+              for (int ch = 0; ch < HB / 64; ++ch)
+                tma_load_2d_2sm(sb + ch * 8192, &p.tmB[pass], full_bar(s), n0 + ch * 64, p.rowB[pass] + kb * UG_BK);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader && lane == 0) {
+      uint32_t it = 0, tl = 0;
+      for (int tile = cluster_id; tile < n_tiles; tile += n_clusters, ++tl) {
+        const int as = tl & 1;
+        const uint32_t aph = (tl >> 1) & 1u;
+        mbar_wait(tempty_bar(as), aph ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+        uint32_t accumulate = 0;
+        for (int pass = 0; pass < p.n_ops; ++pass) {
+          const int nkb = (p.K[pass] + UG_BK - 1) / UG_BK;
+          const int tA = p.transA[pass], tB = p.transB[pass];
+          const uint32_t idesc = make_idesc_2sm(BN, tA, tB, pass == 1);
+          for (int kb = 0; kb < nkb; ++kb, ++it) {
+            const int s = it % STAGES;
+            const uint32_t ph = (it / STAGES) & 1u;
+            mbar_wait(full_bar(s), ph);
+            tc_fence_after();
+            const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + UG_A_BYTES;
+#pragma unroll
+            for (int k4 = 0; k4 < UG_BK / UG_UK; ++k4) {
+              const uint64_t da = tA ? make_smem_desc(sa + k4 * 2048, 8192, 1024) : make_smem_desc(sa + k4 * 32, 16, 1024);
+              const uint64_t db = tB ? make_smem_desc(sb + k4 * 2048, 8192, 1024) : make_smem_desc(sb + k4 * 32, 16, 1024);
+              tc_mma_bf16_2sm(tmem_d, da, db, idesc, accumulate);
+              accumulate = 1;
+            }
+            tc_commit_2sm(empty_bar(s));   // frees this stage in BOTH CTAs
+          }
+        }
+        tc_commit_2sm(tfull_bar(as));      // both CTAs' epilogues may drain their half
+      }
+    }
+  } else {
+    // ===================== epilogue warps (both CTAs, own 128 rows) =====================
+    const int q = warp & 3;
+    uint32_t epoch = 0;
+    if constexpr (!Epi::kIsUpdate) epoch = epi_args.e.rng.epoch + (epi_args.e.rng.epoch_ptr ? *epi_args.e.rng.epoch_ptr : 0u);
+    uint32_t tl = 0;
+    for (int tile = cluster_id; tile < n_tiles; tile += n_clusters, ++tl) {
+      int mb, nb;
+      tile_coords(p, tile, mb, nb);
+      const int as = tl & 1;
+      const uint32_t aph = (tl >> 1) & 1u;
+      mbar_wait(tfull_bar(as), aph);
+      tc_fence_after();
+      const int m = mb * 256 + (int)cta * UG_BM + q * 32 + lane;
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
+      constexpr int CH_PER_WARP = (BN / 32) / (UG_EPI_WARPS / 4);
+      const int ch0 = ((warp - 2) >> 2) * CH_PER_WARP;   // which column half this warp drains
+#pragma unroll 1
+      for (int ch = ch0; ch < ch0 + CH_PER_WARP; ++ch) {
+        const int n0 = nb * BN + ch * 32;
+        if (n0 >= p.N) break;  // warp-uniform
+        uint32_t v[32];
+        tc_ld32(trow + ch * 32, v);
+        float acc[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(v[j]);
+        epi_args.apply(epoch, m, n0, acc, coreM, coreN, augM, augN);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cta(tempty_bar(as), 0);  // the leader's MMA thread owns the accumulator hand-off
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // no CTA may retire while its pair can still read its smem / signal its barriers
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+  }
 }
 
 struct UmmaActEpi {
   static constexpr bool kIsUpdate = false;
   dbn_act_epilogue e;
-  __device__ __forceinline__ void apply(uint32_t epoch, int m, int n4, const float acc[4], int M, int N, int, int) const {
-    act_epilogue_quad(e, epoch, m, n4, acc, M, N);
+  __device__ __forceinline__ void apply(uint32_t epoch, int m, int n0, const float acc[32], int M, int N, int, int) const {
+    act_epilogue_row32<true>(e, epoch, m, n0, acc, M, N);
   }
 };
 struct UmmaUpdEpi {
   static constexpr bool kIsUpdate = true;
   dbn_update_epilogue e;
-  __device__ __forceinline__ void apply(uint32_t, int m, int n4, const float acc[4], int M, int N, int augM, int augN) const {
-    upd_epilogue_quad(e, m, n4, acc, M, N, augM, augN);
+  __device__ __forceinline__ void apply(uint32_t, int m, int n0, const float acc[32], int M, int N, int augM, int augN) const {
+    upd_epilogue_row32(e, m, n0, acc, M, N, augM, augN);
   }
 };
 
@@ -387,9 +637,39 @@ inline int umma_launch(cudaStream_t st, UmmaGemmParams& p, const Epi& epi, int c
   p.group_m = std::max(1, std::min(p.tiles_m, 16));
   const int n_tiles = p.tiles_m * p.tiles_n;
   const int grid = std::min(n_tiles, umma_num_sms());
-  umma_gemm_kernel<BN, Epi><<<grid, UG_THREADS, SMEM, st>>>(p, epi, coreM, coreN, augM, augN);
+  DBN_CUDA_OK(launch_pdl(umma_gemm_kernel<BN, Epi>, dim3(grid), dim3(UG_THREADS), SMEM, st, p, epi, coreM, coreN, augM, augN));
   DBN_LAUNCH_CHECK();
   return DBN_OK;
+}
+
+template <int BN, class Epi>
+inline int umma_launch2(cudaStream_t st, UmmaGemmParams& p, const Epi& epi, int coreM, int coreN, int augM, int augN) {
+  constexpr int STAGE_BYTES = UG_A_BYTES + (BN / 2) * UG_BK * 2;
+  constexpr int STAGES = UG_SMEM_BUDGET / STAGE_BYTES;
+  constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + (2 * STAGES + 4) * 8 + 16;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DBN_CUDA_OK(cudaFuncSetAttribute(umma_gemm2_kernel<BN, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    attr_set = true;
+  }
+  p.tiles_m = ceil_div(p.M, 256);
+  p.tiles_n = ceil_div(p.N, BN);
+  p.group_m = std::max(1, std::min(p.tiles_m, 8));
+  const int n_tiles = p.tiles_m * p.tiles_n;
+  const int clusters = std::min(n_tiles, umma_num_sms() / 2);
+  DBN_CUDA_OK(launch_pdl(umma_gemm2_kernel<BN, Epi>, dim3(clusters * 2), dim3(UG_THREADS), SMEM, st, p, epi, coreM, coreN, augM,
+                         augN));
+  DBN_LAUNCH_CHECK();
+  return DBN_OK;
+}
+
+inline bool umma_use_2cta() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DBN_B200_UMMA_2CTA");
+    v = (e == nullptr || e[0] != '0') ? 1 : 0;
+  }
+  return v == 1;
 }
 
 template <class Epi>
@@ -397,6 +677,7 @@ inline int umma_gemm_run(cudaStream_t st, int M, int N, int augM, int augN, cons
                          const Epi& epi) {
   UmmaGemmParams p;
   memset(&p, 0, sizeof(p));
+  p.trace = umma_trace_ptr();
   p.n_ops = n_ops;
   p.M = M + augM;
   p.N = N + augN;
@@ -413,6 +694,9 @@ inline int umma_gemm_run(cudaStream_t st, int M, int N, int augM, int augN, cons
     const long cost = waves * cyc;
     if (best < 0 || cost < best) { best = cost; bn = cand; }
   }
+  // Large outputs (at least one 256 x 256 tile per SM pair) run on CTA pairs: a third fewer operand
+  // bytes per MAC out of L2.  B boxes then cover half a tile.
+  const bool two_cta = umma_use_2cta() && bn == 256 && (long)ceil_div(p.M, 256) * ceil_div(p.N, 256) >= sms / 2;
   for (int i = 0; i < n_ops; ++i) {
     const dbn_operands& o = ops[i];
     p.K[i] = o.K;
@@ -420,9 +704,10 @@ inline int umma_gemm_run(cudaStream_t st, int M, int N, int augM, int augN, cons
     p.rowA[i] = o.row0_A; p.rowB[i] = o.row0_B;
     if (!o.transA) DBN_TRY(make_operand_map(&p.tmA[i], o.A, o.K, (uint64_t)o.row0_A + p.M, UG_BM));
     else           DBN_TRY(make_operand_map(&p.tmA[i], o.A, p.M, (uint64_t)o.row0_A + o.K, 64));
-    if (!o.transB) DBN_TRY(make_operand_map(&p.tmB[i], o.B, o.K, (uint64_t)o.row0_B + p.N, bn));
+    if (!o.transB) DBN_TRY(make_operand_map(&p.tmB[i], o.B, o.K, (uint64_t)o.row0_B + p.N, two_cta ? bn / 2 : bn));
     else           DBN_TRY(make_operand_map(&p.tmB[i], o.B, p.N, (uint64_t)o.row0_B + o.K, 64));
   }
+  if (two_cta) return umma_launch2<256, Epi>(st, p, epi, M, N, augM, augN);
   if (bn == 256) return umma_launch<256, Epi>(st, p, epi, M, N, augM, augN);
   if (bn == 128) return umma_launch<128, Epi>(st, p, epi, M, N, augM, augN);
   return umma_launch<64, Epi>(st, p, epi, M, N, augM, augN);

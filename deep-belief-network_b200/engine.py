@@ -46,8 +46,9 @@ def ptr(t):
 
 
 def bf16_pitch(cols):
-    """Row pitch of a bf16 operand: room for the ones column, multiple of 8 elements (TMA: 16 B)."""
-    return (cols + 1 + 7) // 8 * 8
+    """Row pitch of a bf16 operand: room for the ones column, multiple of 64 elements so every row starts
+    on a 128-byte line (TMA itself only needs 16 B)."""
+    return (cols + 1 + 63) // 64 * 64
 
 
 def resolve_precision(precision, n_in, n_out, batch_size):

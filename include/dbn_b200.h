@@ -153,6 +153,10 @@ const char* dbn_last_error(void);
 int dbn_device_count(void);
 /* Counts kernels launched by this library since load (bench.py's `gpu_launches`). */
 uint64_t dbn_launch_count(void);
+/* Debug: when device_buf != NULL every tcgen05 contraction writes 8 int64 phase timestamps per CTA
+ * (entry globaltimer; clock64 at entry / setup / first operands / mainloop issued / accumulator ready /
+ * epilogue done / exit) to device_buf[blockIdx.x * 8 ...].  NULL switches it off (default). */
+int dbn_debug_set_trace(void* device_buf);
 /* sizeof() of the structs above as compiled (0 dbn_mat, 1 dbn_rng, 2 dbn_operands, 3 dbn_act_epilogue,
  * 4 dbn_update_epilogue, 5 dbn_rbm_step_args, 6 dbn_mlp_step_args): lets a binding check its layout. */
 size_t dbn_struct_size(int which);

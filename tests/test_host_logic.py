@@ -100,7 +100,7 @@ def test_precision_auto_policy():
     assert E.resolve_precision("auto", 64, 256, 32) == "fp32"
     assert E.resolve_precision("auto", 13, 100, 16) == "fp32"
     assert E.resolve_precision("fp32", 4096, 4096, 32768) == "fp32"
-    assert E.bf16_pitch(784) == 792 and E.bf16_pitch(500) == 504 and E.bf16_pitch(4096) == 4104
+    assert E.bf16_pitch(784) == 832 and E.bf16_pitch(500) == 512 and E.bf16_pitch(4096) == 4160
 
 
 def test_public_names():
