@@ -384,14 +384,21 @@ int dbn_mlp_train_step(void* stream, const dbn_mlp_step_args* a) {
   }
   const int HL = a->dims[L - 1];
   const dbn_mat WoM = make_mat(a->Wo, a->ldwo, DBN_F32);
-  {  // head scores (dbn/models.py:601 / :703), strict FP32: the head is tiny (n_out columns)
+  if (a->n_out <= 32) {  // fused head: scores + softmax/identity + delta + loss in one launch
+    DBN_CUDA_OK(launch_pdl(head_fused_kernel, dim3(ceil_div(B * 32, 256)), dim3(256), 0, st, ws.act[L - 1], HL,
+                           (const float*)a->Wo, a->ldwo, (const float*)a->bo, B, a->n_out, a->head,
+                           a->Y + (size_t)a->row0 * a->ldy, a->ldy, static_cast<float*>(ws.Z.ptr), ws.Z.ld,
+                           static_cast<float*>(ws.dO.ptr), ws.dO.ld, a->loss_rows));
+    DBN_LAUNCH_CHECK();
+  } else {
+    // head scores (dbn/models.py:601 / :703), strict FP32
     dbn_operands o = make_ops(ws.act[L - 1], 0, 0, WoM, 0, 0, HL);
     dbn_act_epilogue e = blank_act();
     e.bias = a->bo; e.act = DBN_ACT_IDENTITY; e.out = ws.Z;
     DBN_TRY(simt_gemm_act(st, B, a->n_out, &o, 1, e));
+    DBN_TRY(dbn_head_delta(stream, a->head, static_cast<float*>(ws.Z.ptr), ws.Z.ld, a->Y + (size_t)a->row0 * a->ldy,
+                           a->ldy, B, a->n_out, static_cast<float*>(ws.dO.ptr), ws.dO.ld, a->loss_rows));
   }
-  DBN_TRY(dbn_head_delta(stream, a->head, static_cast<float*>(ws.Z.ptr), ws.Z.ld, a->Y + (size_t)a->row0 * a->ldy,
-                         a->ldy, B, a->n_out, static_cast<float*>(ws.dO.ptr), ws.dO.ld, a->loss_rows));
   if (a->out.ptr) DBN_TRY(copy2d(st, a->out, ws.Z, B, a->n_out));
 
   // ---- backward deltas (dbn/models.py:489-501), all with the pre-update weights ----

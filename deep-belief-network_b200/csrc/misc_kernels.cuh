@@ -134,6 +134,66 @@ __global__ void __launch_bounds__(128) head_delta_kernel(int head, float* Z, int
   if (train && loss_rows != nullptr && lane == 0) loss_rows[warp] = loss;
 }
 
+
+// Fused output head for narrow heads (C <= 32): one warp per sample row computes the C scores
+// z = a W_o^T + b_o (lanes stride over K, coalesced on both a and the rows of W_o), then
+// softmax / identity, delta = out - y and the per-row loss -- dbn/models.py:594-626, :696-720 in one
+// launch instead of a skinny GEMM (4 CTAs at C = 10) plus a row kernel.
+__global__ void __launch_bounds__(256) head_fused_kernel(dbn_mat A, int K, const float* __restrict__ Wo, int ldwo,
+                                                         const float* __restrict__ bo, int B, int C, int head,
+                                                         const float* __restrict__ Y, int ldy, float* out, int ldo,
+                                                         float* delta, int ldd, float* loss_rows) {
+  if (threadIdx.x == 0) pdl_launch_dependents();
+  pdl_wait();
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= B) return;
+  float z = 0.0f;  // lane c ends up holding score c
+  for (int c0 = 0; c0 < C; c0 += 8) {
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
+    for (int k = lane; k < K; k += 32) {
+      const float a = mat_load(A, row, k);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (c0 + j < C) acc[j] = fmaf(a, __ldg(Wo + (size_t)(c0 + j) * ldwo + k), acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+      if (lane == c0 + j && c0 + j < C) z = acc[j] + bo[c0 + j];
+    }
+  }
+  const bool valid = lane < C;
+  float o_val = z, loss = 0.0f;
+  const float y = (valid && Y != nullptr) ? Y[(size_t)row * ldy + lane] : 0.0f;
+  if (head == DBN_HEAD_SOFTMAX) {
+    float mx = valid ? z : -INFINITY;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    const float e = valid ? expf(z - mx) : 0.0f;
+    float sum = e;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    o_val = e / sum;
+    float py = o_val * y;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) py += __shfl_xor_sync(0xffffffffu, py, o);
+    loss = -logf(py);
+  } else {
+    const float d = valid ? (z - y) : 0.0f;
+    loss = d * d;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) loss += __shfl_xor_sync(0xffffffffu, loss, o);
+  }
+  if (valid) {
+    out[(size_t)row * ldo + lane] = o_val;
+    if (delta != nullptr) delta[(size_t)row * ldd + lane] = o_val - y;
+  }
+  if (loss_rows != nullptr && Y != nullptr && lane == 0) loss_rows[row] = loss;
+}
+
 // W += s * dW, b += s * db (row H), c += s * dc (last column) from a raw [(H+1), ld] delta buffer,
 // rows [h0, h0 + rows).
 __global__ void __launch_bounds__(256) apply_delta_kernel(int V, int H, int h0, int rows, float scale,

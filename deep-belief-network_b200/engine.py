@@ -78,6 +78,29 @@ def dp_context():
     return dist.get_rank(), dist.get_world_size()
 
 
+def dp_check_shapes(n, batch_size, world):
+    if batch_size % world != 0 or n % batch_size != 0:
+        raise ValueError("data-parallel fit needs batch_size % world == 0 and N % batch_size == 0")
+
+
+def dp_local_rows(order, steps, world, bl, rank):
+    """Rows of the (globally shuffled) epoch that `rank` computes: slice [rank*bl, (rank+1)*bl) of every
+    global mini-batch, concatenated in step order."""
+    return np.asarray(order).reshape(steps, world, bl)[:, rank, :].reshape(-1)
+
+
+def dp_global_row0(step, batch_size, rank, bl):
+    """Global epoch-row index of the first local row of `step` (the Philox counter base)."""
+    return step * batch_size + rank * bl
+
+
+def dp_chunks(H, n_chunks):
+    """Row blocks (multiples of 256 rows = one CTA-pair tile) in which the raw delta is produced,
+    all-reduced and applied."""
+    rows = max(256, (H + n_chunks - 1) // n_chunks // 256 * 256)
+    return [(h0, min(H, h0 + rows)) for h0 in range(0, H, rows)]
+
+
 def epoch_order(n):
     """Composed double shuffle of the reference (dbn/models.py:106 then dbn/utils.py:12), drawn
     from the global np.random stream in the same order."""
@@ -315,14 +338,13 @@ class DpRbmEpochRunner:
     `n_chunks` row blocks: block i is all-reduced (NCCL sum over NVLink) and applied on a side stream
     while the tensor cores produce block i+1, so only the last block's exchange is exposed."""
 
-    def __init__(self, layer, Xd, batch_size, k, lr, seed, dp, n_chunks=8):
+    def __init__(self, layer, Xd, batch_size, k, lr, seed, dp, n_chunks=2):
         import torch.distributed as dist
         self.dist = dist
         self.layer, self.Xd = layer, Xd
         self.rank, self.world = dp
         self.n, self.bs, self.k = int(Xd.shape[0]), int(batch_size), int(k)
-        if self.bs % self.world != 0 or self.n % self.bs != 0:
-            raise ValueError("data-parallel fit needs batch_size % world == 0 and N % batch_size == 0")
+        dp_check_shapes(self.n, self.bs, self.world)
         self.bl = self.bs // self.world
         self.steps = self.n // self.bs
         self.n_local = self.steps * self.bl
@@ -338,8 +360,7 @@ class DpRbmEpochRunner:
         self.args.raw_delta = mat(self.raw)
         self.args.B = self.bl
         self.args.flags = L.STEP_SKIP_UPDATE
-        rows = max(128, (H + n_chunks - 1) // n_chunks // 128 * 128)
-        self.chunks = [(h0, min(H, h0 + rows)) for h0 in range(0, H, rows)]
+        self.chunks = dp_chunks(H, n_chunks)
         self.comm = torch.cuda.Stream(device=layer.device)
         self.ev_ready = [torch.cuda.Event() for _ in self.chunks]
         self.ev_done = torch.cuda.Event()
@@ -348,7 +369,7 @@ class DpRbmEpochRunner:
     def step(self, s):
         layer, lib, a = self.layer, self.layer.lib, self.args
         a.row0 = s * self.bl
-        a.rng.row0 = s * self.bs + self.rank * self.bl
+        a.rng.row0 = dp_global_row0(s, self.bs, self.rank, self.bl)
         main = torch.cuda.current_stream()
         L.check(lib.dbn_rbm_cd_step(stream_ptr(), C.byref(a)))          # Gibbs chain only
         for i, (h0, h1) in enumerate(self.chunks):
@@ -368,7 +389,7 @@ class DpRbmEpochRunner:
         before = self.layer.lib.dbn_launch_count()
         if order is None:
             order = epoch_order(self.n)
-        local = order.reshape(self.steps, self.world, self.bl)[:, self.rank, :].reshape(-1)
+        local = dp_local_rows(order, self.steps, self.world, self.bl, self.rank)
         self.feeder.push(local)
         self.layer.stage(self.Xd, idx=self.feeder.dev, out=self.Xp)
         for s in range(self.steps):
