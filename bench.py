@@ -231,9 +231,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup):
+    def timed(fn, steps, warmup, finish=None):
         for _ in range(warmup):
             fn()
+        if finish is not None:
+            finish()
         barrier()
         sampler = ClockSampler(local)
         sampler.start()
@@ -242,6 +244,8 @@ def main():
         e0.record()
         for _ in range(steps):
             fn()
+        if finish is not None:
+            finish()   # the main stream joins outstanding all-reduce / apply work before the stop event
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -340,10 +344,12 @@ def main():
             def step():
                 runner.step(state["s"] % runner.steps)
                 state["s"] += 1
+            drain = runner.drain
         else:
             runner = E.RbmEpochRunner(layer, Xd, C5_BS, 1, 0.01, 99)
             a = runner.args
             state = {"s": 0}
+            drain = None
 
             def step():
                 a.B = C5_BS
@@ -351,7 +357,7 @@ def main():
                 a.rng.row0 = a.row0
                 L.check(lib.dbn_rbm_cd_step(E.stream_ptr(), C.byref(a)))
                 state["s"] += 1
-        ms, clocks, launches = timed(step, args.steps, args.warmup)
+        ms, clocks, launches = timed(step, args.steps, args.warmup, finish=drain)
         rows_per_step = C5_BS
         flops_per_step = 10.0 * C5_V * C5_H * C5_BS
         scaling = "strong"

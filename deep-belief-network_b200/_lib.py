@@ -21,6 +21,7 @@ MUL_NONE, MUL_PRIME_SIGMOID, MUL_PRIME_RELU = 0, 1, 2
 RNG_NONE, RNG_SAMPLE, RNG_MASK = 0, 1, 2
 HEAD_SOFTMAX, HEAD_LINEAR = 0, 1
 STEP_SKIP_UPDATE = 1
+STEP_SKIP_FIRST_HIDDEN = 2
 MAX_LAYERS = 16
 
 
@@ -30,7 +31,7 @@ class Mat(C.Structure):
 
 class Rng(C.Structure):
     _fields_ = [("mode", C.c_int32), ("keep_p", C.c_float), ("seed", C.c_uint64), ("stream", C.c_uint32),
-                ("epoch", C.c_uint32), ("epoch_ptr", C.c_void_p), ("row0", C.c_uint32), ("_pad", C.c_uint32),
+                ("epoch", C.c_uint32), ("epoch_ptr", C.c_void_p), ("row0", C.c_uint32), ("col0", C.c_uint32),
                 ("injected", Mat)]
 
 
@@ -94,6 +95,7 @@ SYMBOLS = {
     "dbn_rbm_workspace_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "dbn_rbm_cd_step": (C.c_int, [C.c_void_p, _P(RbmStepArgs)]),
     "dbn_rbm_fit_epoch": (C.c_int, [C.c_void_p, _P(RbmStepArgs), C.c_int, C.c_int]),
+    "dbn_rbm_first_hidden": (C.c_int, [C.c_void_p, _P(RbmStepArgs), C.c_int, C.c_int]),
     "dbn_rbm_delta_rows": (C.c_int, [C.c_void_p, _P(RbmStepArgs), C.c_int, C.c_int]),
     "dbn_rbm_apply_delta": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p,
                                       C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, _P(Mat)]),

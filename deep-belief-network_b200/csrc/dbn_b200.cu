@@ -221,6 +221,34 @@ int dbn_rbm_workspace_init(void* stream, int precision, int Bmax, int V, int H, 
   return DBN_OK;
 }
 
+// t = 0 hidden phase on hidden units [h0, h1): P0 (kept for dW == h_0 of dbn/models.py:140) and the
+// first sample (dbn/models.py:135 -> :148-155).
+static int rbm_first_hidden_impl(void* stream, const dbn_rbm_step_args* a, int h0, int h1) {
+  const bool tc = a->precision == DBN_PREC_BF16;
+  RbmWorkspace ws;
+  rbm_ws_layout(a->precision, a->B, a->V, a->H, static_cast<char*>(a->workspace), &ws);
+  const dbn_mat Wop = tc ? a->Wb : make_mat(a->W, a->ldw, DBN_F32);
+  dbn_operands o = make_ops(a->X, 0, a->row0, Wop, 0, h0, a->V);
+  dbn_act_epilogue e = blank_act();
+  e.bias = a->c + h0; e.act = a->act;
+  e.rng = a->rng;
+  e.rng.mode = DBN_RNG_SAMPLE;
+  e.rng.col0 = a->rng.col0 + (uint32_t)h0;
+  if (a->rng.injected.ptr) e.rng.injected = offset_cols(a->rng.injected, h0);
+  e.out = offset_cols(ws.P0, h0);
+  e.out2 = offset_cols(a->P0, h0);
+  e.sample = offset_cols(ws.Hs, h0);
+  return dbn_gemm_act(stream, a->precision, a->B, h1 - h0, &o, 1, &e);
+}
+
+int dbn_rbm_first_hidden(void* stream, const dbn_rbm_step_args* a, int h0, int h1) {
+  DBN_NEED_DEVICE();
+  DBN_REQUIRE(a != nullptr, "null args");
+  DBN_REQUIRE(h0 >= 0 && h0 < h1 && h1 <= a->H && (h0 % 8) == 0, "bad unit range");
+  if (a->k == 0) return DBN_OK;
+  return rbm_first_hidden_impl(stream, a, h0, h1);
+}
+
 int dbn_rbm_cd_step(void* stream, const dbn_rbm_step_args* a) {
   DBN_NEED_DEVICE();
   DBN_REQUIRE(a != nullptr, "null args");
@@ -237,17 +265,20 @@ int dbn_rbm_cd_step(void* stream, const dbn_rbm_step_args* a) {
 
   for (int t = 0; t < a->k; ++t) {
     // h_t ~ P(h | v_t): dbn/models.py:135 -> :148-155
-    dbn_operands o = (t == 0) ? make_ops(a->X, 0, a->row0, Wop, 0, 0, V) : make_ops(ws.Vt, 0, 0, Wop, 0, 0, V);
-    dbn_act_epilogue e = blank_act();
-    e.bias = a->c; e.act = a->act;
-    e.rng = a->rng;
-    e.rng.mode = DBN_RNG_SAMPLE;
-    e.rng.stream = a->rng.stream + (uint32_t)t;
-    if (a->rng.injected.ptr) e.rng.injected = offset_cols(a->rng.injected, t * H);
-    e.out = (t == 0) ? ws.P0 : ws.Pk;  // only the t = 0 means are kept (== h_0 of :140)
-    if (t == 0) e.out2 = a->P0;
-    e.sample = ws.Hs;
-    DBN_TRY(dbn_gemm_act(stream, a->precision, B, H, &o, 1, &e));
+    if (t == 0) {
+      if (!(a->flags & DBN_STEP_SKIP_FIRST_HIDDEN)) DBN_TRY(rbm_first_hidden_impl(stream, a, 0, H));
+    } else {
+      dbn_operands o = make_ops(ws.Vt, 0, 0, Wop, 0, 0, V);
+      dbn_act_epilogue e = blank_act();
+      e.bias = a->c; e.act = a->act;
+      e.rng = a->rng;
+      e.rng.mode = DBN_RNG_SAMPLE;
+      e.rng.stream = a->rng.stream + (uint32_t)t;
+      if (a->rng.injected.ptr) e.rng.injected = offset_cols(a->rng.injected, t * H);
+      e.out = ws.Pk;  // only the t = 0 means are kept (== h_0 of :140)
+      e.sample = ws.Hs;
+      DBN_TRY(dbn_gemm_act(stream, a->precision, B, H, &o, 1, &e));
+    }
     if (t == 0 && a->H0s.ptr) DBN_TRY(copy2d(as_stream(stream), a->H0s, ws.Hs, B, H));
     // v_{t+1} = mean visible: dbn/models.py:136 -> :185-201
     dbn_operands o2 = make_ops(ws.Hs, 0, 0, Wop, 1, 0, H);

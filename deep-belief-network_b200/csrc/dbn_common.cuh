@@ -180,7 +180,7 @@ __host__ __device__ __forceinline__ float u01_from_bits(uint32_t x) { return (fl
 // 4 uniforms for columns n4..n4+3 (n4 % 4 == 0) of global row `row`.
 __device__ __forceinline__ void rng_uniform4(const dbn_rng& g, uint32_t epoch, int m, int n4, float u[4]) {
   uint32_t o[4];
-  philox4x32_10(g.row0 + (uint32_t)m, (uint32_t)(n4 >> 2), epoch, g.stream, (uint32_t)g.seed,
+  philox4x32_10(g.row0 + (uint32_t)m, (g.col0 + (uint32_t)n4) >> 2, epoch, g.stream, (uint32_t)g.seed,
                 (uint32_t)(g.seed >> 32), o);
 #pragma unroll
   for (int j = 0; j < 4; ++j) u[j] = u01_from_bits(o[j]);

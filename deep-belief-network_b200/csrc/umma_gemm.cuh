@@ -44,8 +44,16 @@ struct UmmaGemmParams {
 
 // debug trace slots per CTA: 0 entry (globaltimer ns), 1..6 clock64 at: entry, setup done, first operands
 // landed, mainloop of first tile issued, accumulator of first tile ready, first tile's epilogue done, 7 exit
+constexpr int UG_TRACE_SLOTS = 16;
 __device__ __forceinline__ void trace_mark(const UmmaGemmParams& p, int slot) {
-  if (p.trace != nullptr) p.trace[(size_t)blockIdx.x * 8 + slot] = clock64();
+  if (p.trace != nullptr) p.trace[(size_t)blockIdx.x * UG_TRACE_SLOTS + slot] = clock64();
+}
+__device__ __forceinline__ void trace_mark_ns(const UmmaGemmParams& p, int slot) {  // slots 0, 8, 9: globaltimer
+  if (p.trace != nullptr) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+    p.trace[(size_t)blockIdx.x * UG_TRACE_SLOTS + slot] = (long long)gt;
+  }
 }
 inline long long*& umma_trace_ptr() {
   static long long* t = nullptr;
@@ -172,10 +180,8 @@ umma_gemm_kernel(const __grid_constant__ UmmaGemmParams p, const __grid_constant
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = p.tiles_m * p.tiles_n;
-  if (threadIdx.x == 0 && p.trace != nullptr) {
-    unsigned long long gt;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
-    p.trace[(size_t)blockIdx.x * 8 + 0] = (long long)gt;
+  if (threadIdx.x == 0) {
+    trace_mark_ns(p, 0);
     trace_mark(p, 1);
   }
 
@@ -206,8 +212,11 @@ umma_gemm_kernel(const __grid_constant__ UmmaGemmParams p, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) pdl_launch_dependents();
-  pdl_wait();   // nothing above touches global memory; everything below may
-  if (threadIdx.x == 0) trace_mark(p, 2);
+  pdl_wait();   // nothing above touches global memory (bar the debug trace); everything below may
+  if (threadIdx.x == 0) {
+    trace_mark(p, 2);
+    trace_mark_ns(p, 8);
+  }
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -321,7 +330,10 @@ umma_gemm_kernel(const __grid_constant__ UmmaGemmParams p, const __grid_constant
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
                  : "memory");
   }
-  if (threadIdx.x == 32) trace_mark(p, 7);
+  if (threadIdx.x == 32) {
+    trace_mark(p, 7);
+    trace_mark_ns(p, 9);
+  }
 }
 
 
@@ -694,9 +706,9 @@ inline int umma_gemm_run(cudaStream_t st, int M, int N, int augM, int augN, cons
     const long cost = waves * cyc;
     if (best < 0 || cost < best) { best = cost; bn = cand; }
   }
-  // Large outputs (at least one 256 x 256 tile per SM pair) run on CTA pairs: a third fewer operand
-  // bytes per MAC out of L2.  B boxes then cover half a tile.
-  const bool two_cta = umma_use_2cta() && bn == 256 && (long)ceil_div(p.M, 256) * ceil_div(p.N, 256) >= sms / 2;
+  // Large outputs (256 x 256 tiles for at least half of the SM pairs) run on CTA pairs: a third fewer
+  // operand bytes per MAC out of L2.  B boxes then cover half a tile.
+  const bool two_cta = umma_use_2cta() && (long)ceil_div(p.M, 256) * ceil_div(p.N, 256) >= sms / 4;
   for (int i = 0; i < n_ops; ++i) {
     const dbn_operands& o = ops[i];
     p.K[i] = o.K;
@@ -704,7 +716,7 @@ inline int umma_gemm_run(cudaStream_t st, int M, int N, int augM, int augN, cons
     p.rowA[i] = o.row0_A; p.rowB[i] = o.row0_B;
     if (!o.transA) DBN_TRY(make_operand_map(&p.tmA[i], o.A, o.K, (uint64_t)o.row0_A + p.M, UG_BM));
     else           DBN_TRY(make_operand_map(&p.tmA[i], o.A, p.M, (uint64_t)o.row0_A + o.K, 64));
-    if (!o.transB) DBN_TRY(make_operand_map(&p.tmB[i], o.B, o.K, (uint64_t)o.row0_B + p.N, two_cta ? bn / 2 : bn));
+    if (!o.transB) DBN_TRY(make_operand_map(&p.tmB[i], o.B, o.K, (uint64_t)o.row0_B + p.N, two_cta ? 128 : bn));
     else           DBN_TRY(make_operand_map(&p.tmB[i], o.B, p.N, (uint64_t)o.row0_B + o.K, 64));
   }
   if (two_cta) return umma_launch2<256, Epi>(st, p, epi, M, N, augM, augN);

@@ -338,7 +338,7 @@ class DpRbmEpochRunner:
     `n_chunks` row blocks: block i is all-reduced (NCCL sum over NVLink) and applied on a side stream
     while the tensor cores produce block i+1, so only the last block's exchange is exposed."""
 
-    def __init__(self, layer, Xd, batch_size, k, lr, seed, dp, n_chunks=2):
+    def __init__(self, layer, Xd, batch_size, k, lr, seed, dp, n_chunks=4):
         import torch.distributed as dist
         self.dist = dist
         self.layer, self.Xd = layer, Xd
@@ -359,19 +359,28 @@ class DpRbmEpochRunner:
         self.args = layer._step_args(self.Xp, k, self.scale, self.ws, seed, self.epoch_ctr)
         self.args.raw_delta = mat(self.raw)
         self.args.B = self.bl
-        self.args.flags = L.STEP_SKIP_UPDATE
         self.chunks = dp_chunks(H, n_chunks)
         self.comm = torch.cuda.Stream(device=layer.device)
         self.ev_ready = [torch.cuda.Event() for _ in self.chunks]
-        self.ev_done = torch.cuda.Event()
+        self.ev_applied = [torch.cuda.Event() for _ in self.chunks]
+        self.pending = False
         self.launches_per_epoch = 0
 
     def step(self, s):
+        """One data-parallel mini-batch.  Row block i of W is final for this step as soon as block i
+        of the previous step's delta has been all-reduced and applied, and the t = 0 hidden phase on
+        hidden units of block i needs only those rows -- so the tail of the exchange hides behind the
+        head of the next step."""
         layer, lib, a = self.layer, self.layer.lib, self.args
         a.row0 = s * self.bl
         a.rng.row0 = dp_global_row0(s, self.bs, self.rank, self.bl)
         main = torch.cuda.current_stream()
-        L.check(lib.dbn_rbm_cd_step(stream_ptr(), C.byref(a)))          # Gibbs chain only
+        a.flags = L.STEP_SKIP_UPDATE | L.STEP_SKIP_FIRST_HIDDEN
+        for i, (h0, h1) in enumerate(self.chunks):
+            if self.pending:
+                main.wait_event(self.ev_applied[i])
+            L.check(lib.dbn_rbm_first_hidden(stream_ptr(), C.byref(a), h0, h1))
+        L.check(lib.dbn_rbm_cd_step(stream_ptr(), C.byref(a)))          # rest of the Gibbs chain (needs all of W)
         for i, (h0, h1) in enumerate(self.chunks):
             L.check(lib.dbn_rbm_delta_rows(stream_ptr(), C.byref(a), h0, h1))
             self.ev_ready[i].record(main)
@@ -382,8 +391,16 @@ class DpRbmEpochRunner:
                 L.check(lib.dbn_rbm_apply_delta(stream_ptr(), layer.V, layer.H, h0, h1, self.scale, ptr(self.raw),
                                                 self.ldr, ptr(layer.W), layer.V, ptr(layer.b), ptr(layer.c),
                                                 C.byref(mat(layer.Wb))))
-        self.ev_done.record(self.comm)
-        main.wait_event(self.ev_done)
+                self.ev_applied[i].record(self.comm)
+        self.pending = True
+
+    def drain(self):
+        """Make the main stream wait for every outstanding all-reduce + apply."""
+        if self.pending:
+            main = torch.cuda.current_stream()
+            for ev in self.ev_applied:
+                main.wait_event(ev)
+            self.pending = False
 
     def run(self, order=None):
         before = self.layer.lib.dbn_launch_count()
@@ -394,6 +411,7 @@ class DpRbmEpochRunner:
         self.layer.stage(self.Xd, idx=self.feeder.dev, out=self.Xp)
         for s in range(self.steps):
             self.step(s)
+        self.drain()
         self.epoch_ctr.add_(1)
         self.launches_per_epoch = int(self.layer.lib.dbn_launch_count() - before)
 

@@ -76,7 +76,7 @@ typedef struct dbn_mat {
 } dbn_mat;
 
 /* Counter-based randomness.  Uniforms are Philox4x32-10 with key = seed and counter =
- * (row0 + m, n / 4, *epoch_ptr + epoch, stream): a draw depends only on the GLOBAL row index of
+ * (row0 + m, (col0 + n) / 4, *epoch_ptr + epoch, stream): a draw depends only on the GLOBAL row index of
  * the sample inside the epoch, the unit index, the epoch and the purpose -- not on the batch
  * split or the number of GPUs.  u = (x >> 8) * 2^-24, so every uniform is exact in fp32.
  * If `injected.ptr` is non-NULL the values are read from it instead (fp32, [M, ld]): uniforms for
@@ -90,7 +90,7 @@ typedef struct dbn_rng {
   uint32_t epoch;            /* added to *epoch_ptr               */
   const uint32_t* epoch_ptr; /* device counter or NULL            */
   uint32_t row0;             /* global row index of row m = 0     */
-  uint32_t _pad;
+  uint32_t col0;             /* global unit index of column n = 0 (multiple of 4): column blocks of one layer */
   dbn_mat injected;
 } dbn_rng;
 
@@ -153,9 +153,10 @@ const char* dbn_last_error(void);
 int dbn_device_count(void);
 /* Counts kernels launched by this library since load (bench.py's `gpu_launches`). */
 uint64_t dbn_launch_count(void);
-/* Debug: when device_buf != NULL every tcgen05 contraction writes 8 int64 phase timestamps per CTA
- * (entry globaltimer; clock64 at entry / setup / first operands / mainloop issued / accumulator ready /
- * epilogue done / exit) to device_buf[blockIdx.x * 8 ...].  NULL switches it off (default). */
+/* Debug: when device_buf != NULL every single-CTA tcgen05 contraction writes 16 int64 phase timestamps
+ * per CTA to device_buf[blockIdx.x * 16 ...]: [0] entry (globaltimer ns); [1..7] clock64 at entry /
+ * setup done / first operands / mainloop issued / accumulator ready / epilogue done / exit; [8] ns when
+ * the programmatic-dependency wait returned; [9] ns at exit.  NULL switches it off (default). */
 int dbn_debug_set_trace(void* device_buf);
 /* sizeof() of the structs above as compiled (0 dbn_mat, 1 dbn_rng, 2 dbn_operands, 3 dbn_act_epilogue,
  * 4 dbn_update_epilogue, 5 dbn_rbm_step_args, 6 dbn_mlp_step_args): lets a binding check its layout. */
@@ -189,6 +190,7 @@ int dbn_rbm_visible_means(void* stream, int precision, const dbn_mat* Hm, int B,
 
 /* dbn_rbm_step_args.flags */
 #define DBN_STEP_SKIP_UPDATE 1 /* run the Gibbs chain only; deltas are produced later by dbn_rbm_delta_rows */
+#define DBN_STEP_SKIP_FIRST_HIDDEN 2 /* the t = 0 hidden phase was already run by dbn_rbm_first_hidden */
 
 /* Workspace of one CD-k step for a batch of up to Bmax rows (bytes). */
 size_t dbn_rbm_workspace_bytes(int precision, int Bmax, int V, int H);
@@ -227,6 +229,12 @@ int dbn_rbm_cd_step(void* stream, const dbn_rbm_step_args* args);
  * [tmpl->row0, tmpl->row0 + n_rows) of tmpl->X in steps of batch_size, last batch short.  The
  * template's optional outputs must be NULL.  Pure launches: capture it in a CUDA graph. */
 int dbn_rbm_fit_epoch(void* stream, const dbn_rbm_step_args* tmpl, int n_rows, int batch_size);
+
+/* The t = 0 hidden phase (means P0 + first sample) of the step described by args, restricted to hidden
+ * units [h0, h1) (h0 % 8 == 0): it needs only rows [h0, h1) of W, so a data-parallel caller can start
+ * it as soon as that row block of W has been updated, while later blocks are still being all-reduced.
+ * Follow with dbn_rbm_cd_step(flags |= DBN_STEP_SKIP_FIRST_HIDDEN). */
+int dbn_rbm_first_hidden(void* stream, const dbn_rbm_step_args* args, int h0, int h1);
 
 /* Rows [h0, h1) of the raw delta (dW | dc) of the chain left in the workspace by a
  * dbn_rbm_cd_step(flags = DBN_STEP_SKIP_UPDATE) with the same args; h1 == H also writes the db row H.

@@ -17,22 +17,32 @@ names = ["setup", "first operands", "mainloop issue", "acc ready", "epilogue", "
 
 
 def probe(label, fn, n_cta_hint=148):
-    buf = torch.zeros(148 * 8, dtype=torch.int64, device=dev)
+    buf = torch.zeros(148 * 16, dtype=torch.int64, device=dev)
+    buf2 = torch.zeros(148 * 16, dtype=torch.int64, device=dev)
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
     lib.dbn_debug_set_trace(C.c_void_p(buf.data_ptr()))
     fn()
+    lib.dbn_debug_set_trace(C.c_void_p(buf2.data_ptr()))
+    fn()          # dependent launch right behind the first: measures the inter-kernel gap
     torch.cuda.synchronize()
     lib.dbn_debug_set_trace(None)
-    t = buf.cpu().numpy().reshape(148, 8)
+    t = buf.cpu().numpy().reshape(148, 16)
+    t2 = buf2.cpu().numpy().reshape(148, 16)
     t = t[t[:, 7] != 0]
+    t2 = t2[t2[:, 7] != 0]
+    a_exit = t[:, 9].max()
+    gap_entry = t2[:, 0].min() - a_exit
+    gap_wait = t2[:, 8].min() - a_exit
+    dur_a = a_exit - t[:, 0].min()
     d = np.stack([t[:, 2] - t[:, 1], t[:, 3] - t[:, 2], t[:, 4] - t[:, 3], t[:, 5] - t[:, 4], t[:, 6] - t[:, 5],
                   t[:, 7] - t[:, 6], t[:, 7] - t[:, 1]], axis=1)
     med = np.median(d, axis=0)
     span_ns = t[:, 0].max() - t[:, 0].min()
     print("%-34s ctas=%3d  " % (label, len(t)) + "  ".join("%s=%d" % (n, m) for n, m in zip(names, med)) +
-          "  | entry skew %d ns" % span_ns)
+          "  | entry skew %d ns | kernel %d ns, next kernel entered %+d ns, passed its dependency wait %+d ns after this one's exit"
+          % (span_ns, dur_a, gap_entry, gap_wait))
 
 
 rng = np.random.default_rng(0)
