@@ -205,7 +205,11 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--global-batch", type=int, default=None, help="override the c5 global batch (experiments)")
     args = ap.parse_args()
+    if args.global_batch:
+        global C5_BS
+        C5_BS = args.global_batch
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
     if args.impl == "reference":
         return run_reference(args)

@@ -135,6 +135,16 @@ int dbn_abi_version(void) { return DBN_B200_ABI_VERSION; }
 const char* dbn_last_error(void) { return last_error_ref().c_str(); }
 int dbn_device_count(void) { return device_count_cached(); }
 uint64_t dbn_launch_count(void) { return launch_counter().load(); }
+int dbn_set_sm_reserve(int n_sms) {
+  DBN_REQUIRE(n_sms >= 0 && n_sms <= 64, "reserve out of range");
+  umma_sm_reserve() = n_sms;
+  return DBN_OK;
+}
+int dbn_debug_set_flag(int which, int value) {
+  DBN_REQUIRE(which == 0, "unknown flag");
+  umma_mc_flag() = value ? 1 : 0;  // 0: dispatch small contractions to the TMA-multicast cluster kernel
+  return DBN_OK;
+}
 int dbn_debug_set_trace(void* device_buf) {
   umma_trace_ptr() = static_cast<long long*>(device_buf);
   return DBN_OK;

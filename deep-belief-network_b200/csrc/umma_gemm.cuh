@@ -26,7 +26,8 @@ constexpr int UG_BM = 128;
 constexpr int UG_BK = 64;   // bf16 elements per stage along K = one 128-byte swizzle row
 constexpr int UG_UK = 16;   // K of one tcgen05.mma.kind::f16
 constexpr int UG_EPI_WARPS = 8;          // two warps per TMEM lane quarter, each takes half of the columns
-constexpr int UG_THREADS = 64 + 32 * UG_EPI_WARPS;
+constexpr int UG_THREADS = 64 + 32 * UG_EPI_WARPS + 32;   // + TMA producer A, MMA issuer, TMA producer B
+constexpr int UG_WARP_PB = 2 + UG_EPI_WARPS;              // warp index of the second (B-operand) producer
 constexpr int UG_SMEM_BUDGET = 196608;  // operand ring; + 1 KB barriers/alignment  (<= 227 KB per CTA)
 constexpr int UG_A_BYTES = UG_BM * UG_BK * 2;
 
@@ -218,8 +219,11 @@ umma_gemm_kernel(const __grid_constant__ UmmaGemmParams p, const __grid_constant
     trace_mark_ns(p, 8);
   }
 
-  if (warp == 0) {
-    // ===================== TMA producer =====================
+  if (warp == 0 || warp == UG_WARP_PB) {
+    // ===================== TMA producers: warp 0 feeds A, warp UG_WARP_PB feeds B =====================
+    // (one bulk-tensor instruction costs its issuing thread a few hundred cycles, so two issuers
+    //  double the rate at which stages fill when the tiles are small)
+    const bool is_pa = warp == 0;
     if (lane == 0) {
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -231,21 +235,24 @@ umma_gemm_kernel(const __grid_constant__ UmmaGemmParams p, const __grid_constant
             const int s = it % STAGES;
             const uint32_t ph = (it / STAGES) & 1u;
             mbar_wait(empty_bar(s), ph ^ 1u);
-            mbar_expect_tx(full_bar(s), STAGE_BYTES);
             const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + UG_A_BYTES;
-            if (!p.transA[pass]) {
-              tma_load_2d(sa, &p.tmA[pass], full_bar(s), kb * UG_BK, p.rowA[pass] + mb * UG_BM);
-            } else {
+            if (is_pa) {
+              mbar_expect_tx(full_bar(s), STAGE_BYTES);   // A and B bytes; the B producer only adds transactions
+              if (!p.transA[pass]) {
+                tma_load_2d(sa, &p.tmA[pass], full_bar(s), kb * UG_BK, p.rowA[pass] + mb * UG_BM);
+              } else {
 #pragma unroll
-              for (int ch = 0; ch < UG_BM / 64; ++ch)
-                tma_load_2d(sa + ch * 8192, &p.tmA[pass], full_bar(s), mb * UG_BM + ch * 64, p.rowA[pass] + kb * UG_BK);
-            }
-            if (!p.transB[pass]) {
-              tma_load_2d(sb, &p.tmB[pass], full_bar(s), kb * UG_BK, p.rowB[pass] + nb * BN);
+                for (int ch = 0; ch < UG_BM / 64; ++ch)
+                  tma_load_2d(sa + ch * 8192, &p.tmA[pass], full_bar(s), mb * UG_BM + ch * 64, p.rowA[pass] + kb * UG_BK);
+              }
             } else {
+              if (!p.transB[pass]) {
+                tma_load_2d(sb, &p.tmB[pass], full_bar(s), kb * UG_BK, p.rowB[pass] + nb * BN);
+              } else {
 #pragma unroll
-              for (int ch = 0; ch < BN / 64; ++ch)
-                tma_load_2d(sb + ch * 8192, &p.tmB[pass], full_bar(s), nb * BN + ch * 64, p.rowB[pass] + kb * UG_BK);
+                for (int ch = 0; ch < BN / 64; ++ch)
+                  tma_load_2d(sb + ch * 8192, &p.tmB[pass], full_bar(s), nb * BN + ch * 64, p.rowB[pass] + kb * UG_BK);
+              }
             }
           }
         }
@@ -287,7 +294,7 @@ umma_gemm_kernel(const __grid_constant__ UmmaGemmParams p, const __grid_constant
         if (tl == 0) trace_mark(p, 4);
       }
     }
-  } else {
+  } else if (warp < UG_WARP_PB) {
     // ===================== epilogue warps (TMEM lane quarter = warp % 4) =====================
     const int q = warp & 3;
     uint32_t epoch = 0;
@@ -512,7 +519,7 @@ umma_gemm2_kernel(const __grid_constant__ UmmaGemmParams p, const __grid_constan
         tc_commit_2sm(tfull_bar(as));      // both CTAs' epilogues may drain their half
       }
     }
-  } else {
+  } else if (warp < UG_WARP_PB) {
     // ===================== epilogue warps (both CTAs, own 128 rows) =====================
     const int q = warp & 3;
     uint32_t epoch = 0;
@@ -552,6 +559,207 @@ umma_gemm2_kernel(const __grid_constant__ UmmaGemmParams p, const __grid_constan
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+  }
+}
+
+
+// =====================================================================================================
+// Multicast variant for SMALL contractions (mini-batch 256: M = 2-16 row blocks).  Such a GEMM is bound
+// by the ~38 B/clk at which one SM can pull operands through TMA, and every CTA of a row block pulls
+// the same 16 KB A tile.  Here CL CTAs (a cluster along N) share one row block: each fetches 1/CL of
+// the A tile and TMA-multicasts it into all CL shared memories, so per k-block a CTA moves
+// 16 KB / CL + BN * 128 B instead of 16 KB + BN * 128 B, and narrower tiles (BN = 32 / 64) spread the
+// mainloop and the epilogue over CL x more SMs.  Stage release is cluster-wide: a stage may be
+// overwritten by any peer's multicast, so its empty barrier counts one commit from every CTA.
+// =====================================================================================================
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                               uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], "
+      "[%2], %5;" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+      "h"(mask)
+      : "memory");
+}
+
+template <int BN, int CL, class Epi>
+__global__ void __launch_bounds__(UG_THREADS, 1)
+umma_gemm_mc_kernel(const __grid_constant__ UmmaGemmParams p, const __grid_constant__ Epi epi_args, int coreM, int coreN,
+                    int augM, int augN) {
+  constexpr int B_BYTES = BN * UG_BK * 2;
+  constexpr int STAGE_BYTES = UG_A_BYTES + B_BYTES;
+  constexpr int STAGES = UG_SMEM_BUDGET / STAGE_BYTES;
+  constexpr int TMEM_COLS = 2 * BN;
+  constexpr int SLICE_ROWS = UG_BM / CL;                 // rows of the A tile this CTA fetches for everyone
+  constexpr int EPI_GROUPS = (BN / 32) < 2 ? 1 : 2;      // column halves drained in parallel
+  constexpr uint16_t MASK = (uint16_t)((1u << CL) - 1u);
+  static_assert(CL == 2 || CL == 4, "cluster of 2 or 4 CTAs");
+  static_assert(BN == 32 || BN == 64, "narrow tiles only");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t bar_base = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = (int)cluster_ctarank();
+  const int cluster_id = blockIdx.x / CL, n_clusters = gridDim.x / CL;
+  const int tiles_nc = (p.tiles_n + CL - 1) / CL;        // cluster tiles along N
+  const int n_ctiles = p.tiles_m * tiles_nc;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < p.n_ops; ++i) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmA[i]) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmB[i]) : "memory");
+    }
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), CL);   // one multicast commit from every CTA of the cluster
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 4 * EPI_GROUPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // every peer's barriers exist before anyone multicasts into them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) pdl_launch_dependents();
+  pdl_wait();
+
+  if (warp == 0 || warp == UG_WARP_PB) {
+    // ===================== TMA producers (A slice multicast / own B) =====================
+    const bool is_pa = warp == 0;
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int ct = cluster_id; ct < n_ctiles; ct += n_clusters) {
+        const int mb = ct % p.tiles_m;
+        const int nb = (ct / p.tiles_m) * CL + rank;
+        for (int pass = 0; pass < p.n_ops; ++pass) {
+          const int nkb = (p.K[pass] + UG_BK - 1) / UG_BK;
+          for (int kb = 0; kb < nkb; ++kb, ++it) {
+            const int s = it % STAGES;
+            const uint32_t ph = (it / STAGES) & 1u;
+            mbar_wait(empty_bar(s), ph ^ 1u);
+            const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + UG_A_BYTES;
+            const int r0 = rank * SLICE_ROWS;           // this CTA's slice of the 128 smem rows of A
+            if (is_pa) {
+              mbar_expect_tx(full_bar(s), STAGE_BYTES);   // full A tile (CL slices) + own B tile
+              if (!p.transA[pass]) {
+                tma_load_2d_mc(sa + r0 * 128, &p.tmA[pass], full_bar(s), kb * UG_BK, p.rowA[pass] + mb * UG_BM + r0, MASK);
+              } else {  // MN-major A: smem rows = (64-wide m chunk, k row); a slice is a k-row range of one chunk
+                tma_load_2d_mc(sa + r0 * 128, &p.tmA[pass], full_bar(s), mb * UG_BM + (r0 / 64) * 64,
+                               p.rowA[pass] + kb * UG_BK + (r0 % 64), MASK);
+              }
+            } else {
+              if (!p.transB[pass]) {
+                tma_load_2d(sb, &p.tmB[pass], full_bar(s), kb * UG_BK, p.rowB[pass] + nb * BN);
+              } else {
+#pragma unroll
+                for (int ch = 0; ch < BN / 64; ++ch)
+                  tma_load_2d(sb + ch * 8192, &p.tmB[pass], full_bar(s), nb * BN + ch * 64, p.rowB[pass] + kb * UG_BK);
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      uint32_t it = 0, tl = 0;
+      for (int ct = cluster_id; ct < n_ctiles; ct += n_clusters, ++tl) {
+        const int as = tl & 1;
+        const uint32_t aph = (tl >> 1) & 1u;
+        mbar_wait(tempty_bar(as), aph ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+        uint32_t accumulate = 0;
+        for (int pass = 0; pass < p.n_ops; ++pass) {
+          const int nkb = (p.K[pass] + UG_BK - 1) / UG_BK;
+          const int tA = p.transA[pass], tB = p.transB[pass];
+          const uint32_t idesc = make_idesc(BN, tA, tB, pass == 1);
+          for (int kb = 0; kb < nkb; ++kb, ++it) {
+            const int s = it % STAGES;
+            const uint32_t ph = (it / STAGES) & 1u;
+            mbar_wait(full_bar(s), ph);
+            tc_fence_after();
+            const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + UG_A_BYTES;
+#pragma unroll
+            for (int k4 = 0; k4 < UG_BK / UG_UK; ++k4) {
+              const uint64_t da = tA ? make_smem_desc(sa + k4 * 2048, 8192, 1024) : make_smem_desc(sa + k4 * 32, 16, 1024);
+              const uint64_t db = tB ? make_smem_desc(sb + k4 * 2048, 8192, 1024) : make_smem_desc(sb + k4 * 32, 16, 1024);
+              tc_mma_bf16(tmem_d, da, db, idesc, accumulate);
+              accumulate = 1;
+            }
+            tc_commit_mc(empty_bar(s), MASK);   // this CTA is done with stage s: tell every producer of the cluster
+          }
+        }
+        tc_commit(tfull_bar(as));
+      }
+    }
+  } else if (warp < UG_WARP_PB && (warp - 2) / 4 < EPI_GROUPS) {
+    // ===================== epilogue warps =====================
+    const int q = warp & 3;
+    uint32_t epoch = 0;
+    if constexpr (!Epi::kIsUpdate) epoch = epi_args.e.rng.epoch + (epi_args.e.rng.epoch_ptr ? *epi_args.e.rng.epoch_ptr : 0u);
+    uint32_t tl = 0;
+    for (int ct = cluster_id; ct < n_ctiles; ct += n_clusters, ++tl) {
+      const int mb = ct % p.tiles_m;
+      const int nb = (ct / p.tiles_m) * CL + rank;
+      const int as = tl & 1;
+      const uint32_t aph = (tl >> 1) & 1u;
+      mbar_wait(tfull_bar(as), aph);
+      tc_fence_after();
+      const int m = mb * UG_BM + q * 32 + lane;
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
+      constexpr int CH_PER_WARP = (BN / 32) / EPI_GROUPS;
+      const int ch0 = ((warp - 2) >> 2) * CH_PER_WARP;
+#pragma unroll 1
+      for (int ch = ch0; ch < ch0 + CH_PER_WARP; ++ch) {
+        const int n0 = nb * BN + ch * 32;
+        if (n0 >= p.N) break;  // warp-uniform (also the padding CTAs of the last cluster)
+        uint32_t v[32];
+        tc_ld32(trow + ch * 32, v);
+        float acc[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(v[j]);
+        epi_args.apply(epoch, m, n0, acc, coreM, coreN, augM, augN);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(as));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // peers may still multicast-commit into this CTA's barriers until they are done
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
                  : "memory");
   }
 }
@@ -621,6 +829,13 @@ inline bool umma_gemm_supported(int M, int N, const dbn_operands* ops, int n_ops
   return M >= 64 && N >= 32;
 }
 
+// SMs the persistent contraction kernels may occupy.  A data-parallel caller reserves a few SMs
+// (dbn_set_sm_reserve) so that the collective's own kernels can be co-scheduled with the contraction
+// they are meant to overlap with: a 1-CTA-per-SM persistent grid would otherwise starve them.
+inline int& umma_sm_reserve() {
+  static int r = 0;
+  return r;
+}
 inline int umma_num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -629,7 +844,7 @@ inline int umma_num_sms() {
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (n <= 0) n = 148;
   }
-  return n;
+  return std::max(2, (n - umma_sm_reserve()) & ~1);
 }
 
 template <int BN, class Epi>
@@ -675,6 +890,56 @@ inline int umma_launch2(cudaStream_t st, UmmaGemmParams& p, const Epi& epi, int 
   return DBN_OK;
 }
 
+template <int BN, int CL, class Epi>
+inline int umma_launch_mc(cudaStream_t st, UmmaGemmParams& p, const Epi& epi, int coreM, int coreN, int augM, int augN) {
+  constexpr int STAGE_BYTES = UG_A_BYTES + BN * UG_BK * 2;
+  constexpr int STAGES = UG_SMEM_BUDGET / STAGE_BYTES;
+  constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + (2 * STAGES + 4) * 8 + 16;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DBN_CUDA_OK(cudaFuncSetAttribute(umma_gemm_mc_kernel<BN, CL, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    attr_set = true;
+  }
+  p.tiles_m = ceil_div(p.M, UG_BM);
+  p.tiles_n = ceil_div(p.N, BN);
+  p.group_m = 1;
+  const int n_ctiles = p.tiles_m * ceil_div(p.tiles_n, CL);
+  const int clusters = std::min(n_ctiles, umma_num_sms() / CL);
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(clusters * CL);
+  cfg.blockDim = dim3(UG_THREADS);
+  cfg.dynamicSmemBytes = SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 2;
+  DBN_CUDA_OK(cudaLaunchKernelEx(&cfg, umma_gemm_mc_kernel<BN, CL, Epi>, p, epi, coreM, coreN, augM, augN));
+  DBN_LAUNCH_CHECK();
+  return DBN_OK;
+}
+
+// Opt-in (DBN_B200_UMMA_MC=1).  Measured on B200 (profiles/r01_notes.md): the multicast variant is correct
+// but not faster at mini-batch 256 -- the small contractions are bound by the rate at which ONE SM's
+// shared memory can be filled (~38 B/clk, the same figure the 4096-wide kernels show), and a multicast
+// A tile still lands in full in every CTA, so only L2 requests are saved, not fill bytes.
+inline int& umma_mc_flag() {
+  static int v = -1;
+  return v;
+}
+inline bool umma_use_mc() {
+  int& v = umma_mc_flag();
+  if (v < 0) {
+    const char* e = getenv("DBN_B200_UMMA_MC");
+    v = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
 inline bool umma_use_2cta() {
   static int v = -1;
   if (v < 0) {
@@ -709,17 +974,33 @@ inline int umma_gemm_run(cudaStream_t st, int M, int N, int augM, int augN, cons
   // Large outputs (256 x 256 tiles for at least half of the SM pairs) run on CTA pairs: a third fewer
   // operand bytes per MAC out of L2.  B boxes then cover half a tile.
   const bool two_cta = umma_use_2cta() && (long)ceil_div(p.M, 256) * ceil_div(p.N, 256) >= sms / 4;
+  // Small outputs (fewer 128 x 64 tiles than SMs: the mini-batch-256 regime) are TMA-pull bound per SM:
+  // run them on clusters that multicast the shared A tile, with tiles as narrow as B's layout allows.
+  bool any_transB = false;
+  for (int i = 0; i < n_ops; ++i) any_transB |= ops[i].transB != 0;
+  const int mc_bn = any_transB ? 64 : 32;
+  const int mc_tn = ceil_div(p.N, mc_bn);
+  const bool mc = umma_use_mc() && !two_cta && (long)tm * ceil_div(p.N, 64) <= sms && mc_tn >= 2;
+  const int mc_cl = mc_tn >= 4 ? 4 : 2;
+  if (mc) bn = mc_bn;
+  const int a_box_rows = mc ? UG_BM / mc_cl : UG_BM;   // multicast: each CTA fetches one slice of the A tile
   for (int i = 0; i < n_ops; ++i) {
     const dbn_operands& o = ops[i];
     p.K[i] = o.K;
     p.transA[i] = o.transA; p.transB[i] = o.transB;
     p.rowA[i] = o.row0_A; p.rowB[i] = o.row0_B;
-    if (!o.transA) DBN_TRY(make_operand_map(&p.tmA[i], o.A, o.K, (uint64_t)o.row0_A + p.M, UG_BM));
-    else           DBN_TRY(make_operand_map(&p.tmA[i], o.A, p.M, (uint64_t)o.row0_A + o.K, 64));
+    if (!o.transA) DBN_TRY(make_operand_map(&p.tmA[i], o.A, o.K, (uint64_t)o.row0_A + p.M, a_box_rows));
+    else           DBN_TRY(make_operand_map(&p.tmA[i], o.A, p.M, (uint64_t)o.row0_A + o.K, mc ? a_box_rows : 64));
     if (!o.transB) DBN_TRY(make_operand_map(&p.tmB[i], o.B, o.K, (uint64_t)o.row0_B + p.N, two_cta ? 128 : bn));
     else           DBN_TRY(make_operand_map(&p.tmB[i], o.B, p.N, (uint64_t)o.row0_B + o.K, 64));
   }
   if (two_cta) return umma_launch2<256, Epi>(st, p, epi, M, N, augM, augN);
+  if (mc) {
+    if (mc_bn == 32) return mc_cl == 4 ? umma_launch_mc<32, 4, Epi>(st, p, epi, M, N, augM, augN)
+                                       : umma_launch_mc<32, 2, Epi>(st, p, epi, M, N, augM, augN);
+    return mc_cl == 4 ? umma_launch_mc<64, 4, Epi>(st, p, epi, M, N, augM, augN)
+                      : umma_launch_mc<64, 2, Epi>(st, p, epi, M, N, augM, augN);
+  }
   if (bn == 256) return umma_launch<256, Epi>(st, p, epi, M, N, augM, augN);
   if (bn == 128) return umma_launch<128, Epi>(st, p, epi, M, N, augM, augN);
   return umma_launch<64, Epi>(st, p, epi, M, N, augM, augN);

@@ -338,13 +338,17 @@ class DpRbmEpochRunner:
     `n_chunks` row blocks: block i is all-reduced (NCCL sum over NVLink) and applied on a side stream
     while the tensor cores produce block i+1, so only the last block's exchange is exposed."""
 
-    def __init__(self, layer, Xd, batch_size, k, lr, seed, dp, n_chunks=4):
+    def __init__(self, layer, Xd, batch_size, k, lr, seed, dp, n_chunks=2):
         import torch.distributed as dist
         self.dist = dist
         self.layer, self.Xd = layer, Xd
         self.rank, self.world = dp
         self.n, self.bs, self.k = int(Xd.shape[0]), int(batch_size), int(k)
         dp_check_shapes(self.n, self.bs, self.world)
+        # optional: leave SMs for the NCCL kernels (measured: no gain on 8 x B200, default 0)
+        L.check(layer.lib.dbn_set_sm_reserve(int(os.environ.get("DBN_B200_SM_RESERVE", "0"))))
+        n_chunks = int(os.environ.get("DBN_B200_DP_CHUNKS", n_chunks))
+        self.nocomm = os.environ.get("DBN_B200_DP_NOCOMM", "0") == "1"   # debug: time the step without the exchange
         self.bl = self.bs // self.world
         self.steps = self.n // self.bs
         self.n_local = self.steps * self.bl
@@ -387,7 +391,8 @@ class DpRbmEpochRunner:
             with torch.cuda.stream(self.comm):
                 self.comm.wait_event(self.ev_ready[i])
                 blk = self.raw[h0:(h1 + 1 if h1 == layer.H else h1)]
-                self.dist.all_reduce(blk, op=self.dist.ReduceOp.SUM)
+                if not self.nocomm:
+                    self.dist.all_reduce(blk, op=self.dist.ReduceOp.SUM)
                 L.check(lib.dbn_rbm_apply_delta(stream_ptr(), layer.V, layer.H, h0, h1, self.scale, ptr(self.raw),
                                                 self.ldr, ptr(layer.W), layer.V, ptr(layer.b), ptr(layer.c),
                                                 C.byref(mat(layer.Wb))))

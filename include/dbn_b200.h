@@ -153,6 +153,12 @@ const char* dbn_last_error(void);
 int dbn_device_count(void);
 /* Counts kernels launched by this library since load (bench.py's `gpu_launches`). */
 uint64_t dbn_launch_count(void);
+/* Keep n_sms SMs free of the persistent contraction kernels (0 = use all; default).  Data-parallel
+ * callers set this so the collective's kernels can run next to the contraction they overlap with. */
+int dbn_set_sm_reserve(int n_sms);
+/* Debug / experiments: flag 0 = route small contractions to the TMA-multicast cluster kernel (default
+ * off; also DBN_B200_UMMA_MC=1). */
+int dbn_debug_set_flag(int which, int value);
 /* Debug: when device_buf != NULL every single-CTA tcgen05 contraction writes 16 int64 phase timestamps
  * per CTA to device_buf[blockIdx.x * 16 ...]: [0] entry (globaltimer ns); [1..7] clock64 at entry /
  * setup done / first operands / mainloop issued / accumulator ready / epilogue done / exit; [8] ns when
