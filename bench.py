@@ -351,6 +351,7 @@ def main():
             drain = runner.drain
         else:
             runner = E.RbmEpochRunner(layer, Xd, C5_BS, 1, 0.01, 99)
+            layer.stage(Xd, out=runner.Xp)
             a = runner.args
             state = {"s": 0}
             drain = None

@@ -6,6 +6,7 @@
 #include "simt_gemm.cuh"
 #include "umma_gemm.cuh"
 #include "misc_kernels.cuh"
+#include "rbm_persistent.cuh"
 
 using namespace dbn;
 
@@ -314,6 +315,31 @@ int dbn_rbm_cd_step(void* stream, const dbn_rbm_step_args* a) {
     DBN_TRY(dbn_gemm_update(stream, a->precision, H, V, 1, 1, o, 2, &u));
   }
   return DBN_OK;
+}
+
+int dbn_rbm_persistent_plan(int precision, int V, int H, int batch_size) {
+  if (precision != DBN_PREC_FP32) return 0;
+  int Hc = 0;
+  return rp_plan(V, H, batch_size, &Hc);
+}
+
+int dbn_rbm_fit_epoch_persistent(void* stream, const dbn_rbm_step_args* t, const int32_t* idx, int n_rows,
+                                 int batch_size) {
+  DBN_NEED_DEVICE();
+  DBN_REQUIRE(t && idx && n_rows >= 0 && batch_size > 0, "bad argument");
+  DBN_REQUIRE(t->precision == DBN_PREC_FP32 && t->X.dtype == DBN_F32, "the persistent kernel is the strict-FP32 path");
+  DBN_REQUIRE(t->act == DBN_ACT_SIGMOID || t->act == DBN_ACT_RELU, "Invalid activation function.");
+  DBN_REQUIRE(!t->rng.injected.ptr || t->rng.injected.dtype == DBN_F32, "injected uniforms must be fp32");
+  if (n_rows == 0 || t->k == 0) return DBN_OK;
+  RbmPersistArgs a;
+  memset(&a, 0, sizeof(a));
+  a.X = static_cast<const float*>(t->X.ptr); a.ldx = t->X.ld;
+  a.idx = idx; a.n_rows = n_rows; a.batch_size = batch_size;
+  a.V = t->V; a.H = t->H; a.k = t->k; a.act = t->act;
+  a.lr_over_bs = t->lr_over_bs;
+  a.W = t->W; a.ldw = t->ldw; a.b = t->b; a.c = t->c;
+  a.rng = t->rng;
+  return rbm_persistent_launch(as_stream(stream), a, t->V, t->H, batch_size);
 }
 
 int dbn_rbm_fit_epoch(void* stream, const dbn_rbm_step_args* tmpl, int n_rows, int batch_size) {

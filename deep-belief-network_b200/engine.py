@@ -169,16 +169,19 @@ class DeviceRbm:
         return mat(self.Wb) if self.prec == L.PREC_BF16 else mat(self.W)
 
     # -- operand staging ---------------------------------------------------------------------------
+    def alloc_staged(self, n, cols):
+        """Uninitialised operand buffer for n rows of `cols` features in this precision's layout."""
+        if self.prec == L.PREC_BF16:
+            return torch.empty(n, bf16_pitch(cols), dtype=torch.bfloat16, device=self.device)
+        return torch.empty(n, cols, dtype=torch.float32, device=self.device)
+
     def stage(self, Xd, idx=None, out=None, dropout=None):
         """Rows of Xd (fp32 or bf16) -> operand layout of this precision (bf16 + ones column in
         BF16 mode), optionally permuted by idx (device int32)."""
         n = int(idx.numel()) if idx is not None else int(Xd.shape[0])
         cols = int(Xd.shape[1])
         if out is None:
-            if self.prec == L.PREC_BF16:
-                out = torch.empty(n, bf16_pitch(cols), dtype=torch.bfloat16, device=self.device)
-            else:
-                out = torch.empty(n, cols, dtype=torch.float32, device=self.device)
+            out = self.alloc_staged(n, cols)
         ones = cols if self.prec == L.PREC_BF16 else -1
         L.check(self.lib.dbn_gather_rows(stream_ptr(), mat(Xd), ptr(idx), n, cols, mat(out), ones,
                                          C.byref(dropout) if dropout is not None else None))
@@ -283,28 +286,31 @@ class RbmEpochRunner:
         self.n, self.bs, self.k = int(Xd.shape[0]), int(batch_size), int(k)
         n, lib = self.n, layer.lib
         self.feeder = _IndexFeeder(n, layer.device)
-        self.Xp = layer.stage(Xd)  # allocates the epoch array; rewritten by the gather every epoch
+        self.Xp = layer.alloc_staged(n, int(Xd.shape[1]))  # epoch array; (re)written by the gather every epoch
         self.ws = layer.make_workspace(min(self.bs, n))
         self.epoch_ctr = torch.zeros(1, dtype=torch.int32, device=layer.device)
         self.U = None
         if rng_mode == "numpy":
             self.U = torch.empty(n, k * layer.H, dtype=torch.float32, device=layer.device)
         self.args = layer._step_args(self.Xp, k, lr / batch_size, self.ws, seed, self.epoch_ctr, self.U)
-        # warm-up launch of every kernel of the step outside graph capture (lr = 0: parameters unchanged)
-        warm = layer._step_args(self.Xp, k, 0.0, self.ws, seed, self.epoch_ctr, self.U)
-        warm.B, warm.row0 = min(self.bs, n), 0
-        if self.U is not None:
-            self.U[:warm.B].fill_(0.5)
-        L.check(lib.dbn_rbm_cd_step(stream_ptr(), C.byref(warm)))
-        torch.cuda.current_stream().synchronize()
+        # layers that fit on chip: one persistent cluster kernel per epoch, W resident in shared memory
+        self.persistent = (os.environ.get("DBN_B200_PERSISTENT", "1") != "0" and Xd.dtype == torch.float32 and
+                           Xd.is_contiguous() and
+                           lib.dbn_rbm_persistent_plan(layer.prec, layer.V, layer.H, min(self.bs, n)) > 0)
+        if self.persistent:
+            self.args.X = mat(Xd)
         self.graph = None
         self.launches_per_epoch = 0
         self.epochs_run = 0
 
     def _enqueue(self):
         lib = self.layer.lib
-        self.layer.stage(self.Xd, idx=self.feeder.dev, out=self.Xp)
-        L.check(lib.dbn_rbm_fit_epoch(stream_ptr(), C.byref(self.args), self.n, self.bs))
+        if self.persistent:
+            L.check(lib.dbn_rbm_fit_epoch_persistent(stream_ptr(), C.byref(self.args), ptr(self.feeder.dev), self.n,
+                                                     min(self.bs, self.n)))
+        else:
+            self.layer.stage(self.Xd, idx=self.feeder.dev, out=self.Xp)
+            L.check(lib.dbn_rbm_fit_epoch(stream_ptr(), C.byref(self.args), self.n, self.bs))
         self.epoch_ctr.add_(1)
 
     def run(self, order=None):
@@ -313,13 +319,14 @@ class RbmEpochRunner:
         self.feeder.push(epoch_order(self.n) if order is None else order)
         if self.U is not None:  # replay the reference's uniform stream
             self.U.copy_(torch.from_numpy(np.random.random_sample((self.n, self.k * layer.H)).astype(np.float32)))
-        if _use_graphs():
+        # Epoch 1 runs eagerly (it doubles as the warm-up that loads every kernel before capture, and a
+        # one-epoch fit never pays for capture + instantiation); epoch 2 is captured; later epochs replay.
+        if _use_graphs() and self.epochs_run >= 1 and not self.persistent:
             if self.graph is None:
-                before = layer.lib.dbn_launch_count()
+                torch.cuda.current_stream().synchronize()
                 self.graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(self.graph):
                     self._enqueue()
-                self.launches_per_epoch = int(layer.lib.dbn_launch_count() - before)
             self.graph.replay()
         else:
             before = layer.lib.dbn_launch_count()
@@ -355,7 +362,7 @@ class DpRbmEpochRunner:
         self.scale = lr / batch_size
         H, V = layer.H, layer.V
         self.feeder = _IndexFeeder(self.n_local, layer.device)
-        self.Xp = layer.stage(Xd[:self.n_local])
+        self.Xp = layer.alloc_staged(self.n_local, int(Xd.shape[1]))
         self.ws = layer.make_workspace(self.bl)
         self.epoch_ctr = torch.zeros(1, dtype=torch.int32, device=layer.device)
         self.ldr = (V + 1 + 3) // 4 * 4
@@ -524,8 +531,8 @@ class MlpIterRunner:
         self.keep_p = 1.0 - dropout_p
         self.first = mlp.layers[0]
         self.feeder = _IndexFeeder(n, dev)
-        self.Xp = self.first.stage(Xd)
-        self.Yp = Yd.clone()
+        self.Xp = self.first.alloc_staged(n, int(Xd.shape[1]))
+        self.Yp = torch.empty_like(Yd)
         self.ws = mlp.make_workspace(min(self.bs, n))
         self.iter_ctr = torch.zeros(1, dtype=torch.int32, device=dev)
         self.loss_rows = torch.zeros(n, dtype=torch.float32, device=dev)
@@ -536,13 +543,9 @@ class MlpIterRunner:
         decay = 1.0 - (lr * l2) / n
         self.args = mlp.step_args(self.Xp, self.Yp, lr / batch_size, decay, self.keep_p, self.ws, seed, self.iter_ctr,
                                   self.loss_rows, self.masks)
-        warm = mlp.step_args(self.Xp, self.Yp, 0.0, 1.0, self.keep_p, self.ws, seed, self.iter_ctr, self.loss_rows,
-                             self.masks)
-        warm.B, warm.row0 = min(self.bs, n), 0
-        L.check(lib.dbn_mlp_train_step(stream_ptr(), C.byref(warm)))
-        torch.cuda.current_stream().synchronize()
         self.graph = None
         self.launches_per_iter = 0
+        self.iters_run = 0
 
     def _enqueue(self):
         lib = self.mlp.lib
@@ -561,15 +564,15 @@ class MlpIterRunner:
             for m, w in zip(self.masks, self.widths):
                 m.copy_(torch.from_numpy(np.ascontiguousarray(flat[:, o:o + w])))
                 o += w
-        if _use_graphs():
+        if _use_graphs() and self.iters_run >= 1:   # iteration 1 eager (warm-up), iteration 2 captured, then replays
             if self.graph is None:
-                before = lib.dbn_launch_count()
+                torch.cuda.current_stream().synchronize()
                 self.graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(self.graph):
                     self._enqueue()
-                self.launches_per_iter = int(lib.dbn_launch_count() - before)
             self.graph.replay()
         else:
             before = lib.dbn_launch_count()
             self._enqueue()
             self.launches_per_iter = int(lib.dbn_launch_count() - before)
+        self.iters_run += 1

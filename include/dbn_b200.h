@@ -236,6 +236,16 @@ int dbn_rbm_cd_step(void* stream, const dbn_rbm_step_args* args);
  * template's optional outputs must be NULL.  Pure launches: capture it in a CUDA graph. */
 int dbn_rbm_fit_epoch(void* stream, const dbn_rbm_step_args* tmpl, int n_rows, int batch_size);
 
+/* On-chip persistent variant of dbn_rbm_fit_epoch for layers whose weights fit in the shared memory of
+ * one thread-block cluster (strict FP32 only): ONE launch trains the whole epoch with W resident in
+ * distributed shared memory; hidden units are sharded over the cluster's CTAs.  tmpl->X is the
+ * UN-permuted fp32 dataset, idx[n_rows] the epoch order (device), tmpl->rng.injected (optional) the
+ * uniforms in epoch order.  dbn_rbm_persistent_plan returns the cluster size it would use, 0 if the
+ * shape does not fit (then use dbn_rbm_fit_epoch). */
+int dbn_rbm_persistent_plan(int precision, int V, int H, int batch_size);
+int dbn_rbm_fit_epoch_persistent(void* stream, const dbn_rbm_step_args* tmpl, const int32_t* idx, int n_rows,
+                                 int batch_size);
+
 /* The t = 0 hidden phase (means P0 + first sample) of the step described by args, restricted to hidden
  * units [h0, h1) (h0 % 8 == 0): it needs only rows [h0, h1) of W, so a data-parallel caller can start
  * it as soon as that row block of W has been updated, while later blocks are still being all-reduced.
