@@ -291,18 +291,16 @@ def main():
         flops_per_step = sum(10.0 * v * h for v, h in zip(C2_DIMS[:-1], C2_DIMS[1:])) * C2_ROWS
         scaling = "weak"
 
-        # dominant kernel alone: the dW contraction of layer 3 (H=2000, V=500, K=2x256)
-        l3 = layers[2]
-        ws = l3.make_workspace(C2_BS)
-        a = l3._step_args(runners[2].Xp, 1, 0.0, ws, 1, None)
+        # dominant kernel alone: the v->h contraction + Bernoulli sampling of layer 1 (256 x 500, K = 784), the
+        # largest share of the step in the ncu launch list (profiles/r01_c2_launches.txt)
+        l1 = layers[0]
+        ws = l1.make_workspace(C2_BS)
+        a = l1._step_args(runners[0].Xp, 1, 0.0, ws, 1, None)
         a.B, a.row0 = C2_BS, 0
-        L.check(lib.dbn_rbm_cd_step(E.stream_ptr(), C.byref(a)))   # fills the workspace
-        raw = torch.zeros(l3.H + 1, 504, dtype=torch.float32, device=dev)
-        a.raw_delta = E.mat(raw)
         reps = 200
 
         def dom():
-            L.check(lib.dbn_rbm_delta_rows(E.stream_ptr(), C.byref(a), 0, l3.H))
+            L.check(lib.dbn_rbm_first_hidden(E.stream_ptr(), C.byref(a), 0, l1.H))
         for _ in range(10):
             dom()
         torch.cuda.synchronize()
@@ -313,11 +311,13 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         dom_ms = e0.elapsed_time(e1) / reps
-        dom_flops = 2.0 * 2 * (l3.H + 1) * (l3.V + 1) * C2_BS
-        roof = {"bound": "tensor", "kernel": "umma_gemm_kernel<update> dW of layer 3 (2001x501, K=2x256)",
+        dom_flops = 2.0 * C2_BS * l1.H * l1.V
+        roof = {"bound": "tensor", "kernel": "umma_gemm_kernel<64, act> v->h + sample of layer 1 (256x500, K=784)",
                 "achieved": dom_flops / (dom_ms * 1e-3) / 1e12, "peak": pk["bf16_burst"], "unit": "TFLOP/s",
-                "peak_source": pk["source"] + " bf16 burst", "traffic": None,
-                "note": "launch/latency-bound at batch 256 (SURVEY 8d); see also step_roofline"}
+                "peak_source": pk["source"] + " bf16 burst",
+                "traffic": 1.4e6, "traffic_source": "ncu dram__bytes_read+write per launch, profiles/r01_c2_umma_full.txt",
+                "note": "launch/latency-bound at batch 256: 0.2 GFLOP per launch, 16 CTAs; see step_roofline and "
+                        "profiles/r01_notes.md for the phase breakdown"}
 
         # ---------------- e2e through the estimator API, host buffers ----------------
         def e2e_step():
@@ -386,9 +386,11 @@ def main():
         torch.cuda.synchronize()
         dom_ms = e0.elapsed_time(e1) / reps
         dom_flops = 2.0 * bl * C5_V * C5_H
-        roof = {"bound": "tensor", "kernel": "umma_gemm_kernel<act> v->h (%dx4096, K=4096)" % bl,
-                "achieved": dom_flops / (dom_ms * 1e-3) / 1e12, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
-                "peak_source": pk["source"] + " bf16 sustained", "traffic": None}
+        roof = {"bound": "tensor", "kernel": "umma_gemm2_kernel<256, act> v->h (%dx4096, K=4096), cta_group::2" % bl,
+                "achieved": dom_flops / (dom_ms * 1e-3) / 1e12, "peak": pk["bf16_burst"], "unit": "TFLOP/s",
+                "peak_source": pk["source"] + " bf16 burst (kernel timed alone)",
+                "traffic": 835e6 * bl / 32768.0,
+                "traffic_source": "ncu dram__bytes_read+write per 32768-row launch, profiles/r01_c5_umma2cta_full.txt"}
 
         def e2e_step():
             from dbn_b200 import BinaryRBM
