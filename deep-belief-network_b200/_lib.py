@@ -101,8 +101,8 @@ SYMBOLS = {
     "dbn_rbm_fit_epoch_persistent": (C.c_int, [C.c_void_p, _P(RbmStepArgs), C.c_void_p, C.c_int, C.c_int]),
     "dbn_rbm_first_hidden": (C.c_int, [C.c_void_p, _P(RbmStepArgs), C.c_int, C.c_int]),
     "dbn_rbm_delta_rows": (C.c_int, [C.c_void_p, _P(RbmStepArgs), C.c_int, C.c_int]),
-    "dbn_rbm_apply_delta": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p,
-                                      C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, _P(Mat)]),
+    "dbn_rbm_apply_delta": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p,
+                                      C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, _P(Mat)]),
     "dbn_mlp_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, _P(C.c_int32), C.c_int, C.c_int]),
     "dbn_mlp_workspace_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, _P(C.c_int32), C.c_int, C.c_int,
                                          C.c_void_p]),

@@ -374,16 +374,17 @@ int dbn_rbm_delta_rows(void* stream, const dbn_rbm_step_args* a, int h0, int h1)
   return dbn_gemm_update(stream, a->precision, h1 - h0, a->V, h1 == a->H ? 1 : 0, 1, o, 2, &u);
 }
 
-int dbn_rbm_apply_delta(void* stream, int V, int H, int h0, int h1, float scale, const float* raw, int ld, float* W,
-                        int ldw, float* b, float* c, const dbn_mat* Wb) {
+int dbn_rbm_apply_delta(void* stream, int V, int H, int h0, int h1, int with_db, float scale, const float* raw, int ld,
+                        int raw_row0, float* W, int ldw, float* b, float* c, const dbn_mat* Wb) {
   DBN_NEED_DEVICE();
   DBN_REQUIRE(raw && W && b && c, "null argument");
-  DBN_REQUIRE(h0 >= 0 && h0 < h1 && h1 <= H, "bad row range");
-  const int rows = (h1 - h0) + (h1 == H ? 1 : 0);
+  DBN_REQUIRE(h0 >= 0 && h0 <= h1 && h1 <= H && (h0 < h1 || with_db), "bad row range");
+  DBN_REQUIRE(raw_row0 <= h0 || h0 == h1, "raw_row0 beyond the first row");
+  const int rows = (h1 - h0) + (with_db ? 1 : 0);
   const long total = (long)rows * ((V + 4) / 4);
   const int blocks = (int)std::min<long>((total + 255) / 256, 148L * 8);
-  apply_delta_kernel<<<blocks, 256, 0, as_stream(stream)>>>(V, H, h0, rows, scale, raw, ld, W, ldw, b, c,
-                                                           Wb ? *Wb : null_mat());
+  apply_delta_kernel<<<blocks, 256, 0, as_stream(stream)>>>(V, H, h0, h1 - h0, with_db, scale, raw, ld, raw_row0, W, ldw, b,
+                                                           c, Wb ? *Wb : null_mat());
   DBN_LAUNCH_CHECK();
   return DBN_OK;
 }

@@ -194,21 +194,23 @@ __global__ void __launch_bounds__(256) head_fused_kernel(dbn_mat A, int K, const
   if (loss_rows != nullptr && Y != nullptr && lane == 0) loss_rows[row] = loss;
 }
 
-// W += s * dW, b += s * db (row H), c += s * dc (last column) from a raw [(H+1), ld] delta buffer,
-// rows [h0, h0 + rows).
-__global__ void __launch_bounds__(256) apply_delta_kernel(int V, int H, int h0, int rows, float scale,
-                                                          const float* __restrict__ raw, int ld, float* W, int ldw,
-                                                          float* b, float* c, dbn_mat Wb) {
+// W += s * dW, c += s * dc (last column) for rows [h0, h0 + n_w_rows) and, if with_db, b += s * db (row H)
+// from a raw [(H+1), ld] delta buffer whose first stored row is raw_row0 (a reduce-scatter shard).
+__global__ void __launch_bounds__(256) apply_delta_kernel(int V, int H, int h0, int n_w_rows, int with_db, float scale,
+                                                          const float* __restrict__ raw, int ld, int raw_row0, float* W,
+                                                          int ldw, float* b, float* c, dbn_mat Wb) {
   const int quads = (V + 1 + 3) >> 2;
+  const int rows = n_w_rows + (with_db ? 1 : 0);
   const long total = (long)rows * quads;
   dbn_update_epilogue e;
   e.W = W; e.ldw = ldw; e.Wb = Wb; e.vecM = c; e.vecN = b; e.decay = 1.0f; e.scale = scale;
   e.raw.ptr = nullptr; e.raw.ld = 0; e.raw.dtype = DBN_F32;
   for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
-    const int m = h0 + (int)(t / quads), n4 = (int)(t % quads) << 2;
+    const int r = (int)(t / quads), n4 = (int)(t % quads) << 2;
+    const int m = (r < n_w_rows) ? h0 + r : H;       // the extra row is the visible-bias statistics row
     float acc[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[j] = (n4 + j <= V) ? raw[(size_t)m * ld + n4 + j] : 0.0f;
+    for (int j = 0; j < 4; ++j) acc[j] = (n4 + j <= V) ? raw[(size_t)(m - raw_row0) * ld + n4 + j] : 0.0f;
     upd_epilogue_quad(e, m, n4, acc, H, V, 1, 1);
   }
 }

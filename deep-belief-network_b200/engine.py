@@ -343,9 +343,12 @@ class DpRbmEpochRunner:
     by the GLOBAL row index, so the sampled states do not depend on the GPU count.  Per step the
     Gibbs chain runs locally, then the raw delta [(H+1) x (V+1)] = dW | dc ; db is produced in
     `n_chunks` row blocks: block i is all-reduced (NCCL sum over NVLink) and applied on a side stream
-    while the tensor cores produce block i+1, so only the last block's exchange is exposed."""
+    while the tensor cores produce block i+1, and the next step's first hidden phase on block i starts
+    as soon as block i has been applied.  Measured on 8 x B200 (profiles/r01_notes.md) the extra
+    launches and smaller contractions of the pipeline cost more than the overlap returns, so the
+    default is ONE block (plain step -> all-reduce -> apply); DBN_B200_DP_CHUNKS selects more."""
 
-    def __init__(self, layer, Xd, batch_size, k, lr, seed, dp, n_chunks=2):
+    def __init__(self, layer, Xd, batch_size, k, lr, seed, dp, n_chunks=1):
         import torch.distributed as dist
         self.dist = dist
         self.layer, self.Xd = layer, Xd
@@ -376,12 +379,22 @@ class DpRbmEpochRunner:
         self.ev_applied = [torch.cuda.Event() for _ in self.chunks]
         self.pending = False
         self.launches_per_epoch = 0
+        # sharded update (reduce-scatter -> row-block update -> all-gather of the bf16 shadow): BF16 mode only,
+        # because every contraction then reads the shadow and the fp32 master may stay sharded between steps
+        self.sharded = (layer.prec == L.PREC_BF16 and H % self.world == 0 and len(self.chunks) == 1 and
+                        os.environ.get("DBN_B200_DP_SHARDED", "1") != "0")
+        self.master_sharded = False
+        if self.sharded:
+            self.hs = H // self.world
+            self.shard = torch.zeros(self.hs, self.ldr, dtype=torch.float32, device=layer.device)
 
     def step(self, s):
         """One data-parallel mini-batch.  Row block i of W is final for this step as soon as block i
         of the previous step's delta has been all-reduced and applied, and the t = 0 hidden phase on
         hidden units of block i needs only those rows -- so the tail of the exchange hides behind the
         head of the next step."""
+        if self.sharded:
+            return self.step_sharded(s)
         layer, lib, a = self.layer, self.layer.lib, self.args
         a.row0 = s * self.bl
         a.rng.row0 = dp_global_row0(s, self.bs, self.rank, self.bl)
@@ -400,11 +413,47 @@ class DpRbmEpochRunner:
                 blk = self.raw[h0:(h1 + 1 if h1 == layer.H else h1)]
                 if not self.nocomm:
                     self.dist.all_reduce(blk, op=self.dist.ReduceOp.SUM)
-                L.check(lib.dbn_rbm_apply_delta(stream_ptr(), layer.V, layer.H, h0, h1, self.scale, ptr(self.raw),
-                                                self.ldr, ptr(layer.W), layer.V, ptr(layer.b), ptr(layer.c),
-                                                C.byref(mat(layer.Wb))))
+                L.check(lib.dbn_rbm_apply_delta(stream_ptr(), layer.V, layer.H, h0, h1, 1 if h1 == layer.H else 0,
+                                                self.scale, ptr(self.raw), self.ldr, 0, ptr(layer.W), layer.V,
+                                                ptr(layer.b), ptr(layer.c), C.byref(mat(layer.Wb))))
                 self.ev_applied[i].record(self.comm)
         self.pending = True
+
+    def step_sharded(self, s):
+        """One data-parallel mini-batch with a sharded update: reduce-scatter the fp32 delta so that rank r
+        receives the summed rows [r*H/w, (r+1)*H/w), update that row block of the fp32 master (and of c),
+        then all-gather the refreshed bf16 shadow that every contraction reads.  Against a plain all-reduce
+        this moves 3/4 of the bytes (fp32 delta one way, bf16 weights back) and divides the update pass by
+        the number of ranks; the fp32 master is gathered once at the end (`finalize`)."""
+        layer, lib, a, dist = self.layer, self.layer.lib, self.args, self.dist
+        H, V = layer.H, layer.V
+        a.row0 = s * self.bl
+        a.rng.row0 = dp_global_row0(s, self.bs, self.rank, self.bl)
+        a.flags = L.STEP_SKIP_UPDATE
+        L.check(lib.dbn_rbm_cd_step(stream_ptr(), C.byref(a)))                     # whole Gibbs chain, local rows
+        L.check(lib.dbn_rbm_delta_rows(stream_ptr(), C.byref(a), 0, H))           # raw = dW | dc ; db  (partial sums)
+        h0, h1 = self.rank * self.hs, (self.rank + 1) * self.hs
+        if not self.nocomm:
+            dist.reduce_scatter_tensor(self.shard, self.raw[:H], op=dist.ReduceOp.SUM)
+            dist.all_reduce(self.raw[H:H + 1], op=dist.ReduceOp.SUM)                 # visible-bias row (tiny)
+        else:
+            self.shard.copy_(self.raw[h0:h1])
+        L.check(lib.dbn_rbm_apply_delta(stream_ptr(), V, H, h0, h1, 0, self.scale, ptr(self.shard), self.ldr, h0,
+                                        ptr(layer.W), V, ptr(layer.b), ptr(layer.c), C.byref(mat(layer.Wb))))
+        L.check(lib.dbn_rbm_apply_delta(stream_ptr(), V, H, H, H, 1, self.scale, ptr(self.raw), self.ldr, 0,
+                                        ptr(layer.W), V, ptr(layer.b), ptr(layer.c), C.byref(mat(layer.Wb))))
+        if not self.nocomm:
+            dist.all_gather_into_tensor(layer.Wb, layer.Wb[h0:h1])
+            dist.all_gather_into_tensor(layer.c, layer.c[h0:h1])
+        self.master_sharded = True
+
+    def finalize(self):
+        """Bring the fp32 master back to every rank after sharded steps (before export / metrics in fp32)."""
+        self.drain()
+        if self.sharded and self.master_sharded and not self.nocomm:
+            h0, h1 = self.rank * self.hs, (self.rank + 1) * self.hs
+            self.dist.all_gather_into_tensor(self.layer.W, self.layer.W[h0:h1])
+            self.master_sharded = False
 
     def drain(self):
         """Make the main stream wait for every outstanding all-reduce + apply."""
@@ -423,7 +472,7 @@ class DpRbmEpochRunner:
         self.layer.stage(self.Xd, idx=self.feeder.dev, out=self.Xp)
         for s in range(self.steps):
             self.step(s)
-        self.drain()
+        self.finalize()
         self.epoch_ctr.add_(1)
         self.launches_per_epoch = int(self.layer.lib.dbn_launch_count() - before)
 

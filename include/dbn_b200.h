@@ -257,10 +257,13 @@ int dbn_rbm_first_hidden(void* stream, const dbn_rbm_step_args* args, int h0, in
  * h0 % 8 == 0.  Lets the caller pipeline delta production with the all-reduce of earlier rows. */
 int dbn_rbm_delta_rows(void* stream, const dbn_rbm_step_args* args, int h0, int h1);
 
-/* W/b/c update from an (all-reduced) raw delta buffer [(H+1), ld], rows [h0, h1) (+ the db row when
- * h1 == H): W += s*dW, c += s*dc, b += s*db, and refresh of the bf16 shadow. */
-int dbn_rbm_apply_delta(void* stream, int V, int H, int h0, int h1, float scale, const float* raw, int ld,
-                        float* W, int ldw, float* b, float* c, const dbn_mat* Wb);
+/* Parameter update from a summed raw delta buffer (layout [(H+1), ld] = dW | dc ; db):
+ *   rows [h0, h1):  W += s*dW, c += s*dc, bf16 shadow refreshed        (h0 == h1: none)
+ *   with_db != 0 :  b += s*db from row H
+ * `raw` points at stored row `raw_row0` of that layout, so a reduce-scatter shard (rows [h0, h1) only)
+ * is passed with raw_row0 = h0 and a full buffer with raw_row0 = 0. */
+int dbn_rbm_apply_delta(void* stream, int V, int H, int h0, int h1, int with_db, float scale, const float* raw,
+                        int ld, int raw_row0, float* W, int ldw, float* b, float* c, const dbn_mat* Wb);
 
 /* ---- supervised fine-tune: _backpropagation + SGD update ------------------------------------ */
 #define DBN_MAX_LAYERS 16
