@@ -142,8 +142,9 @@ int dbn_set_sm_reserve(int n_sms) {
   return DBN_OK;
 }
 int dbn_debug_set_flag(int which, int value) {
-  DBN_REQUIRE(which == 0, "unknown flag");
-  umma_mc_flag() = value ? 1 : 0;  // 0: dispatch small contractions to the TMA-multicast cluster kernel
+  DBN_REQUIRE(which == 0 || which == 1, "unknown flag");
+  if (which == 0) umma_mc_flag() = value ? 1 : 0;   // small contractions -> TMA-multicast cluster kernel
+  else umma_m64_flag() = value ? 1 : 0;             // small contractions -> 64-row tiles
   return DBN_OK;
 }
 int dbn_debug_set_trace(void* device_buf) {

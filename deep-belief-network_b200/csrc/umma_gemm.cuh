@@ -141,9 +141,9 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t lbo_b
 // Instruction descriptor of tcgen05.mma.kind::f16: D = F32, A = B = BF16.
 //   [4,6) D format (1 = F32) | [7,10) A format (1 = BF16) | [10,13) B format | 13 negate A | 15 A MN-major
 //   16 B MN-major | [17,23) N >> 3 | [24,29) M >> 4
-__device__ __forceinline__ uint32_t make_idesc(int bn, int transA, int transB, int negA) {
+__device__ __forceinline__ uint32_t make_idesc(int bm, int bn, int transA, int transB, int negA) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)negA << 13) | ((uint32_t)transA << 15) |
-         ((uint32_t)transB << 16) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(UG_BM >> 4) << 24);
+         ((uint32_t)transB << 16) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(bm >> 4) << 24);
 }
 
 __device__ __forceinline__ void tile_coords(const UmmaGemmParams& p, int tile, int& mb, int& nb) {
@@ -157,14 +157,19 @@ __device__ __forceinline__ void tile_coords(const UmmaGemmParams& p, int tile, i
   nb = r / gm;
 }
 
-template <int BN, class Epi>
+template <int BM, int BN, class Epi>
 __global__ void __launch_bounds__(UG_THREADS, 1)
 umma_gemm_kernel(const __grid_constant__ UmmaGemmParams p, const __grid_constant__ Epi epi_args, int coreM, int coreN,
                  int augM, int augN) {
+  // BM = 128: accumulator row m lives in TMEM lane m.  BM = 64 (small contractions: half the A bytes per
+  // k-block, twice the CTAs): row m lives in lane 32*(m/16) + m%16, i.e. the low 16 lanes of each quarter.
+  static_assert(BM == 64 || BM == 128, "UMMA M");
+  constexpr int A_BYTES = BM * UG_BK * 2;
   constexpr int B_BYTES = BN * UG_BK * 2;
-  constexpr int STAGE_BYTES = UG_A_BYTES + B_BYTES;
-  constexpr int STAGES = UG_SMEM_BUDGET / STAGE_BYTES;
-  constexpr int TMEM_COLS = 2 * BN;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int STAGES = (UG_SMEM_BUDGET / STAGE_BYTES) > 12 ? 12 : (UG_SMEM_BUDGET / STAGE_BYTES);
+  constexpr int TMEM_COLS = (2 * BN) < 32 ? 32 : (2 * BN);
+  constexpr int EPI_GROUPS = (BN / 32) < 2 ? 1 : 2;      // column halves drained in parallel
   static_assert(STAGES >= 3, "pipeline too shallow");
 
   extern __shared__ uint8_t smem_raw[];
@@ -197,7 +202,7 @@ umma_gemm_kernel(const __grid_constant__ UmmaGemmParams p, const __grid_constant
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), UG_EPI_WARPS);  // one arrive per epilogue warp
+      mbar_init(tempty_bar(s), 4 * EPI_GROUPS);  // one arrive per active epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -235,15 +240,15 @@ umma_gemm_kernel(const __grid_constant__ UmmaGemmParams p, const __grid_constant
             const int s = it % STAGES;
             const uint32_t ph = (it / STAGES) & 1u;
             mbar_wait(empty_bar(s), ph ^ 1u);
-            const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + UG_A_BYTES;
+            const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + A_BYTES;
             if (is_pa) {
               mbar_expect_tx(full_bar(s), STAGE_BYTES);   // A and B bytes; the B producer only adds transactions
               if (!p.transA[pass]) {
-                tma_load_2d(sa, &p.tmA[pass], full_bar(s), kb * UG_BK, p.rowA[pass] + mb * UG_BM);
+                tma_load_2d(sa, &p.tmA[pass], full_bar(s), kb * UG_BK, p.rowA[pass] + mb * BM);
               } else {
 #pragma unroll
-                for (int ch = 0; ch < UG_BM / 64; ++ch)
-                  tma_load_2d(sa + ch * 8192, &p.tmA[pass], full_bar(s), mb * UG_BM + ch * 64, p.rowA[pass] + kb * UG_BK);
+                for (int ch = 0; ch < BM / 64; ++ch)
+                  tma_load_2d(sa + ch * 8192, &p.tmA[pass], full_bar(s), mb * BM + ch * 64, p.rowA[pass] + kb * UG_BK);
               }
             } else {
               if (!p.transB[pass]) {
@@ -272,14 +277,14 @@ umma_gemm_kernel(const __grid_constant__ UmmaGemmParams p, const __grid_constant
         for (int pass = 0; pass < p.n_ops; ++pass) {
           const int nkb = (p.K[pass] + UG_BK - 1) / UG_BK;
           const int tA = p.transA[pass], tB = p.transB[pass];
-          const uint32_t idesc = make_idesc(BN, tA, tB, pass == 1);
+          const uint32_t idesc = make_idesc(BM, BN, tA, tB, pass == 1);
           for (int kb = 0; kb < nkb; ++kb, ++it) {
             const int s = it % STAGES;
             const uint32_t ph = (it / STAGES) & 1u;
             mbar_wait(full_bar(s), ph);
             tc_fence_after();
             if (it == 0) trace_mark(p, 3);
-            const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + UG_A_BYTES;
+            const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + A_BYTES;
 #pragma unroll
             for (int k4 = 0; k4 < UG_BK / UG_UK; ++k4) {
               const uint64_t da = tA ? make_smem_desc(sa + k4 * 2048, 8192, 1024) : make_smem_desc(sa + k4 * 32, 16, 1024);
@@ -294,7 +299,7 @@ umma_gemm_kernel(const __grid_constant__ UmmaGemmParams p, const __grid_constant
         if (tl == 0) trace_mark(p, 4);
       }
     }
-  } else if (warp < UG_WARP_PB) {
+  } else if (warp < UG_WARP_PB && (warp - 2) / 4 < EPI_GROUPS) {
     // ===================== epilogue warps (TMEM lane quarter = warp % 4) =====================
     const int q = warp & 3;
     uint32_t epoch = 0;
@@ -308,9 +313,10 @@ umma_gemm_kernel(const __grid_constant__ UmmaGemmParams p, const __grid_constant
       mbar_wait(tfull_bar(as), aph);
       tc_fence_after();
       if (tl == 0 && warp == 2 && lane == 0) trace_mark(p, 5);
-      const int m = mb * UG_BM + q * 32 + lane;
+      const bool row_ok = (BM == 128) || lane < 16;
+      const int m = (BM == 128) ? mb * BM + q * 32 + lane : mb * BM + q * 16 + lane;
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
-      constexpr int CH_PER_WARP = (BN / 32) / (UG_EPI_WARPS / 4);
+      constexpr int CH_PER_WARP = (BN / 32) / EPI_GROUPS;
       const int ch0 = ((warp - 2) >> 2) * CH_PER_WARP;   // which column half this warp drains
 #pragma unroll 1
       for (int ch = ch0; ch < ch0 + CH_PER_WARP; ++ch) {
@@ -321,7 +327,7 @@ umma_gemm_kernel(const __grid_constant__ UmmaGemmParams p, const __grid_constant
         float acc[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(v[j]);
-        epi_args.apply(epoch, m, n0, acc, coreM, coreN, augM, augN);
+        if (row_ok) epi_args.apply(epoch, m, n0, acc, coreM, coreN, augM, augN);
       }
       tc_fence_before();
       __syncwarp();
@@ -700,7 +706,7 @@ umma_gemm_mc_kernel(const __grid_constant__ UmmaGemmParams p, const __grid_const
         for (int pass = 0; pass < p.n_ops; ++pass) {
           const int nkb = (p.K[pass] + UG_BK - 1) / UG_BK;
           const int tA = p.transA[pass], tB = p.transB[pass];
-          const uint32_t idesc = make_idesc(BN, tA, tB, pass == 1);
+          const uint32_t idesc = make_idesc(UG_BM, BN, tA, tB, pass == 1);
           for (int kb = 0; kb < nkb; ++kb, ++it) {
             const int s = it % STAGES;
             const uint32_t ph = (it / STAGES) & 1u;
@@ -847,24 +853,24 @@ inline int umma_num_sms() {
   return std::max(2, (n - umma_sm_reserve()) & ~1);
 }
 
-template <int BN, class Epi>
+template <int BM, int BN, class Epi>
 inline int umma_launch(cudaStream_t st, UmmaGemmParams& p, const Epi& epi, int coreM, int coreN, int augM, int augN) {
-  constexpr int B_BYTES = BN * UG_BK * 2;
-  constexpr int STAGE_BYTES = UG_A_BYTES + B_BYTES;
-  constexpr int STAGES = UG_SMEM_BUDGET / STAGE_BYTES;
+  constexpr int STAGE_BYTES = BM * UG_BK * 2 + BN * UG_BK * 2;
+  constexpr int STAGES = (UG_SMEM_BUDGET / STAGE_BYTES) > 12 ? 12 : (UG_SMEM_BUDGET / STAGE_BYTES);
   constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + (2 * STAGES + 4) * 8 + 16;
   static bool attr_set = false;
   if (!attr_set) {
-    DBN_CUDA_OK(cudaFuncSetAttribute(umma_gemm_kernel<BN, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    DBN_CUDA_OK(cudaFuncSetAttribute(umma_gemm_kernel<BM, BN, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     attr_set = true;
   }
-  p.tiles_m = ceil_div(p.M, UG_BM);
+  p.tiles_m = ceil_div(p.M, BM);
   p.tiles_n = ceil_div(p.N, BN);
-  // super-tile of group_m row blocks: A slab (group_m * 128 rows) + all of B stay L2-resident
+  // super-tile of group_m row blocks: A slab (group_m * BM rows) + all of B stay L2-resident
   p.group_m = std::max(1, std::min(p.tiles_m, 16));
   const int n_tiles = p.tiles_m * p.tiles_n;
   const int grid = std::min(n_tiles, umma_num_sms());
-  DBN_CUDA_OK(launch_pdl(umma_gemm_kernel<BN, Epi>, dim3(grid), dim3(UG_THREADS), SMEM, st, p, epi, coreM, coreN, augM, augN));
+  DBN_CUDA_OK(launch_pdl(umma_gemm_kernel<BM, BN, Epi>, dim3(grid), dim3(UG_THREADS), SMEM, st, p, epi, coreM, coreN, augM,
+                         augN));
   DBN_LAUNCH_CHECK();
   return DBN_OK;
 }
@@ -927,6 +933,18 @@ inline int umma_launch_mc(cudaStream_t st, UmmaGemmParams& p, const Epi& epi, in
 // but not faster at mini-batch 256 -- the small contractions are bound by the rate at which ONE SM's
 // shared memory can be filled (~38 B/clk, the same figure the 4096-wide kernels show), and a multicast
 // A tile still lands in full in every CTA, so only L2 requests are saved, not fill bytes.
+inline int& umma_m64_flag() {
+  static int v = -1;
+  return v;
+}
+inline bool umma_use_m64() {
+  int& v = umma_m64_flag();
+  if (v < 0) {
+    const char* e = getenv("DBN_B200_UMMA_M64");
+    v = (e != nullptr && e[0] == '1') ? 1 : 0;   // opt-in: measured slower than 128-row tiles (profiles/r01_notes.md)
+  }
+  return v == 1;
+}
 inline int& umma_mc_flag() {
   static int v = -1;
   return v;
@@ -980,10 +998,15 @@ inline int umma_gemm_run(cudaStream_t st, int M, int N, int augM, int augN, cons
   for (int i = 0; i < n_ops; ++i) any_transB |= ops[i].transB != 0;
   const int mc_bn = any_transB ? 64 : 32;
   const int mc_tn = ceil_div(p.N, mc_bn);
-  const bool mc = umma_use_mc() && !two_cta && (long)tm * ceil_div(p.N, 64) <= sms && mc_tn >= 2;
+  const bool small = !two_cta && (long)tm * ceil_div(p.N, 64) <= sms;
+  const bool mc = umma_use_mc() && small && mc_tn >= 2;
   const int mc_cl = mc_tn >= 4 ? 4 : 2;
-  if (mc) bn = mc_bn;
-  const int a_box_rows = mc ? UG_BM / mc_cl : UG_BM;   // multicast: each CTA fetches one slice of the A tile
+  // Opt-in for small outputs: 64-row tiles (UMMA M = 64) as narrow as B's layout allows.  Measured: not
+  // faster -- a pipeline stage completes every ~640 cycles whether it carries 12 KB or 24 KB (a floor of
+  // ~320 cycles per bulk-tensor copy), so halving the tile only doubles the L2 traffic.
+  const bool m64 = small && !mc && umma_use_m64();
+  if (mc || m64) bn = mc_bn;
+  const int a_box_rows = mc ? UG_BM / mc_cl : (m64 ? 64 : UG_BM);   // multicast: each CTA fetches one slice of the A tile
   for (int i = 0; i < n_ops; ++i) {
     const dbn_operands& o = ops[i];
     p.K[i] = o.K;
@@ -1001,9 +1024,13 @@ inline int umma_gemm_run(cudaStream_t st, int M, int N, int augM, int augN, cons
     return mc_cl == 4 ? umma_launch_mc<64, 4, Epi>(st, p, epi, M, N, augM, augN)
                       : umma_launch_mc<64, 2, Epi>(st, p, epi, M, N, augM, augN);
   }
-  if (bn == 256) return umma_launch<256, Epi>(st, p, epi, M, N, augM, augN);
-  if (bn == 128) return umma_launch<128, Epi>(st, p, epi, M, N, augM, augN);
-  return umma_launch<64, Epi>(st, p, epi, M, N, augM, augN);
+  if (m64) {
+    if (bn == 32) return umma_launch<64, 32, Epi>(st, p, epi, M, N, augM, augN);
+    return umma_launch<64, 64, Epi>(st, p, epi, M, N, augM, augN);
+  }
+  if (bn == 256) return umma_launch<128, 256, Epi>(st, p, epi, M, N, augM, augN);
+  if (bn == 128) return umma_launch<128, 128, Epi>(st, p, epi, M, N, augM, augN);
+  return umma_launch<128, 64, Epi>(st, p, epi, M, N, augM, augN);
 }
 
 inline int umma_gemm_act(cudaStream_t st, int M, int N, const dbn_operands* ops, int n_ops, const dbn_act_epilogue& e) {

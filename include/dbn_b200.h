@@ -157,7 +157,8 @@ uint64_t dbn_launch_count(void);
  * callers set this so the collective's kernels can run next to the contraction they overlap with. */
 int dbn_set_sm_reserve(int n_sms);
 /* Debug / experiments: flag 0 = route small contractions to the TMA-multicast cluster kernel (default
- * off; also DBN_B200_UMMA_MC=1). */
+ * off; also DBN_B200_UMMA_MC=1); flag 1 = 64-row (UMMA M = 64) tiles for small contractions (default off;
+ * also DBN_B200_UMMA_M64=1).  Both variants are covered by the parity tests; neither is faster. */
 int dbn_debug_set_flag(int which, int value);
 /* Debug: when device_buf != NULL every single-CTA tcgen05 contraction writes 16 int64 phase timestamps
  * per CTA to device_buf[blockIdx.x * 16 ...]: [0] entry (globaltimer ns); [1..7] clock64 at entry /

@@ -25,13 +25,17 @@ def load(golden_dir, name):
 # ---------------------------------------------------------------------------------------------------
 # fused contraction building blocks against NumPy
 # ---------------------------------------------------------------------------------------------------
-@pytest.fixture(params=["default", "multicast"])
+@pytest.fixture(params=["default", "m64", "multicast"])
 def umma_variant(request):
-    """The opt-in TMA-multicast cluster kernel must stay correct: run the contraction tests under both
-    dispatch policies (the flag is read once per process, so it is toggled through the library)."""
-    G.lib().dbn_debug_set_flag(0, 1 if request.param == "multicast" else 0)
+    """Dispatch policies of the tcgen05 path for small outputs: 128-row tiles (default) and the two opt-in
+    experiments, 64-row tiles and the TMA-multicast cluster kernel.  All must stay correct (flags are toggled
+    through the library)."""
+    lib = G.lib()
+    lib.dbn_debug_set_flag(0, 1 if request.param == "multicast" else 0)
+    lib.dbn_debug_set_flag(1, 1 if request.param == "m64" else 0)
     yield request.param
-    G.lib().dbn_debug_set_flag(0, 0)
+    lib.dbn_debug_set_flag(0, 0)
+    lib.dbn_debug_set_flag(1, 0)
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
