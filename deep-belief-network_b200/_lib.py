@@ -83,7 +83,6 @@ SYMBOLS = {
     "dbn_struct_size": (C.c_size_t, [C.c_int]),
     "dbn_debug_set_trace": (C.c_int, [C.c_void_p]),
     "dbn_set_sm_reserve": (C.c_int, [C.c_int]),
-    "dbn_debug_set_flag": (C.c_int, [C.c_int, C.c_int]),
     "dbn_philox_uniforms_host": (C.c_int, [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_int,
                                            C.c_void_p]),
     "dbn_gemm_act": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, _P(Operands), C.c_int, _P(ActEpilogue)]),

@@ -141,12 +141,6 @@ int dbn_set_sm_reserve(int n_sms) {
   umma_sm_reserve() = n_sms;
   return DBN_OK;
 }
-int dbn_debug_set_flag(int which, int value) {
-  DBN_REQUIRE(which == 0 || which == 1, "unknown flag");
-  if (which == 0) umma_mc_flag() = value ? 1 : 0;   // small contractions -> TMA-multicast cluster kernel
-  else umma_m64_flag() = value ? 1 : 0;             // small contractions -> 64-row tiles
-  return DBN_OK;
-}
 int dbn_debug_set_trace(void* device_buf) {
   umma_trace_ptr() = static_cast<long long*>(device_buf);
   return DBN_OK;
@@ -256,7 +250,7 @@ static int rbm_first_hidden_impl(void* stream, const dbn_rbm_step_args* a, int h
 int dbn_rbm_first_hidden(void* stream, const dbn_rbm_step_args* a, int h0, int h1) {
   DBN_NEED_DEVICE();
   DBN_REQUIRE(a != nullptr, "null args");
-  DBN_REQUIRE(h0 >= 0 && h0 < h1 && h1 <= a->H && (h0 % 8) == 0, "bad unit range");
+  DBN_REQUIRE(h0 >= 0 && h0 < h1 && h1 <= a->H && (h0 % 64) == 0, "bad unit range (h0 must be a multiple of 64)");
   if (a->k == 0) return DBN_OK;
   return rbm_first_hidden_impl(stream, a, h0, h1);
 }
@@ -360,7 +354,7 @@ int dbn_rbm_fit_epoch(void* stream, const dbn_rbm_step_args* tmpl, int n_rows, i
 int dbn_rbm_delta_rows(void* stream, const dbn_rbm_step_args* a, int h0, int h1) {
   DBN_NEED_DEVICE();
   DBN_REQUIRE(a && a->raw_delta.ptr, "needs args with a raw_delta buffer");
-  DBN_REQUIRE(h0 >= 0 && h0 < h1 && h1 <= a->H && (h0 % 8) == 0, "bad row range");
+  DBN_REQUIRE(h0 >= 0 && h0 < h1 && h1 <= a->H && (h0 % 64) == 0, "bad row range (h0 must be a multiple of 64)");
   if (a->k == 0) return DBN_OK;
   const bool tc = a->precision == DBN_PREC_BF16;
   RbmWorkspace ws;

@@ -9,7 +9,13 @@
 // shadow therefore serves v->h (K-major B), h->v (MN-major B) and, with the activations, the
 // dW = P0^T V0 - Pk^T Vk contraction (MN-major A and B) without any transposed copy in HBM.
 //
-// Kernel shape: persistent, one CTA per SM, 6 warps:
+// Stages are FAT: one pipeline stage carries KS 64-wide k-slabs of both operands, each fetched by ONE
+// 3-D bulk-tensor copy (dims: 64 elements of a slab row, rows, slab/chunk index at a 128-byte stride).
+// Measured on B200 (tools/probes/tma_probe.cu): a bulk-tensor copy costs ~310 cycles whatever it
+// carries (4 KB or 32 KB; >100 B/clk per SM for 32 KB boxes), so the mainloop is paced by the NUMBER
+// of copies -- two per stage here, i.e. two per KS*64 of K.
+//
+// Kernel shape: persistent, one CTA per SM, 11 warps:
 //   warp 0    TMA producer (one elected lane)         -- ring of S smem stages, mbarrier full/empty
 //   warp 1    TMEM allocator + tcgen05.mma issuer      -- one elected lane issues 4 MMAs (K=16) per stage
 //   warps 2-5 epilogue (one TMEM lane quarter each)    -- double-buffered accumulator (2 x BN columns)
@@ -29,13 +35,13 @@ constexpr int UG_EPI_WARPS = 8;          // two warps per TMEM lane quarter, eac
 constexpr int UG_THREADS = 64 + 32 * UG_EPI_WARPS + 32;   // + TMA producer A, MMA issuer, TMA producer B
 constexpr int UG_WARP_PB = 2 + UG_EPI_WARPS;              // warp index of the second (B-operand) producer
 constexpr int UG_SMEM_BUDGET = 196608;  // operand ring; + 1 KB barriers/alignment  (<= 227 KB per CTA)
-constexpr int UG_A_BYTES = UG_BM * UG_BK * 2;
 
 struct UmmaGemmParams {
   CUtensorMap tmA[2];
   CUtensorMap tmB[2];
   int n_ops;
   int K[2];
+  int nslab[2];   // ceil(K / 64): 64-wide k-slabs per pass
   int transA[2], transB[2];
   int rowA[2], rowB[2];
   int M, N;  // accumulator extent (incl. the ones row / column)
@@ -95,6 +101,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
       "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -157,20 +169,20 @@ __device__ __forceinline__ void tile_coords(const UmmaGemmParams& p, int tile, i
   nb = r / gm;
 }
 
-template <int BM, int BN, class Epi>
+template <int BN, int KS, class Epi>
 __global__ void __launch_bounds__(UG_THREADS, 1)
 umma_gemm_kernel(const __grid_constant__ UmmaGemmParams p, const __grid_constant__ Epi epi_args, int coreM, int coreN,
                  int augM, int augN) {
-  // BM = 128: accumulator row m lives in TMEM lane m.  BM = 64 (small contractions: half the A bytes per
-  // k-block, twice the CTAs): row m lives in lane 32*(m/16) + m%16, i.e. the low 16 lanes of each quarter.
-  static_assert(BM == 64 || BM == 128, "UMMA M");
-  constexpr int A_BYTES = BM * UG_BK * 2;
-  constexpr int B_BYTES = BN * UG_BK * 2;
+  constexpr int BM = UG_BM;   // UMMA M = 128: accumulator row m lives in TMEM lane m
+  constexpr int A_SLAB = BM * UG_BK * 2;                 // one 64-wide k-slab of the A tile
+  constexpr int B_SLAB = BN * UG_BK * 2;
+  constexpr int A_BYTES = KS * A_SLAB;                   // operand regions of one (fat) stage
+  constexpr int B_BYTES = KS * B_SLAB;
   constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  constexpr int STAGES = (UG_SMEM_BUDGET / STAGE_BYTES) > 12 ? 12 : (UG_SMEM_BUDGET / STAGE_BYTES);
+  constexpr int STAGES = (UG_SMEM_BUDGET / STAGE_BYTES) > 8 ? 8 : (UG_SMEM_BUDGET / STAGE_BYTES);
   constexpr int TMEM_COLS = (2 * BN) < 32 ? 32 : (2 * BN);
   constexpr int EPI_GROUPS = (BN / 32) < 2 ? 1 : 2;      // column halves drained in parallel
-  static_assert(STAGES >= 3, "pipeline too shallow");
+  static_assert(STAGES >= 2, "pipeline too shallow");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -235,29 +247,20 @@ umma_gemm_kernel(const __grid_constant__ UmmaGemmParams p, const __grid_constant
         int mb, nb;
         tile_coords(p, tile, mb, nb);
         for (int pass = 0; pass < p.n_ops; ++pass) {
-          const int nkb = (p.K[pass] + UG_BK - 1) / UG_BK;
-          for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int nfs = (p.nslab[pass] + KS - 1) / KS;   // fat stages of this pass
+          for (int f = 0; f < nfs; ++f, ++it) {
             const int s = it % STAGES;
             const uint32_t ph = (it / STAGES) & 1u;
             mbar_wait(empty_bar(s), ph ^ 1u);
             const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + A_BYTES;
+            const int slab0 = f * KS;
             if (is_pa) {
               mbar_expect_tx(full_bar(s), STAGE_BYTES);   // A and B bytes; the B producer only adds transactions
-              if (!p.transA[pass]) {
-                tma_load_2d(sa, &p.tmA[pass], full_bar(s), kb * UG_BK, p.rowA[pass] + mb * BM);
-              } else {
-#pragma unroll
-                for (int ch = 0; ch < BM / 64; ++ch)
-                  tma_load_2d(sa + ch * 8192, &p.tmA[pass], full_bar(s), mb * BM + ch * 64, p.rowA[pass] + kb * UG_BK);
-              }
+              if (!p.transA[pass]) tma_load_3d(sa, &p.tmA[pass], full_bar(s), 0, p.rowA[pass] + mb * BM, slab0);
+              else                 tma_load_3d(sa, &p.tmA[pass], full_bar(s), 0, p.rowA[pass] + slab0 * UG_BK, mb * (BM / 64));
             } else {
-              if (!p.transB[pass]) {
-                tma_load_2d(sb, &p.tmB[pass], full_bar(s), kb * UG_BK, p.rowB[pass] + nb * BN);
-              } else {
-#pragma unroll
-                for (int ch = 0; ch < BN / 64; ++ch)
-                  tma_load_2d(sb + ch * 8192, &p.tmB[pass], full_bar(s), nb * BN + ch * 64, p.rowB[pass] + kb * UG_BK);
-              }
+              if (!p.transB[pass]) tma_load_3d(sb, &p.tmB[pass], full_bar(s), 0, p.rowB[pass] + nb * BN, slab0);
+              else                 tma_load_3d(sb, &p.tmB[pass], full_bar(s), 0, p.rowB[pass] + slab0 * UG_BK, nb * (BN / 64));
             }
           }
         }
@@ -275,22 +278,33 @@ umma_gemm_kernel(const __grid_constant__ UmmaGemmParams p, const __grid_constant
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
         uint32_t accumulate = 0;
         for (int pass = 0; pass < p.n_ops; ++pass) {
-          const int nkb = (p.K[pass] + UG_BK - 1) / UG_BK;
+          const int nslab = p.nslab[pass];
+          const int nfs = (nslab + KS - 1) / KS;
           const int tA = p.transA[pass], tB = p.transB[pass];
           const uint32_t idesc = make_idesc(BM, BN, tA, tB, pass == 1);
-          for (int kb = 0; kb < nkb; ++kb, ++it) {
+          for (int f = 0; f < nfs; ++f, ++it) {
             const int s = it % STAGES;
             const uint32_t ph = (it / STAGES) & 1u;
             mbar_wait(full_bar(s), ph);
             tc_fence_after();
             if (it == 0) trace_mark(p, 3);
             const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + A_BYTES;
+            const int slabs = min(KS, nslab - f * KS);   // the last stage of a pass may be partly beyond K (zero-filled)
 #pragma unroll
-            for (int k4 = 0; k4 < UG_BK / UG_UK; ++k4) {
-              const uint64_t da = tA ? make_smem_desc(sa + k4 * 2048, 8192, 1024) : make_smem_desc(sa + k4 * 32, 16, 1024);
-              const uint64_t db = tB ? make_smem_desc(sb + k4 * 2048, 8192, 1024) : make_smem_desc(sb + k4 * 32, 16, 1024);
-              tc_mma_bf16(tmem_d, da, db, idesc, accumulate);
-              accumulate = 1;
+            for (int sl = 0; sl < KS; ++sl) {
+              if (sl < slabs) {
+#pragma unroll
+                for (int k4 = 0; k4 < UG_BK / UG_UK; ++k4) {
+                  // K-major: slab sl = [rows][128 B] at sl * SLAB.  MN-major: [64-wide chunk][KS*64 k rows][128 B],
+                  // slab sl = rows sl*64.. of every chunk, chunks KS*8192 B apart (LBO).
+                  const uint64_t da = tA ? make_smem_desc(sa + sl * 8192 + k4 * 2048, KS * 8192, 1024)
+                                         : make_smem_desc(sa + sl * A_SLAB + k4 * 32, 16, 1024);
+                  const uint64_t db = tB ? make_smem_desc(sb + sl * 8192 + k4 * 2048, KS * 8192, 1024)
+                                         : make_smem_desc(sb + sl * B_SLAB + k4 * 32, 16, 1024);
+                  tc_mma_bf16(tmem_d, da, db, idesc, accumulate);
+                  accumulate = 1;
+                }
+              }
             }
             tc_commit(empty_bar(s));  // frees the smem stage once these MMAs have read it
           }
@@ -313,8 +327,7 @@ umma_gemm_kernel(const __grid_constant__ UmmaGemmParams p, const __grid_constant
       mbar_wait(tfull_bar(as), aph);
       tc_fence_after();
       if (tl == 0 && warp == 2 && lane == 0) trace_mark(p, 5);
-      const bool row_ok = (BM == 128) || lane < 16;
-      const int m = (BM == 128) ? mb * BM + q * 32 + lane : mb * BM + q * 16 + lane;
+      const int m = mb * BM + q * 32 + lane;
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
       constexpr int CH_PER_WARP = (BN / 32) / EPI_GROUPS;
       const int ch0 = ((warp - 2) >> 2) * CH_PER_WARP;   // which column half this warp drains
@@ -327,7 +340,7 @@ umma_gemm_kernel(const __grid_constant__ UmmaGemmParams p, const __grid_constant
         float acc[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(v[j]);
-        if (row_ok) epi_args.apply(epoch, m, n0, acc, coreM, coreN, augM, augN);
+        epi_args.apply(epoch, m, n0, acc, coreM, coreN, augM, augN);
       }
       tc_fence_before();
       __syncwarp();
@@ -366,11 +379,12 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+__device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
   // the transaction bytes are credited to the LEADER CTA's barrier (peer bit cleared)
   asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
-      "l"(map), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], "
+      "[%2];" ::"r"(dst),
+      "l"(map), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
 __device__ __forceinline__ void tc_commit_2sm(uint32_t bar) {
@@ -398,14 +412,18 @@ __device__ __forceinline__ uint32_t make_idesc_2sm(int bn, int transA, int trans
          ((uint32_t)transB << 16) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 }
 
-template <int BN, class Epi>
+template <int BN, int KS, class Epi>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UG_THREADS, 1)
 umma_gemm2_kernel(const __grid_constant__ UmmaGemmParams p, const __grid_constant__ Epi epi_args, int coreM, int coreN,
                   int augM, int augN) {
   constexpr int HB = BN / 2;                     // B columns staged by each CTA
-  constexpr int B_BYTES = HB * UG_BK * 2;
-  constexpr int STAGE_BYTES = UG_A_BYTES + B_BYTES;
+  constexpr int A_SLAB = UG_BM * UG_BK * 2;
+  constexpr int B_SLAB = HB * UG_BK * 2;
+  constexpr int A_BYTES = KS * A_SLAB;
+  constexpr int B_BYTES = KS * B_SLAB;
+  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr int STAGES = UG_SMEM_BUDGET / STAGE_BYTES;
+  static_assert(STAGES >= 2, "pipeline too shallow");
   constexpr int TMEM_COLS = 2 * BN;
   static_assert(HB % 64 == 0, "MN-major B halves come in 64-column chunks");
 
@@ -466,27 +484,18 @@ umma_gemm2_kernel(const __grid_constant__ UmmaGemmParams p, const __grid_constan
         const int m0 = mb * 256 + (int)cta * UG_BM;
         const int n0 = nb * BN + (int)cta * HB;
         for (int pass = 0; pass < p.n_ops; ++pass) {
-          const int nkb = (p.K[pass] + UG_BK - 1) / UG_BK;
-          for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int nfs = (p.nslab[pass] + KS - 1) / KS;
+          for (int f = 0; f < nfs; ++f, ++it) {
             const int s = it % STAGES;
             const uint32_t ph = (it / STAGES) & 1u;
             mbar_wait(empty_bar(s), ph ^ 1u);
             if (leader) mbar_expect_tx(full_bar(s), 2 * STAGE_BYTES);
-            const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + UG_A_BYTES;
-            if (!p.transA[pass]) {
-              tma_load_2d_2sm(sa, &p.tmA[pass], full_bar(s), kb * UG_BK, p.rowA[pass] + m0);
-            } else {
-#pragma unroll
-              for (int ch = 0; ch < UG_BM / 64; ++ch)
-                tma_load_2d_2sm(sa + ch * 8192, &p.tmA[pass], full_bar(s), m0 + ch * 64, p.rowA[pass] + kb * UG_BK);
-            }
-            if (!p.transB[pass]) {
-              tma_load_2d_2sm(sb, &p.tmB[pass], full_bar(s), kb * UG_BK, p.rowB[pass] + n0);
-            } else {
-#pragma unroll
-              for (int ch = 0; ch < HB / 64; ++ch)
-                tma_load_2d_2sm(sb + ch * 8192, &p.tmB[pass], full_bar(s), n0 + ch * 64, p.rowB[pass] + kb * UG_BK);
-            }
+            const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + A_BYTES;
+            const int slab0 = f * KS;
+            if (!p.transA[pass]) tma_load_3d_2sm(sa, &p.tmA[pass], full_bar(s), 0, p.rowA[pass] + m0, slab0);
+            else                 tma_load_3d_2sm(sa, &p.tmA[pass], full_bar(s), 0, p.rowA[pass] + slab0 * UG_BK, m0 / 64);
+            if (!p.transB[pass]) tma_load_3d_2sm(sb, &p.tmB[pass], full_bar(s), 0, p.rowB[pass] + n0, slab0);
+            else                 tma_load_3d_2sm(sb, &p.tmB[pass], full_bar(s), 0, p.rowB[pass] + slab0 * UG_BK, n0 / 64);
           }
         }
       }
@@ -503,21 +512,30 @@ umma_gemm2_kernel(const __grid_constant__ UmmaGemmParams p, const __grid_constan
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
         uint32_t accumulate = 0;
         for (int pass = 0; pass < p.n_ops; ++pass) {
-          const int nkb = (p.K[pass] + UG_BK - 1) / UG_BK;
+          const int nslab = p.nslab[pass];
+          const int nfs = (nslab + KS - 1) / KS;
           const int tA = p.transA[pass], tB = p.transB[pass];
           const uint32_t idesc = make_idesc_2sm(BN, tA, tB, pass == 1);
-          for (int kb = 0; kb < nkb; ++kb, ++it) {
+          for (int f = 0; f < nfs; ++f, ++it) {
             const int s = it % STAGES;
             const uint32_t ph = (it / STAGES) & 1u;
             mbar_wait(full_bar(s), ph);
             tc_fence_after();
-            const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + UG_A_BYTES;
+            const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + A_BYTES;
+            const int slabs = min(KS, nslab - f * KS);
 #pragma unroll
-            for (int k4 = 0; k4 < UG_BK / UG_UK; ++k4) {
-              const uint64_t da = tA ? make_smem_desc(sa + k4 * 2048, 8192, 1024) : make_smem_desc(sa + k4 * 32, 16, 1024);
-              const uint64_t db = tB ? make_smem_desc(sb + k4 * 2048, 8192, 1024) : make_smem_desc(sb + k4 * 32, 16, 1024);
-              tc_mma_bf16_2sm(tmem_d, da, db, idesc, accumulate);
-              accumulate = 1;
+            for (int sl = 0; sl < KS; ++sl) {
+              if (sl < slabs) {
+#pragma unroll
+                for (int k4 = 0; k4 < UG_BK / UG_UK; ++k4) {
+                  const uint64_t da = tA ? make_smem_desc(sa + sl * 8192 + k4 * 2048, KS * 8192, 1024)
+                                         : make_smem_desc(sa + sl * A_SLAB + k4 * 32, 16, 1024);
+                  const uint64_t db = tB ? make_smem_desc(sb + sl * 8192 + k4 * 2048, KS * 8192, 1024)
+                                         : make_smem_desc(sb + sl * B_SLAB + k4 * 32, 16, 1024);
+                  tc_mma_bf16_2sm(tmem_d, da, db, idesc, accumulate);
+                  accumulate = 1;
+                }
+              }
             }
             tc_commit_2sm(empty_bar(s));   // frees this stage in BOTH CTAs
           }
@@ -570,206 +588,6 @@ umma_gemm2_kernel(const __grid_constant__ UmmaGemmParams p, const __grid_constan
 }
 
 
-// =====================================================================================================
-// Multicast variant for SMALL contractions (mini-batch 256: M = 2-16 row blocks).  Such a GEMM is bound
-// by the ~38 B/clk at which one SM can pull operands through TMA, and every CTA of a row block pulls
-// the same 16 KB A tile.  Here CL CTAs (a cluster along N) share one row block: each fetches 1/CL of
-// the A tile and TMA-multicasts it into all CL shared memories, so per k-block a CTA moves
-// 16 KB / CL + BN * 128 B instead of 16 KB + BN * 128 B, and narrower tiles (BN = 32 / 64) spread the
-// mainloop and the epilogue over CL x more SMs.  Stage release is cluster-wide: a stage may be
-// overwritten by any peer's multicast, so its empty barrier counts one commit from every CTA.
-// =====================================================================================================
-__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
-                                               uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], "
-      "[%2], %5;" ::"r"(dst),
-      "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
-      : "memory");
-}
-__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
-  asm volatile(
-      "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
-      "h"(mask)
-      : "memory");
-}
-
-template <int BN, int CL, class Epi>
-__global__ void __launch_bounds__(UG_THREADS, 1)
-umma_gemm_mc_kernel(const __grid_constant__ UmmaGemmParams p, const __grid_constant__ Epi epi_args, int coreM, int coreN,
-                    int augM, int augN) {
-  constexpr int B_BYTES = BN * UG_BK * 2;
-  constexpr int STAGE_BYTES = UG_A_BYTES + B_BYTES;
-  constexpr int STAGES = UG_SMEM_BUDGET / STAGE_BYTES;
-  constexpr int TMEM_COLS = 2 * BN;
-  constexpr int SLICE_ROWS = UG_BM / CL;                 // rows of the A tile this CTA fetches for everyone
-  constexpr int EPI_GROUPS = (BN / 32) < 2 ? 1 : 2;      // column halves drained in parallel
-  constexpr uint16_t MASK = (uint16_t)((1u << CL) - 1u);
-  static_assert(CL == 2 || CL == 4, "cluster of 2 or 4 CTAs");
-  static_assert(BN == 32 || BN == 64, "narrow tiles only");
-
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
-  const uint32_t smem_base = smem_u32(smem);
-  const uint32_t bar_base = smem_u32(bars);
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
-  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int rank = (int)cluster_ctarank();
-  const int cluster_id = blockIdx.x / CL, n_clusters = gridDim.x / CL;
-  const int tiles_nc = (p.tiles_n + CL - 1) / CL;        // cluster tiles along N
-  const int n_ctiles = p.tiles_m * tiles_nc;
-
-  if (warp == 0 && lane == 0) {
-    for (int i = 0; i < p.n_ops; ++i) {
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmA[i]) : "memory");
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmB[i]) : "memory");
-    }
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), CL);   // one multicast commit from every CTA of the cluster
-    }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 4 * EPI_GROUPS);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"((uint32_t)TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();   // every peer's barriers exist before anyone multicasts into them
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  if (threadIdx.x == 0) pdl_launch_dependents();
-  pdl_wait();
-
-  if (warp == 0 || warp == UG_WARP_PB) {
-    // ===================== TMA producers (A slice multicast / own B) =====================
-    const bool is_pa = warp == 0;
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (int ct = cluster_id; ct < n_ctiles; ct += n_clusters) {
-        const int mb = ct % p.tiles_m;
-        const int nb = (ct / p.tiles_m) * CL + rank;
-        for (int pass = 0; pass < p.n_ops; ++pass) {
-          const int nkb = (p.K[pass] + UG_BK - 1) / UG_BK;
-          for (int kb = 0; kb < nkb; ++kb, ++it) {
-            const int s = it % STAGES;
-            const uint32_t ph = (it / STAGES) & 1u;
-            mbar_wait(empty_bar(s), ph ^ 1u);
-            const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + UG_A_BYTES;
-            const int r0 = rank * SLICE_ROWS;           // this CTA's slice of the 128 smem rows of A
-            if (is_pa) {
-              mbar_expect_tx(full_bar(s), STAGE_BYTES);   // full A tile (CL slices) + own B tile
-              if (!p.transA[pass]) {
-                tma_load_2d_mc(sa + r0 * 128, &p.tmA[pass], full_bar(s), kb * UG_BK, p.rowA[pass] + mb * UG_BM + r0, MASK);
-              } else {  // MN-major A: smem rows = (64-wide m chunk, k row); a slice is a k-row range of one chunk
-                tma_load_2d_mc(sa + r0 * 128, &p.tmA[pass], full_bar(s), mb * UG_BM + (r0 / 64) * 64,
-                               p.rowA[pass] + kb * UG_BK + (r0 % 64), MASK);
-              }
-            } else {
-              if (!p.transB[pass]) {
-                tma_load_2d(sb, &p.tmB[pass], full_bar(s), kb * UG_BK, p.rowB[pass] + nb * BN);
-              } else {
-#pragma unroll
-                for (int ch = 0; ch < BN / 64; ++ch)
-                  tma_load_2d(sb + ch * 8192, &p.tmB[pass], full_bar(s), nb * BN + ch * 64, p.rowB[pass] + kb * UG_BK);
-              }
-            }
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      uint32_t it = 0, tl = 0;
-      for (int ct = cluster_id; ct < n_ctiles; ct += n_clusters, ++tl) {
-        const int as = tl & 1;
-        const uint32_t aph = (tl >> 1) & 1u;
-        mbar_wait(tempty_bar(as), aph ^ 1u);
-        tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
-        uint32_t accumulate = 0;
-        for (int pass = 0; pass < p.n_ops; ++pass) {
-          const int nkb = (p.K[pass] + UG_BK - 1) / UG_BK;
-          const int tA = p.transA[pass], tB = p.transB[pass];
-          const uint32_t idesc = make_idesc(UG_BM, BN, tA, tB, pass == 1);
-          for (int kb = 0; kb < nkb; ++kb, ++it) {
-            const int s = it % STAGES;
-            const uint32_t ph = (it / STAGES) & 1u;
-            mbar_wait(full_bar(s), ph);
-            tc_fence_after();
-            const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + UG_A_BYTES;
-#pragma unroll
-            for (int k4 = 0; k4 < UG_BK / UG_UK; ++k4) {
-              const uint64_t da = tA ? make_smem_desc(sa + k4 * 2048, 8192, 1024) : make_smem_desc(sa + k4 * 32, 16, 1024);
-              const uint64_t db = tB ? make_smem_desc(sb + k4 * 2048, 8192, 1024) : make_smem_desc(sb + k4 * 32, 16, 1024);
-              tc_mma_bf16(tmem_d, da, db, idesc, accumulate);
-              accumulate = 1;
-            }
-            tc_commit_mc(empty_bar(s), MASK);   // this CTA is done with stage s: tell every producer of the cluster
-          }
-        }
-        tc_commit(tfull_bar(as));
-      }
-    }
-  } else if (warp < UG_WARP_PB && (warp - 2) / 4 < EPI_GROUPS) {
-    // ===================== epilogue warps =====================
-    const int q = warp & 3;
-    uint32_t epoch = 0;
-    if constexpr (!Epi::kIsUpdate) epoch = epi_args.e.rng.epoch + (epi_args.e.rng.epoch_ptr ? *epi_args.e.rng.epoch_ptr : 0u);
-    uint32_t tl = 0;
-    for (int ct = cluster_id; ct < n_ctiles; ct += n_clusters, ++tl) {
-      const int mb = ct % p.tiles_m;
-      const int nb = (ct / p.tiles_m) * CL + rank;
-      const int as = tl & 1;
-      const uint32_t aph = (tl >> 1) & 1u;
-      mbar_wait(tfull_bar(as), aph);
-      tc_fence_after();
-      const int m = mb * UG_BM + q * 32 + lane;
-      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
-      constexpr int CH_PER_WARP = (BN / 32) / EPI_GROUPS;
-      const int ch0 = ((warp - 2) >> 2) * CH_PER_WARP;
-#pragma unroll 1
-      for (int ch = ch0; ch < ch0 + CH_PER_WARP; ++ch) {
-        const int n0 = nb * BN + ch * 32;
-        if (n0 >= p.N) break;  // warp-uniform (also the padding CTAs of the last cluster)
-        uint32_t v[32];
-        tc_ld32(trow + ch * 32, v);
-        float acc[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(v[j]);
-        epi_args.apply(epoch, m, n0, acc, coreM, coreN, augM, augN);
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(as));
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();   // peers may still multicast-commit into this CTA's barriers until they are done
-  if (warp == 1) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
-                 : "memory");
-  }
-}
-
 struct UmmaActEpi {
   static constexpr bool kIsUpdate = false;
   dbn_act_epilogue e;
@@ -802,16 +620,22 @@ inline PFN_encodeTiled get_encode_fn() {
   return fn;
 }
 
-// Tensor map over a bf16 operand stored [rows, ld].  valid_cols / valid_rows bound the region TMA may
-// read; everything outside is zero-filled, which is what makes ragged shapes and short batches exact.
-inline int make_operand_map(CUtensorMap* map, const dbn_mat& X, uint64_t valid_cols, uint64_t valid_rows, uint32_t box_rows) {
+// 3-D tensor map over a bf16 operand stored [rows, ld] (ld a multiple of 64 elements):
+//   dim0 = 64 elements (one 128-byte slab row), dim1 = stored rows, dim2 = 64-column slab index (stride 128 B).
+// K-major operand : dim1 = M/N rows (valid_rows), dim2 = k-slabs (ceil(K/64));   box {64, tile rows, KS}
+// MN-major operand: dim1 = k rows (valid_rows),   dim2 = 64-wide M/N chunks;     box {64, KS*64, tile chunks}
+// Out-of-range rows and slabs are zero-filled by TMA.  Columns between an extent and the next multiple of 64
+// are READ: M/N tails only feed accumulator rows/columns the epilogue masks, but for a K tail the padding
+// columns of at least one operand of the pair must be zero and the other finite (weight shadows are zero there).
+inline int make_operand_map(CUtensorMap* map, const dbn_mat& X, uint64_t valid_rows, uint64_t n_slabs, uint32_t box_rows,
+                            uint32_t box_slabs) {
   PFN_encodeTiled enc = get_encode_fn();
   if (!enc) return fail(DBN_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available%s%s");
-  cuuint64_t gdim[2] = {valid_cols, valid_rows};
-  cuuint64_t gstride[1] = {(cuuint64_t)X.ld * 2};
-  cuuint32_t box[2] = {64, box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, X.ptr, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  cuuint64_t gdim[3] = {64, valid_rows, n_slabs};
+  cuuint64_t gstride[2] = {(cuuint64_t)X.ld * 2, 128};
+  cuuint32_t box[3] = {64, box_rows, box_slabs};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, X.ptr, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     char buf[64];
@@ -821,15 +645,20 @@ inline int make_operand_map(CUtensorMap* map, const dbn_mat& X, uint64_t valid_c
   return DBN_OK;
 }
 
-inline bool umma_operand_ok(const dbn_mat& X) {
-  return X.ptr != nullptr && X.dtype == DBN_BF16 && (X.ld % 8) == 0 && (reinterpret_cast<uintptr_t>(X.ptr) % 16) == 0;
+inline bool umma_operand_ok(const dbn_mat& X, int cols) {
+  // pitch: multiple of 64 elements and wide enough for every 64-column slab the 3-D map addresses; base 16-byte
+  // aligned (TMA), 128-byte aligned in practice -- column-offset views (row blocks of P0 in the data-parallel
+  // path) start at multiples of 64 columns
+  return X.ptr != nullptr && X.dtype == DBN_BF16 && (X.ld % 64) == 0 && X.ld >= (int)align_up((size_t)cols, 64) &&
+         (reinterpret_cast<uintptr_t>(X.ptr) % 16) == 0;
 }
 
 // The tensor-core path takes bf16 operands with 16-byte aligned rows and is worth its 128 x BN tiles
 // only for contractions that fill at least part of one; everything else runs on the FP32 SIMT kernel.
 inline bool umma_gemm_supported(int M, int N, const dbn_operands* ops, int n_ops) {
   for (int i = 0; i < n_ops; ++i) {
-    if (!umma_operand_ok(ops[i].A) || !umma_operand_ok(ops[i].B)) return false;
+    if (!umma_operand_ok(ops[i].A, ops[i].transA ? M : ops[i].K)) return false;
+    if (!umma_operand_ok(ops[i].B, ops[i].transB ? N : ops[i].K)) return false;
     if (ops[i].K < 32) return false;
   }
   return M >= 64 && N >= 32;
@@ -853,14 +682,19 @@ inline int umma_num_sms() {
   return std::max(2, (n - umma_sm_reserve()) & ~1);
 }
 
-template <int BM, int BN, class Epi>
+// slabs per pipeline stage: as many as keep >= 2 stages in the 192 KB ring (and a 256-row TMA box)
+constexpr int umma_ks(int bm, int bn) { return (bm + bn) * 128 * 4 * 2 <= UG_SMEM_BUDGET ? 4 : 2; }
+
+template <int BN, class Epi>
 inline int umma_launch(cudaStream_t st, UmmaGemmParams& p, const Epi& epi, int coreM, int coreN, int augM, int augN) {
-  constexpr int STAGE_BYTES = BM * UG_BK * 2 + BN * UG_BK * 2;
-  constexpr int STAGES = (UG_SMEM_BUDGET / STAGE_BYTES) > 12 ? 12 : (UG_SMEM_BUDGET / STAGE_BYTES);
+  constexpr int BM = UG_BM;
+  constexpr int KS = umma_ks(BM, BN);
+  constexpr int STAGE_BYTES = KS * (BM + BN) * UG_BK * 2;
+  constexpr int STAGES = (UG_SMEM_BUDGET / STAGE_BYTES) > 8 ? 8 : (UG_SMEM_BUDGET / STAGE_BYTES);
   constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + (2 * STAGES + 4) * 8 + 16;
   static bool attr_set = false;
   if (!attr_set) {
-    DBN_CUDA_OK(cudaFuncSetAttribute(umma_gemm_kernel<BM, BN, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    DBN_CUDA_OK(cudaFuncSetAttribute(umma_gemm_kernel<BN, KS, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     attr_set = true;
   }
   p.tiles_m = ceil_div(p.M, BM);
@@ -869,20 +703,22 @@ inline int umma_launch(cudaStream_t st, UmmaGemmParams& p, const Epi& epi, int c
   p.group_m = std::max(1, std::min(p.tiles_m, 16));
   const int n_tiles = p.tiles_m * p.tiles_n;
   const int grid = std::min(n_tiles, umma_num_sms());
-  DBN_CUDA_OK(launch_pdl(umma_gemm_kernel<BM, BN, Epi>, dim3(grid), dim3(UG_THREADS), SMEM, st, p, epi, coreM, coreN, augM,
-                         augN));
+  DBN_CUDA_OK(launch_pdl(umma_gemm_kernel<BN, KS, Epi>, dim3(grid), dim3(UG_THREADS), SMEM, st, p, epi, coreM, coreN,
+                         augM, augN));
   DBN_LAUNCH_CHECK();
   return DBN_OK;
 }
 
+constexpr int UG2_KS = 2;   // CTA-pair kernel: 2 slabs (K = 128) per stage, 64 KB per CTA, 3 stages
+
 template <int BN, class Epi>
 inline int umma_launch2(cudaStream_t st, UmmaGemmParams& p, const Epi& epi, int coreM, int coreN, int augM, int augN) {
-  constexpr int STAGE_BYTES = UG_A_BYTES + (BN / 2) * UG_BK * 2;
+  constexpr int STAGE_BYTES = UG2_KS * (UG_BM + BN / 2) * UG_BK * 2;
   constexpr int STAGES = UG_SMEM_BUDGET / STAGE_BYTES;
   constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + (2 * STAGES + 4) * 8 + 16;
   static bool attr_set = false;
   if (!attr_set) {
-    DBN_CUDA_OK(cudaFuncSetAttribute(umma_gemm2_kernel<BN, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    DBN_CUDA_OK(cudaFuncSetAttribute(umma_gemm2_kernel<BN, UG2_KS, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     attr_set = true;
   }
   p.tiles_m = ceil_div(p.M, 256);
@@ -890,72 +726,10 @@ inline int umma_launch2(cudaStream_t st, UmmaGemmParams& p, const Epi& epi, int 
   p.group_m = std::max(1, std::min(p.tiles_m, 8));
   const int n_tiles = p.tiles_m * p.tiles_n;
   const int clusters = std::min(n_tiles, umma_num_sms() / 2);
-  DBN_CUDA_OK(launch_pdl(umma_gemm2_kernel<BN, Epi>, dim3(clusters * 2), dim3(UG_THREADS), SMEM, st, p, epi, coreM, coreN, augM,
-                         augN));
+  DBN_CUDA_OK(launch_pdl(umma_gemm2_kernel<BN, UG2_KS, Epi>, dim3(clusters * 2), dim3(UG_THREADS), SMEM, st, p, epi, coreM,
+                         coreN, augM, augN));
   DBN_LAUNCH_CHECK();
   return DBN_OK;
-}
-
-template <int BN, int CL, class Epi>
-inline int umma_launch_mc(cudaStream_t st, UmmaGemmParams& p, const Epi& epi, int coreM, int coreN, int augM, int augN) {
-  constexpr int STAGE_BYTES = UG_A_BYTES + BN * UG_BK * 2;
-  constexpr int STAGES = UG_SMEM_BUDGET / STAGE_BYTES;
-  constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + (2 * STAGES + 4) * 8 + 16;
-  static bool attr_set = false;
-  if (!attr_set) {
-    DBN_CUDA_OK(cudaFuncSetAttribute(umma_gemm_mc_kernel<BN, CL, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    attr_set = true;
-  }
-  p.tiles_m = ceil_div(p.M, UG_BM);
-  p.tiles_n = ceil_div(p.N, BN);
-  p.group_m = 1;
-  const int n_ctiles = p.tiles_m * ceil_div(p.tiles_n, CL);
-  const int clusters = std::min(n_ctiles, umma_num_sms() / CL);
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(clusters * CL);
-  cfg.blockDim = dim3(UG_THREADS);
-  cfg.dynamicSmemBytes = SMEM;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[2];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
-  cfg.attrs = attr;
-  cfg.numAttrs = 2;
-  DBN_CUDA_OK(cudaLaunchKernelEx(&cfg, umma_gemm_mc_kernel<BN, CL, Epi>, p, epi, coreM, coreN, augM, augN));
-  DBN_LAUNCH_CHECK();
-  return DBN_OK;
-}
-
-// Opt-in (DBN_B200_UMMA_MC=1).  Measured on B200 (profiles/r01_notes.md): the multicast variant is correct
-// but not faster at mini-batch 256 -- the small contractions are bound by the rate at which ONE SM's
-// shared memory can be filled (~38 B/clk, the same figure the 4096-wide kernels show), and a multicast
-// A tile still lands in full in every CTA, so only L2 requests are saved, not fill bytes.
-inline int& umma_m64_flag() {
-  static int v = -1;
-  return v;
-}
-inline bool umma_use_m64() {
-  int& v = umma_m64_flag();
-  if (v < 0) {
-    const char* e = getenv("DBN_B200_UMMA_M64");
-    v = (e != nullptr && e[0] == '1') ? 1 : 0;   // opt-in: measured slower than 128-row tiles (profiles/r01_notes.md)
-  }
-  return v == 1;
-}
-inline int& umma_mc_flag() {
-  static int v = -1;
-  return v;
-}
-inline bool umma_use_mc() {
-  int& v = umma_mc_flag();
-  if (v < 0) {
-    const char* e = getenv("DBN_B200_UMMA_MC");
-    v = (e != nullptr && e[0] == '1') ? 1 : 0;
-  }
-  return v == 1;
 }
 
 inline bool umma_use_2cta() {
@@ -992,45 +766,24 @@ inline int umma_gemm_run(cudaStream_t st, int M, int N, int augM, int augN, cons
   // Large outputs (256 x 256 tiles for at least half of the SM pairs) run on CTA pairs: a third fewer
   // operand bytes per MAC out of L2.  B boxes then cover half a tile.
   const bool two_cta = umma_use_2cta() && (long)ceil_div(p.M, 256) * ceil_div(p.N, 256) >= sms / 4;
-  // Small outputs (fewer 128 x 64 tiles than SMs: the mini-batch-256 regime) are TMA-pull bound per SM:
-  // run them on clusters that multicast the shared A tile, with tiles as narrow as B's layout allows.
-  bool any_transB = false;
-  for (int i = 0; i < n_ops; ++i) any_transB |= ops[i].transB != 0;
-  const int mc_bn = any_transB ? 64 : 32;
-  const int mc_tn = ceil_div(p.N, mc_bn);
-  const bool small = !two_cta && (long)tm * ceil_div(p.N, 64) <= sms;
-  const bool mc = umma_use_mc() && small && mc_tn >= 2;
-  const int mc_cl = mc_tn >= 4 ? 4 : 2;
-  // Opt-in for small outputs: 64-row tiles (UMMA M = 64) as narrow as B's layout allows.  Measured: not
-  // faster -- a pipeline stage completes every ~640 cycles whether it carries 12 KB or 24 KB (a floor of
-  // ~320 cycles per bulk-tensor copy), so halving the tile only doubles the L2 traffic.
-  const bool m64 = small && !mc && umma_use_m64();
-  if (mc || m64) bn = mc_bn;
-  const int a_box_rows = mc ? UG_BM / mc_cl : (m64 ? 64 : UG_BM);   // multicast: each CTA fetches one slice of the A tile
+  const int bm = UG_BM;
+  const int ks = two_cta ? UG2_KS : umma_ks(bm, bn);
+  const int b_rows = two_cta ? 128 : bn;        // B rows (K-major) / columns (MN-major) staged per CTA
   for (int i = 0; i < n_ops; ++i) {
     const dbn_operands& o = ops[i];
     p.K[i] = o.K;
+    p.nslab[i] = ceil_div(o.K, UG_BK);
     p.transA[i] = o.transA; p.transB[i] = o.transB;
     p.rowA[i] = o.row0_A; p.rowB[i] = o.row0_B;
-    if (!o.transA) DBN_TRY(make_operand_map(&p.tmA[i], o.A, o.K, (uint64_t)o.row0_A + p.M, a_box_rows));
-    else           DBN_TRY(make_operand_map(&p.tmA[i], o.A, p.M, (uint64_t)o.row0_A + o.K, mc ? a_box_rows : 64));
-    if (!o.transB) DBN_TRY(make_operand_map(&p.tmB[i], o.B, o.K, (uint64_t)o.row0_B + p.N, two_cta ? 128 : bn));
-    else           DBN_TRY(make_operand_map(&p.tmB[i], o.B, p.N, (uint64_t)o.row0_B + o.K, 64));
+    if (!o.transA) DBN_TRY(make_operand_map(&p.tmA[i], o.A, (uint64_t)o.row0_A + p.M, p.nslab[i], bm, ks));
+    else           DBN_TRY(make_operand_map(&p.tmA[i], o.A, (uint64_t)o.row0_A + o.K, ceil_div(p.M, 64), ks * 64, bm / 64));
+    if (!o.transB) DBN_TRY(make_operand_map(&p.tmB[i], o.B, (uint64_t)o.row0_B + p.N, p.nslab[i], b_rows, ks));
+    else           DBN_TRY(make_operand_map(&p.tmB[i], o.B, (uint64_t)o.row0_B + o.K, ceil_div(p.N, 64), ks * 64, b_rows / 64));
   }
   if (two_cta) return umma_launch2<256, Epi>(st, p, epi, M, N, augM, augN);
-  if (mc) {
-    if (mc_bn == 32) return mc_cl == 4 ? umma_launch_mc<32, 4, Epi>(st, p, epi, M, N, augM, augN)
-                                       : umma_launch_mc<32, 2, Epi>(st, p, epi, M, N, augM, augN);
-    return mc_cl == 4 ? umma_launch_mc<64, 4, Epi>(st, p, epi, M, N, augM, augN)
-                      : umma_launch_mc<64, 2, Epi>(st, p, epi, M, N, augM, augN);
-  }
-  if (m64) {
-    if (bn == 32) return umma_launch<64, 32, Epi>(st, p, epi, M, N, augM, augN);
-    return umma_launch<64, 64, Epi>(st, p, epi, M, N, augM, augN);
-  }
-  if (bn == 256) return umma_launch<128, 256, Epi>(st, p, epi, M, N, augM, augN);
-  if (bn == 128) return umma_launch<128, 128, Epi>(st, p, epi, M, N, augM, augN);
-  return umma_launch<128, 64, Epi>(st, p, epi, M, N, augM, augN);
+  if (bn == 256) return umma_launch<256, Epi>(st, p, epi, M, N, augM, augN);
+  if (bn == 128) return umma_launch<128, Epi>(st, p, epi, M, N, augM, augN);
+  return umma_launch<64, Epi>(st, p, epi, M, N, augM, augN);
 }
 
 inline int umma_gemm_act(cudaStream_t st, int M, int N, const dbn_operands* ops, int n_ops, const dbn_act_epilogue& e) {

@@ -171,8 +171,8 @@ class DeviceRbm:
     # -- operand staging ---------------------------------------------------------------------------
     def alloc_staged(self, n, cols):
         """Uninitialised operand buffer for n rows of `cols` features in this precision's layout."""
-        if self.prec == L.PREC_BF16:
-            return torch.empty(n, bf16_pitch(cols), dtype=torch.bfloat16, device=self.device)
+        if self.prec == L.PREC_BF16:   # zero padding: the tensor-core path reads K tails up to the next 64 columns
+            return torch.zeros(n, bf16_pitch(cols), dtype=torch.bfloat16, device=self.device)
         return torch.empty(n, cols, dtype=torch.float32, device=self.device)
 
     def stage(self, Xd, idx=None, out=None, dropout=None):
@@ -220,7 +220,7 @@ class DeviceRbm:
             m = min(_CHUNK, n - s)
             xs = Xd[s:s + m]
             xop = self.stage(xs) if self.prec == L.PREC_BF16 else xs
-            hm = torch.empty(m, hld, dtype=hdt, device=self.device)
+            hm = torch.zeros(m, hld, dtype=hdt, device=self.device)   # operand of the next contraction: finite padding
             self.hidden_means(xop, 0, m, hm)
             rec = torch.empty(m, self.V, dtype=torch.float32, device=self.device)
             self.visible_means(hm, m, rec)

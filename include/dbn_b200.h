@@ -156,10 +156,6 @@ uint64_t dbn_launch_count(void);
 /* Keep n_sms SMs free of the persistent contraction kernels (0 = use all; default).  Data-parallel
  * callers set this so the collective's kernels can run next to the contraction they overlap with. */
 int dbn_set_sm_reserve(int n_sms);
-/* Debug / experiments: flag 0 = route small contractions to the TMA-multicast cluster kernel (default
- * off; also DBN_B200_UMMA_MC=1); flag 1 = 64-row (UMMA M = 64) tiles for small contractions (default off;
- * also DBN_B200_UMMA_M64=1).  Both variants are covered by the parity tests; neither is faster. */
-int dbn_debug_set_flag(int which, int value);
 /* Debug: when device_buf != NULL every single-CTA tcgen05 contraction writes 16 int64 phase timestamps
  * per CTA to device_buf[blockIdx.x * 16 ...]: [0] entry (globaltimer ns); [1..7] clock64 at entry /
  * setup done / first operands / mainloop issued / accumulator ready / epilogue done / exit; [8] ns when
@@ -177,7 +173,11 @@ int dbn_philox_uniforms_host(uint64_t seed, uint32_t stream, uint32_t epoch, uin
 /* ---- fused contractions (building blocks of every path-level call) ----------------------- */
 /* acc = ops[0] - ops[1] (n_ops = 1 or 2), M x N output, activation epilogue.
  * precision = DBN_PREC_FP32: operands fp32, SIMT FFMA kernel.
- * precision = DBN_PREC_BF16: operands bf16, TMA + tcgen05.mma kernel (ld % 8 == 0, 16B-aligned). */
+ * precision = DBN_PREC_BF16: operands bf16, TMA + tcgen05.mma kernel.  Operand contract: base 128-byte
+ *   aligned, ld a multiple of 64 elements and >= the extent rounded up to 64; the columns between an
+ *   operand's K extent and the next multiple of 64 are read, so they must be finite in both operands of a
+ *   pair and zero in at least one (the engine zero-initialises every staged buffer and weight shadow;
+ *   only the ones column lives there).  Anything else runs on the FP32 SIMT kernel. */
 int dbn_gemm_act(void* stream, int precision, int M, int N, const dbn_operands* ops, int n_ops,
                  const dbn_act_epilogue* epi);
 
@@ -248,14 +248,14 @@ int dbn_rbm_fit_epoch_persistent(void* stream, const dbn_rbm_step_args* tmpl, co
                                  int batch_size);
 
 /* The t = 0 hidden phase (means P0 + first sample) of the step described by args, restricted to hidden
- * units [h0, h1) (h0 % 8 == 0): it needs only rows [h0, h1) of W, so a data-parallel caller can start
+ * units [h0, h1) (h0 % 64 == 0): it needs only rows [h0, h1) of W, so a data-parallel caller can start
  * it as soon as that row block of W has been updated, while later blocks are still being all-reduced.
  * Follow with dbn_rbm_cd_step(flags |= DBN_STEP_SKIP_FIRST_HIDDEN). */
 int dbn_rbm_first_hidden(void* stream, const dbn_rbm_step_args* args, int h0, int h1);
 
 /* Rows [h0, h1) of the raw delta (dW | dc) of the chain left in the workspace by a
  * dbn_rbm_cd_step(flags = DBN_STEP_SKIP_UPDATE) with the same args; h1 == H also writes the db row H.
- * h0 % 8 == 0.  Lets the caller pipeline delta production with the all-reduce of earlier rows. */
+ * h0 % 64 == 0.  Lets the caller pipeline delta production with the all-reduce of earlier rows. */
 int dbn_rbm_delta_rows(void* stream, const dbn_rbm_step_args* args, int h0, int h1);
 
 /* Parameter update from a summed raw delta buffer (layout [(H+1), ld] = dW | dc ; db):

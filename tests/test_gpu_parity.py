@@ -25,19 +25,6 @@ def load(golden_dir, name):
 # ---------------------------------------------------------------------------------------------------
 # fused contraction building blocks against NumPy
 # ---------------------------------------------------------------------------------------------------
-@pytest.fixture(params=["default", "m64", "multicast"])
-def umma_variant(request):
-    """Dispatch policies of the tcgen05 path for small outputs: 128-row tiles (default) and the two opt-in
-    experiments, 64-row tiles and the TMA-multicast cluster kernel.  All must stay correct (flags are toggled
-    through the library)."""
-    lib = G.lib()
-    lib.dbn_debug_set_flag(0, 1 if request.param == "multicast" else 0)
-    lib.dbn_debug_set_flag(1, 1 if request.param == "m64" else 0)
-    yield request.param
-    lib.dbn_debug_set_flag(0, 0)
-    lib.dbn_debug_set_flag(1, 0)
-
-
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 @pytest.mark.parametrize("M,N,K,tA,tB", [(70, 50, 33, 0, 0), (64, 64, 64, 0, 1), (130, 257, 96, 1, 1),
                                          (256, 512, 384, 0, 0), (256, 384, 512, 0, 1), (384, 520, 256, 1, 1),
@@ -45,7 +32,7 @@ def umma_variant(request):
                                          # >= 74 tiles of 256x256: the cta_group::2 kernel (BF16 mode)
                                          (2304, 2200, 320, 0, 0), (2304, 2200, 320, 0, 1), (2200, 2304, 192, 1, 1),
                                          (2100, 2500, 130, 1, 0)])
-def test_gemm_act_matches_numpy(precision, M, N, K, tA, tB, umma_variant):
+def test_gemm_act_matches_numpy(precision, M, N, K, tA, tB):
     import ctypes as C
     import torch
     from dbn_b200 import _lib as L, engine as E

@@ -59,8 +59,8 @@ for (V, H) in [(784, 500), (500, 2000)]:
     a = layer._step_args(Xop, 1, 0.01 / 256, ws, 1, None)
     a.B, a.row0 = B, 0
     L.check(lib.dbn_rbm_cd_step(E.stream_ptr(), C.byref(a)))
-    hm = torch.empty(B, E.bf16_pitch(H), dtype=torch.bfloat16, device=dev)
-    vm = torch.empty(B, E.bf16_pitch(V), dtype=torch.bfloat16, device=dev)
+    hm = torch.zeros(B, E.bf16_pitch(H), dtype=torch.bfloat16, device=dev)
+    vm = torch.zeros(B, E.bf16_pitch(V), dtype=torch.bfloat16, device=dev)
     raw = torch.zeros(H + 1, (V + 1 + 3) // 4 * 4, dtype=torch.float32, device=dev)
     a.raw_delta = E.mat(raw)
     probe("v->h %dx%d K=%d" % (B, H, V), lambda: layer.hidden_means(Xop, 0, B, hm))
