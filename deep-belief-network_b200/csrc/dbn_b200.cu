@@ -92,6 +92,7 @@ struct MlpWorkspace {
   dbn_mat act[DBN_MAX_LAYERS];        // a_1..a_L
   dbn_mat delta[DBN_MAX_LAYERS];      // delta_1..delta_L
   dbn_mat Z, dO;                      // head scores/outputs, head delta (fp32)
+  dbn_mat dOb;                        // bf16 copy of the head delta (BF16 mode: operand of the head-gradient contraction)
 };
 size_t mlp_ws_layout(int precision, int Bmax, int n_in, const int32_t* dims, int L, int n_out, char* base,
                      MlpWorkspace* ws) {
@@ -110,6 +111,7 @@ size_t mlp_ws_layout(int precision, int Bmax, int n_in, const int32_t* dims, int
   for (int l = 0; l < L; ++l) w.delta[l] = carve(dims[l], dt, false);
   w.Z = carve(n_out, DBN_F32, false);
   w.dO = carve(n_out, DBN_F32, false);
+  w.dOb = (precision == DBN_PREC_BF16) ? carve(n_out, DBN_BF16, false) : null_mat();
   if (ws) *ws = w;
   return off;
 }
@@ -451,7 +453,8 @@ int dbn_mlp_train_step(void* stream, const dbn_mlp_step_args* a) {
     DBN_CUDA_OK(launch_pdl(head_fused_kernel, dim3(ceil_div(B * 32, 256)), dim3(256), 0, st, ws.act[L - 1], HL,
                            (const float*)a->Wo, a->ldwo, (const float*)a->bo, B, a->n_out, a->head,
                            a->Y + (size_t)a->row0 * a->ldy, a->ldy, static_cast<float*>(ws.Z.ptr), ws.Z.ld,
-                           static_cast<float*>(ws.dO.ptr), ws.dO.ld, a->loss_rows));
+                           static_cast<float*>(ws.dO.ptr), ws.dO.ld, static_cast<bf16*>(ws.dOb.ptr), ws.dOb.ld,
+                           a->loss_rows));
     DBN_LAUNCH_CHECK();
   } else {
     // head scores (dbn/models.py:601 / :703), strict FP32
@@ -479,7 +482,21 @@ int dbn_mlp_train_step(void* stream, const dbn_mlp_step_args* a) {
   }
 
   // ---- gradients + decayed SGD update (dbn/models.py:508-513, :454-465) ----
-  {
+  if (tc && a->n_out <= 32) {
+    // narrow head in BF16 mode: the same tcgen05 contraction as the hidden layers (M = n_out rows of a
+    // 128-row tile), operands = bf16 copy of the head delta and the last activations with their ones column
+    dbn_operands o = make_ops(ws.dOb, 1, 0, ws.act[L - 1], 1, 0, B);
+    dbn_update_epilogue u = blank_upd();
+    u.W = a->Wo; u.ldw = a->ldwo; u.vecM = a->bo; u.decay = a->decay; u.scale = -a->lr_over_bs;
+    if (raw) u.raw = a->raw_grads[L];
+    DBN_TRY(dbn_gemm_update(stream, a->precision, a->n_out, HL, 0, 1, &o, 1, &u));
+  } else if (a->n_out <= 32 && (size_t)B * a->n_out * sizeof(float) <= 48 * 1024) {   // narrow head, FP32 mode
+    float* rawp = raw ? static_cast<float*>(a->raw_grads[L].ptr) : nullptr;
+    DBN_CUDA_OK(launch_pdl(head_grad_kernel, dim3(ceil_div(HL + 1, 128)), dim3(128), (size_t)B * a->n_out * sizeof(float), st,
+                           ws.act[L - 1], HL, (const float*)ws.dO.ptr, ws.dO.ld, B, a->n_out, a->Wo, a->ldwo, a->bo, a->decay,
+                           -a->lr_over_bs, rawp, raw ? a->raw_grads[L].ld : 0));
+    DBN_LAUNCH_CHECK();
+  } else {
     dbn_operands o = make_ops(ws.dO, 1, 0, ws.act[L - 1], 1, 0, B);
     dbn_update_epilogue u = blank_upd();
     u.W = a->Wo; u.ldw = a->ldwo; u.vecM = a->bo; u.decay = a->decay; u.scale = -a->lr_over_bs;

@@ -136,33 +136,73 @@ __global__ void __launch_bounds__(128) head_delta_kernel(int head, float* Z, int
 
 
 // Fused output head for narrow heads (C <= 32): one warp per sample row computes the C scores
-// z = a W_o^T + b_o (lanes stride over K, coalesced on both a and the rows of W_o), then
-// softmax / identity, delta = out - y and the per-row loss -- dbn/models.py:594-626, :696-720 in one
-// launch instead of a skinny GEMM (4 CTAs at C = 10) plus a row kernel.
+// z = a W_o^T + b_o, then softmax / identity, delta = out - y and the per-row loss --
+// dbn/models.py:594-626, :696-720 in one launch instead of a skinny GEMM (4 CTAs at C = 10) plus a row kernel.
+// Each lane owns 8 consecutive k of every 256-wide slab of K: one 16-byte load of the activations and two
+// float4 loads per class row, all independent, so a slab puts 1 + 2C loads in flight per lane.
+__device__ __forceinline__ void head_load8(const dbn_mat& A, int row, int k, float v[8]) {
+  if (A.dtype == DBN_F32) {
+    const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(A.ptr) + (size_t)row * A.ld + k);
+    const float4 t0 = p[0], t1 = p[1];
+    v[0] = t0.x; v[1] = t0.y; v[2] = t0.z; v[3] = t0.w; v[4] = t1.x; v[5] = t1.y; v[6] = t1.z; v[7] = t1.w;
+  } else {
+    const uint4 t = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(A.ptr) + (size_t)row * A.ld + k);
+    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[j]);
+      v[2 * j] = __low2float(h);
+      v[2 * j + 1] = __high2float(h);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) head_fused_kernel(dbn_mat A, int K, const float* __restrict__ Wo, int ldwo,
                                                          const float* __restrict__ bo, int B, int C, int head,
                                                          const float* __restrict__ Y, int ldy, float* out, int ldo,
-                                                         float* delta, int ldd, float* loss_rows) {
+                                                         float* delta, int ldd, bf16* delta_b, int lddb,
+                                                         float* loss_rows) {
   if (threadIdx.x == 0) pdl_launch_dependents();
   pdl_wait();
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (row >= B) return;
-  float z = 0.0f;  // lane c ends up holding score c
-  for (int c0 = 0; c0 < C; c0 += 8) {
-    float acc[8];
+  float acc[32];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
+  for (int c = 0; c < 32; ++c) acc[c] = 0.0f;
+  const bool vec = (K % 8 == 0) && (ldwo % 4 == 0) && (A.ld % 8 == 0) && ((reinterpret_cast<uintptr_t>(A.ptr) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(Wo) & 15) == 0);
+  if (vec) {
+    for (int k = lane * 8; k < K; k += 256) {
+      float a[8];
+      head_load8(A, row, k, a);
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        if (c < C) {
+          const float4* w = reinterpret_cast<const float4*>(Wo + (size_t)c * ldwo + k);
+          const float4 w0 = __ldg(w), w1 = __ldg(w + 1);
+          float s = acc[c];
+          s = fmaf(a[0], w0.x, s); s = fmaf(a[1], w0.y, s); s = fmaf(a[2], w0.z, s); s = fmaf(a[3], w0.w, s);
+          s = fmaf(a[4], w1.x, s); s = fmaf(a[5], w1.y, s); s = fmaf(a[6], w1.z, s); s = fmaf(a[7], w1.w, s);
+          acc[c] = s;
+        }
+      }
+    }
+  } else {
     for (int k = lane; k < K; k += 32) {
       const float a = mat_load(A, row, k);
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (c0 + j < C) acc[j] = fmaf(a, __ldg(Wo + (size_t)(c0 + j) * ldwo + k), acc[j]);
+      for (int c = 0; c < 32; ++c)
+        if (c < C) acc[c] = fmaf(a, __ldg(Wo + (size_t)c * ldwo + k), acc[c]);
     }
+  }
+  float z = 0.0f;  // lane c ends up holding score c
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+  for (int c = 0; c < 32; ++c) {
+    if (c < C) {   // warp-uniform
+      float s = acc[c];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
-      if (lane == c0 + j && c0 + j < C) z = acc[j] + bo[c0 + j];
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == c) z = s + bo[c];
     }
   }
   const bool valid = lane < C;
@@ -190,8 +230,57 @@ __global__ void __launch_bounds__(256) head_fused_kernel(dbn_mat A, int K, const
   if (valid) {
     out[(size_t)row * ldo + lane] = o_val;
     if (delta != nullptr) delta[(size_t)row * ldd + lane] = o_val - y;
+    if (delta_b != nullptr) delta_b[(size_t)row * lddb + lane] = __float2bfloat16_rn(o_val - y);   // tensor-core operand copy
   }
   if (loss_rows != nullptr && Y != nullptr && lane == 0) loss_rows[row] = loss;
+}
+
+// Gradient + decayed SGD update of a narrow head (C <= 32), dbn/models.py:508-513 with :462-465:
+//   W_o[c][h] = decay * W_o[c][h] + scale * sum_b delta[b][c] * a[b][h],   b_o[c] += scale * sum_b delta[b][c].
+// One thread per input unit h (plus one for the bias, whose "activation" is 1); the deltas of the mini-batch
+// are staged in shared memory; the batch loop is unrolled so the activation loads overlap.  If raw != NULL
+// the un-scaled sums are written to raw [C, ldr] (column H = bias) and nothing is updated.
+__global__ void __launch_bounds__(128) head_grad_kernel(dbn_mat A, int H, const float* __restrict__ delta, int ldd, int B,
+                                                        int C, float* Wo, int ldwo, float* bo, float decay, float scale,
+                                                        float* raw, int ldr) {
+  if (threadIdx.x == 0) pdl_launch_dependents();
+  pdl_wait();
+  extern __shared__ float hg_delta[];   // [B][C]
+  for (int i = threadIdx.x; i < B * C; i += blockDim.x) hg_delta[i] = delta[(size_t)(i / C) * ldd + (i % C)];
+  __syncthreads();
+  const int h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h > H) return;
+  float acc[32];
+#pragma unroll
+  for (int c = 0; c < 32; ++c) acc[c] = 0.0f;
+  int b = 0;
+  for (; b + 4 <= B; b += 4) {
+    float a[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) a[j] = (h < H) ? mat_load(A, b + j, h) : 1.0f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float* d = hg_delta + (size_t)(b + j) * C;
+#pragma unroll
+      for (int c = 0; c < 32; ++c)
+        if (c < C) acc[c] = fmaf(d[c], a[j], acc[c]);
+    }
+  }
+  for (; b < B; ++b) {
+    const float a = (h < H) ? mat_load(A, b, h) : 1.0f;
+    const float* d = hg_delta + (size_t)b * C;
+#pragma unroll
+    for (int c = 0; c < 32; ++c)
+      if (c < C) acc[c] = fmaf(d[c], a, acc[c]);
+  }
+#pragma unroll
+  for (int c = 0; c < 32; ++c) {
+    if (c < C) {
+      if (raw != nullptr) raw[(size_t)c * ldr + h] = acc[c];
+      else if (h < H) Wo[(size_t)c * ldwo + h] = fmaf(scale, acc[c], decay * Wo[(size_t)c * ldwo + h]);
+      else bo[c] = fmaf(scale, acc[c], bo[c]);
+    }
+  }
 }
 
 // W += s * dW, c += s * dc (last column) for rows [h0, h0 + n_w_rows) and, if with_db, b += s * db (row H)

@@ -661,7 +661,9 @@ inline bool umma_gemm_supported(int M, int N, const dbn_operands* ops, int n_ops
     if (!umma_operand_ok(ops[i].B, ops[i].transB ? N : ops[i].K)) return false;
     if (ops[i].K < 32) return false;
   }
-  return M >= 64 && N >= 32;
+  // worth a 128-row tile: a real row block, or a skinny output whose contraction is still large
+  // (the narrow-head gradient: 10 x 2001 with K = batch)
+  return N >= 32 && (M >= 64 || (long)N * ops[0].K >= 64 * 1024);
 }
 
 // SMs the persistent contraction kernels may occupy.  A data-parallel caller reserves a few SMs
