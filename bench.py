@@ -57,27 +57,41 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.rows, self.proc = index, [], None
+        self.t0 = self.t1 = None
 
     def run(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
-                self.rows.append([x.strip() for x in line.split(",")])
+                self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
         except Exception:
             pass
+
+    def mark_start(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
         if self.proc is not None:
             self.proc.terminate()
         self.join(timeout=2)
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        # samples taken inside the timed region; if it was shorter than the sampling period, the samples
+        # of the (identical-load) warm-up that immediately precedes it are used and the window says so
+        inside = [r for (t, r) in self.rows if self.t0 is not None and self.t0 - 0.05 <= t <= self.t1 + 0.05]
+        window = "timed region"
+        if len(inside) < 2:
+            inside = [r for (_t, r) in self.rows][-10:]
+            window = "warm-up + timed region"
+        sm = [float(r[0]) for r in inside if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in inside if len(r) > 1 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i] == "Active"})
+        reasons = sorted({names[i] for r in inside if len(r) >= 7 for i in range(4) if r[3 + i] == "Active"})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "window": window}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -198,7 +212,7 @@ def workload_config(wl, gpus):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--workload", default=None, choices=[None, "c2", "c3", "c5"])
@@ -236,15 +250,16 @@ def main():
         torch.cuda.synchronize()
 
     def timed(fn, steps, warmup, finish=None):
+        sampler = ClockSampler(local)
+        sampler.start()
         for _ in range(warmup):
             fn()
         if finish is not None:
             finish()
         barrier()
-        sampler = ClockSampler(local)
-        sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         n0 = lib.dbn_launch_count()
+        sampler.mark_start()
         e0.record()
         for _ in range(steps):
             fn()
@@ -252,6 +267,7 @@ def main():
             finish()   # the main stream joins outstanding all-reduce / apply work before the stop event
         e1.record()
         barrier()
+        sampler.mark_end()
         ms = e0.elapsed_time(e1)
         clocks = sampler.stop()
         if world > 1:
@@ -392,6 +408,37 @@ def main():
                 "traffic": 835e6 * bl / 32768.0,
                 "traffic_source": "ncu dram__bytes_read+write per 32768-row launch, profiles/r01_c5_umma2cta_full.txt"}
 
+        # the same workload on ONE GPU of this box (rank 0 alone, after the timed region), so that the
+        # N > 1 line carries its own scaling denominator: the N = 1 default command benches config 2
+        if world > 1:
+            barrier()
+            if rank == 0:
+                l1 = E.DeviceRbm(W, np.zeros(C5_V), np.zeros(C5_H), "sigmoid", args.precision, dev)
+                r1 = E.RbmEpochRunner(l1, Xd, C5_BS, 1, 0.01, 99)
+                l1.stage(Xd, out=r1.Xp)
+                a1 = r1.args
+
+                def step1(i):
+                    a1.B = C5_BS
+                    a1.row0 = (i % steps_per_epoch) * C5_BS
+                    a1.rng.row0 = a1.row0
+                    L.check(lib.dbn_rbm_cd_step(E.stream_ptr(), C.byref(a1)))
+                for i in range(3):
+                    step1(i)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for i in range(10):
+                    step1(i)
+                e1.record()
+                torch.cuda.synchronize()
+                t1 = e0.elapsed_time(e1) / 10
+                extra["same_workload_1gpu"] = {"value": C5_BS / (t1 * 1e-3), "unit": "samples/s", "ms_per_step": t1,
+                                               "note": "rank 0 alone, full 32768-row batch, same box, 10 steps"}
+                del l1, r1
+                torch.cuda.empty_cache()
+            barrier()
+
         def e2e_step():
             from dbn_b200 import BinaryRBM
             os.environ["DBN_B200_DATA_PARALLEL"] = "1"
@@ -472,8 +519,10 @@ def main():
         out = {"metric": METRIC if wl != "c3" else "backprop samples/sec", "value": value, "unit": "samples/s",
                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
                "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
-               "dtype": "bf16 operands, f32 accumulate" if args.precision == "bf16" else "f32",
-               "data": "synthetic", "config": workload_config(wl, world), "clocks": clocks, "e2e": e2e,
+               "dtype": "bf16" if args.precision == "bf16" else "f32",
+               "data": "synthetic", "config": dict(workload_config(wl, world), arithmetic=(
+                   "bf16 operands on tcgen05, fp32 accumulation in TMEM, fp32 master weights"
+                   if args.precision == "bf16" else "strict fp32 FFMA")), "clocks": clocks, "e2e": e2e,
                "gpu_launches": int(launches), "roofline": roof}
         out.update(extra)
         if not args.no_cpu and world == 1:
