@@ -186,3 +186,42 @@ def test_caller_data_is_not_mutated():
     SupervisedDBNClassification(hidden_layers_structure=[8], n_epochs_rbm=1, n_iter_backprop=2, batch_size=16,
                                 dropout_p=0.5, verbose=False).fit(X, y)
     assert np.array_equal(X, X0)
+
+
+def test_edge_shapes_and_degenerate_settings():
+    """Shapes the reference handles implicitly: batch larger than the dataset (one short batch), a
+    dataset that is not a multiple of the batch, a single hidden unit, CD-0 (no-op updates,
+    dbn/models.py:134), a single training row."""
+    rng = np.random.default_rng(3)
+    X = rng.random((37, 9)).astype(np.float32)
+    np.random.seed(0)
+    m = BinaryRBM(n_hidden_units=5, n_epochs=2, batch_size=64, verbose=False).fit(X)      # batch_size > N
+    assert m.W.shape == (5, 9) and np.all(np.isfinite(m.W))
+    np.random.seed(0)
+    ref = orc.rbm_init(9, 5, "sigmoid")
+    assert not np.allclose(m.W, ref[0])                                                    # it did train
+    np.random.seed(0)
+    m1 = BinaryRBM(n_hidden_units=1, n_epochs=1, batch_size=8, verbose=False).fit(X)       # H = 1
+    assert m1.transform(X).shape == (37, 1) and m1.transform(X[0]).shape == (1,)
+    np.random.seed(0)
+    m0 = BinaryRBM(n_hidden_units=4, n_epochs=3, batch_size=8, contrastive_divergence_iter=0, verbose=False).fit(X)
+    np.random.seed(0)
+    W0, b0, c0 = orc.rbm_init(9, 4, "sigmoid")
+    assert np.allclose(m0.W, W0, atol=1e-7) and np.allclose(m0.b, b0, atol=1e-7)           # CD-0: v_k == v_0, zero deltas
+    np.random.seed(0)
+    one = BinaryRBM(n_hidden_units=3, n_epochs=2, batch_size=4, verbose=False).fit(X[:1])  # a single row
+    assert np.all(np.isfinite(one.W))
+    # integer / float64 / non-contiguous inputs are accepted like NumPy would
+    Xi = (X * 16).astype(np.int64)
+    np.random.seed(1)
+    mi = BinaryRBM(n_hidden_units=3, n_epochs=1, batch_size=8, verbose=False).fit(Xi[:, ::-1])
+    assert mi.transform(Xi[:, ::-1].astype(np.float64)).shape == (37, 3)
+    # string labels, classes seen out of order
+    y = np.array(["dog", "cat", "bird"])[rng.integers(0, 3, 37)]
+    np.random.seed(2)
+    clf = SupervisedDBNClassification(hidden_layers_structure=[6], n_epochs_rbm=1, n_iter_backprop=2, batch_size=16,
+                                      verbose=False).fit(X, y)
+    pred = clf.predict(X)
+    assert set(pred) <= {"dog", "cat", "bird"} and clf.predict_proba(X).shape == (37, 3)
+    assert abs(clf.predict_proba(X).sum(axis=1) - 1).max() < 1e-5
+    assert 0.0 <= clf.score(X, y) <= 1.0

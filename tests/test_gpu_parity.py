@@ -251,3 +251,46 @@ def test_finetune_step_against_oracle(precision, B, n_in, hs, n_out, act, head, 
         assert np.linalg.norm(res2["layers"][l][1] - lay[l][1]) < allowed_c, "layer %d bias update" % l
     assert np.linalg.norm(res2["Wo"] - Wo2) < depth * gate * tol * (lr / bs) * scales[-1] + 1e-6
     assert np.max(np.abs(res2["bo"] - bo2)) < 1e-4
+
+
+# ---------------------------------------------------------------------------------------------------
+# size-independent properties at the full widths of BASELINE.json (no oracle needed at these sizes)
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,V,H,precision", [(2048, 4096, 4096, "bf16"),      # config 5 (per-GPU slice of the batch)
+                                              (256, 784, 500, "bf16"), (256, 500, 2000, "bf16"),   # config 2
+                                              (256, 784, 500, "fp32")])
+def test_full_size_step_properties(B, V, H, precision):
+    rng = np.random.default_rng(B + V)
+    W = (rng.standard_normal((H, V)) / np.sqrt(V)).astype(np.float32).astype(np.float64)
+    b = rng.standard_normal(V) * 0.1
+    c = rng.standard_normal(H) * 0.1
+    V0 = (rng.random((B, V)) < 0.3).astype(np.float64)
+    seed = 2024
+    full = G.run_cd_step(W, b, c, V0, 1, "sigmoid", precision, seed=seed, raw=True, row0=1000)
+    # determinism: same seed, same inputs -> bit-identical outputs
+    again = G.run_cd_step(W, b, c, V0, 1, "sigmoid", precision, seed=seed, raw=True, row0=1000)
+    assert np.array_equal(full["dW"], again["dW"]) and np.array_equal(full["H0s"], again["H0s"])
+    # linearity in the mini-batch (what data parallelism relies on): parts with their global row offsets
+    # sample identically and their raw deltas add up to the whole
+    half = B // 2
+    p0 = G.run_cd_step(W, b, c, V0[:half], 1, "sigmoid", precision, seed=seed, raw=True, row0=1000)
+    p1 = G.run_cd_step(W, b, c, V0[half:], 1, "sigmoid", precision, seed=seed, raw=True, row0=1000 + half)
+    assert np.array_equal(np.concatenate([p0["H0s"], p1["H0s"]]), full["H0s"])
+    scale = np.linalg.norm((full["P0"].T) @ V0)     # size of one of the two products whose difference dW is
+    assert np.linalg.norm(p0["dW"] + p1["dW"] - full["dW"]) < 1e-5 * scale
+    assert np.max(np.abs(p0["db"] + p1["db"] - full["db"])) < 1e-3
+    assert np.max(np.abs(p0["dc"] + p1["dc"] - full["dc"])) < 1e-3 * max(1.0, np.max(np.abs(full["dc"])))
+    # a different seed gives different samples with the same mean rate
+    other = G.run_cd_step(W, b, c, V0, 1, "sigmoid", precision, seed=seed + 1, raw=True, row0=1000)
+    assert not np.array_equal(other["H0s"], full["H0s"])
+    assert abs(other["H0s"].mean() - full["H0s"].mean()) < 5e-3
+    assert abs(full["H0s"].mean() - full["P0"].mean()) < 5e-3          # E[u < p] = p
+    # lr = 0: the update is the identity on the fp32 master, and the shadow is its bf16 rounding
+    ident = G.run_cd_step(W, b, c, V0, 1, "sigmoid", precision, seed=seed, raw=False, lr_over_bs=0.0)
+    assert np.array_equal(ident["W"], W) and np.allclose(ident["b"], b, atol=1e-7)
+    if precision == "bf16":
+        import torch
+        assert np.array_equal(ident["Wb"], torch.as_tensor(W).float().to(torch.bfloat16).double().numpy())
+    # probabilities are probabilities; samples are binary
+    assert full["P0"].min() >= 0.0 and full["P0"].max() <= 1.0
+    assert set(np.unique(full["H0s"])) <= {0.0, 1.0}
