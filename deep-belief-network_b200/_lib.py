@@ -55,7 +55,8 @@ class RbmStepArgs(C.Structure):
                 ("H", C.c_int32), ("k", C.c_int32), ("lr_over_bs", C.c_float), ("row0", C.c_int32),
                 ("X", Mat), ("W", C.c_void_p), ("ldw", C.c_int32), ("flags", C.c_int32), ("b", C.c_void_p),
                 ("c", C.c_void_p), ("Wb", Mat), ("rng", Rng), ("workspace", C.c_void_p),
-                ("workspace_bytes", C.c_size_t), ("P0", Mat), ("Vk", Mat), ("Pk", Mat), ("H0s", Mat),
+                ("workspace_bytes", C.c_size_t), ("ws_rows", C.c_int32), ("_pad2", C.c_int32),
+                ("P0", Mat), ("Vk", Mat), ("Pk", Mat), ("H0s", Mat),
                 ("raw_delta", Mat)]
 
 
@@ -69,7 +70,8 @@ class MlpStepArgs(C.Structure):
                 ("Y", C.c_void_p), ("ldy", C.c_int32), ("_pad2", C.c_int32),
                 ("lr_over_bs", C.c_float), ("decay", C.c_float), ("keep_p", C.c_float), ("_pad3", C.c_int32),
                 ("rng", Rng), ("masks", Mat * (MAX_LAYERS + 1)), ("workspace", C.c_void_p),
-                ("workspace_bytes", C.c_size_t), ("loss_rows", C.c_void_p), ("out", Mat),
+                ("workspace_bytes", C.c_size_t), ("ws_rows", C.c_int32), ("_pad4", C.c_int32),
+                ("loss_rows", C.c_void_p), ("out", Mat),
                 ("raw_grads", Mat * (MAX_LAYERS + 1))]
 
 

@@ -229,12 +229,15 @@ int dbn_rbm_workspace_init(void* stream, int precision, int Bmax, int V, int H, 
   return DBN_OK;
 }
 
+// The workspace layout (and its ones columns) is fixed by the row count it was initialised for.
+static inline int rbm_ws_rows(const dbn_rbm_step_args* a) { return a->ws_rows > 0 ? a->ws_rows : a->B; }
+
 // t = 0 hidden phase on hidden units [h0, h1): P0 (kept for dW == h_0 of dbn/models.py:140) and the
 // first sample (dbn/models.py:135 -> :148-155).
 static int rbm_first_hidden_impl(void* stream, const dbn_rbm_step_args* a, int h0, int h1) {
   const bool tc = a->precision == DBN_PREC_BF16;
   RbmWorkspace ws;
-  rbm_ws_layout(a->precision, a->B, a->V, a->H, static_cast<char*>(a->workspace), &ws);
+  rbm_ws_layout(a->precision, rbm_ws_rows(a), a->V, a->H, static_cast<char*>(a->workspace), &ws);
   const dbn_mat Wop = tc ? a->Wb : make_mat(a->W, a->ldw, DBN_F32);
   dbn_operands o = make_ops(a->X, 0, a->row0, Wop, 0, h0, a->V);
   dbn_act_epilogue e = blank_act();
@@ -262,12 +265,13 @@ int dbn_rbm_cd_step(void* stream, const dbn_rbm_step_args* a) {
   DBN_REQUIRE(a != nullptr, "null args");
   DBN_REQUIRE(a->B > 0 && a->V > 0 && a->H > 0 && a->k >= 0, "bad shape");
   DBN_REQUIRE(a->act == DBN_ACT_SIGMOID || a->act == DBN_ACT_RELU, "Invalid activation function.");
-  DBN_REQUIRE(a->workspace_bytes >= dbn_rbm_workspace_bytes(a->precision, a->B, a->V, a->H), "workspace too small");
+  DBN_REQUIRE(a->ws_rows == 0 || a->ws_rows >= a->B, "ws_rows smaller than the mini-batch");
+  DBN_REQUIRE(a->workspace_bytes >= dbn_rbm_workspace_bytes(a->precision, rbm_ws_rows(a), a->V, a->H), "workspace too small");
   const bool tc = a->precision == DBN_PREC_BF16;
   DBN_REQUIRE(!tc || (a->Wb.ptr && a->X.dtype == DBN_BF16), "BF16 mode needs bf16 X and the bf16 shadow of W");
   if (a->k == 0) return DBN_OK;  // v_k == v_0: all deltas are zero (dbn/models.py:134 loop is empty)
   RbmWorkspace ws;
-  rbm_ws_layout(a->precision, a->B, a->V, a->H, static_cast<char*>(a->workspace), &ws);
+  rbm_ws_layout(a->precision, rbm_ws_rows(a), a->V, a->H, static_cast<char*>(a->workspace), &ws);
   const dbn_mat Wop = tc ? a->Wb : make_mat(a->W, a->ldw, DBN_F32);
   const int B = a->B, V = a->V, H = a->H;
 
@@ -344,6 +348,7 @@ int dbn_rbm_fit_epoch(void* stream, const dbn_rbm_step_args* tmpl, int n_rows, i
   for (int s = 0; s < n_rows; s += batch_size) {  // batch_generator: dbn/utils.py:14-22 (short last batch)
     dbn_rbm_step_args a = *tmpl;
     a.B = std::min(batch_size, n_rows - s);
+    if (a.ws_rows == 0) a.ws_rows = std::min(batch_size, n_rows);   // one layout for every batch of the epoch
     a.row0 = tmpl->row0 + s;
     a.rng.row0 = tmpl->rng.row0 + (uint32_t)s;
     if (a.rng.injected.ptr)
@@ -360,7 +365,7 @@ int dbn_rbm_delta_rows(void* stream, const dbn_rbm_step_args* a, int h0, int h1)
   if (a->k == 0) return DBN_OK;
   const bool tc = a->precision == DBN_PREC_BF16;
   RbmWorkspace ws;
-  rbm_ws_layout(a->precision, a->B, a->V, a->H, static_cast<char*>(a->workspace), &ws);
+  rbm_ws_layout(a->precision, rbm_ws_rows(a), a->V, a->H, static_cast<char*>(a->workspace), &ws);
   dbn_operands o[2];
   o[0] = make_ops(offset_cols(ws.P0, h0), 1, 0, a->X, 1, a->row0, a->B);
   o[1] = make_ops(offset_cols(ws.Pk, h0), 1, 0, ws.Vt, 1, 0, a->B);
@@ -411,14 +416,16 @@ int dbn_mlp_train_step(void* stream, const dbn_mlp_step_args* a) {
   const int L = a->n_layers, B = a->B;
   DBN_REQUIRE(L >= 1 && L <= DBN_MAX_LAYERS && B > 0 && a->n_in > 0 && a->n_out > 0, "bad shape");
   DBN_REQUIRE(a->act == DBN_ACT_SIGMOID || a->act == DBN_ACT_RELU, "Invalid activation function.");
-  DBN_REQUIRE(a->workspace_bytes >= dbn_mlp_workspace_bytes(a->precision, B, a->n_in, a->dims, L, a->n_out),
+  const int ws_rows = a->ws_rows > 0 ? a->ws_rows : B;   // the layout (and its ones columns) is fixed by this
+  DBN_REQUIRE(ws_rows >= B, "ws_rows smaller than the mini-batch");
+  DBN_REQUIRE(a->workspace_bytes >= dbn_mlp_workspace_bytes(a->precision, ws_rows, a->n_in, a->dims, L, a->n_out),
               "workspace too small");
   const bool tc = a->precision == DBN_PREC_BF16;
   const bool dropout = a->keep_p < 1.0f;
   const bool raw = a->raw_grads[0].ptr != nullptr;
   cudaStream_t st = as_stream(stream);
   MlpWorkspace ws;
-  mlp_ws_layout(a->precision, B, a->n_in, a->dims, L, a->n_out, static_cast<char*>(a->workspace), &ws);
+  mlp_ws_layout(a->precision, ws_rows, a->n_in, a->dims, L, a->n_out, static_cast<char*>(a->workspace), &ws);
   auto Wop = [&](int l) { return tc ? a->Wb[l] : make_mat(a->W[l], a->ldw[l], DBN_F32); };
   const int prime = a->act == DBN_ACT_SIGMOID ? DBN_MUL_PRIME_SIGMOID : DBN_MUL_PRIME_RELU;
 
@@ -520,6 +527,7 @@ int dbn_mlp_fit_epoch(void* stream, const dbn_mlp_step_args* tmpl, int n_rows, i
   for (int s = 0; s < n_rows; s += batch_size) {
     dbn_mlp_step_args a = *tmpl;
     a.B = std::min(batch_size, n_rows - s);
+    if (a.ws_rows == 0) a.ws_rows = std::min(batch_size, n_rows);
     a.row0 = tmpl->row0 + s;
     a.rng.row0 = tmpl->rng.row0 + (uint32_t)s;
     if (a.loss_rows) a.loss_rows += s;

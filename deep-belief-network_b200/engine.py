@@ -242,12 +242,14 @@ class DeviceRbm:
         if U is not None:
             a.rng.injected = mat(U)
         a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+        a.ws_rows = getattr(ws, "dbn_rows", 0)
         return a
 
     def make_workspace(self, bmax):
         nbytes = self.lib.dbn_rbm_workspace_bytes(self.prec, bmax, self.V, self.H)
         ws = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=self.device)
         L.check(self.lib.dbn_rbm_workspace_init(stream_ptr(), self.prec, bmax, self.V, self.H, ptr(ws)))
+        ws.dbn_rows = int(bmax)   # the layout (and its ones columns) is fixed by this row count
         return ws
 
     def fit(self, Xd, n_epochs, batch_size, k, lr, seed, rng_mode="philox", verbose=None, dp=None):
@@ -510,6 +512,7 @@ class DeviceMlp:
         ws = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=self.device)
         L.check(self.lib.dbn_mlp_workspace_init(stream_ptr(), self.prec, bmax, self.n_in, self._dims_array(),
                                                 len(self.dims), self.n_out, ptr(ws)))
+        ws.dbn_rows = int(bmax)
         return ws
 
     def step_args(self, Xop, Yd, lr_over_bs, decay, keep_p, ws, seed, iter_ctr, loss_rows=None, masks=None):
@@ -531,6 +534,7 @@ class DeviceMlp:
             for j, m in enumerate(masks):
                 a.masks[j] = mat(m)
         a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+        a.ws_rows = getattr(ws, "dbn_rows", 0)
         a.loss_rows = loss_rows.data_ptr() if loss_rows is not None else None
         return a
 

@@ -218,8 +218,11 @@ typedef struct dbn_rbm_step_args {
   float* c;                /* (H,) */
   dbn_mat Wb;              /* bf16 shadow of W (BF16 mode), else NULL               */
   dbn_rng rng;             /* mode ignored; .injected = U[B, k*H] or NULL; stream = Gibbs step is added */
-  void* workspace;         /* >= dbn_rbm_workspace_bytes */
+  void* workspace;         /* >= dbn_rbm_workspace_bytes(precision, ws_rows, V, H) */
   size_t workspace_bytes;
+  int32_t ws_rows;         /* rows (Bmax) the workspace was sized and initialised for; 0 = B.  The layout of the
+                              workspace depends on it, so a short last batch must pass the SAME value. */
+  int32_t _pad2;
   /* optional outputs (parity tests): */
   dbn_mat P0;              /* fp32 [B,H]  hidden means at t=0  (h_0, models.py:140)   */
   dbn_mat Vk;              /* fp32 [B,V]                                            */
@@ -289,6 +292,7 @@ typedef struct dbn_mlp_step_args {
   dbn_rng rng;                      /* dropout: .injected unused here; see masks[]   */
   dbn_mat masks[DBN_MAX_LAYERS + 1];/* injected keep-masks fp32 (input, H_1..H_L) or NULL ptr -> Philox */
   void* workspace; size_t workspace_bytes;
+  int32_t ws_rows, _pad4;           /* rows (Bmax) the workspace was sized / initialised for; 0 = B */
   float* loss_rows;                 /* optional [B]: -log p[label] or sum_t (pred-y)^2 */
   dbn_mat out;                      /* optional fp32 [B, n_out] head outputs          */
   dbn_mat raw_grads[DBN_MAX_LAYERS + 1]; /* optional fp32 [(out_l), in_l + 1] raw gradient | bias column; if raw_grads[0].ptr set nothing is updated */

@@ -225,3 +225,28 @@ def test_edge_shapes_and_degenerate_settings():
     assert set(pred) <= {"dog", "cat", "bird"} and clf.predict_proba(X).shape == (37, 3)
     assert abs(clf.predict_proba(X).sum(axis=1) - 1).max() < 1e-5
     assert 0.0 <= clf.score(X, y) <= 1.0
+
+
+@pytest.mark.parametrize("precision,tol", [("bf16", 2e-2), ("fp32", 1e-4)])
+def test_ragged_last_batch_whole_fit_against_oracle(precision, tol):
+    """N not a multiple of batch_size on the tiled (multi-launch) path in both precisions: the short last
+    batch reuses the workspace of the full batches, so its layout and ones columns must not depend on the
+    batch's row count.  Replays the reference's uniform stream (rng='numpy') and compares the trained
+    parameters -- in particular both bias vectors, which ride on the ones row/column -- with the oracle."""
+    rng = np.random.default_rng(8)
+    N, V, H, bs = 300, 192, 160, 128                      # last batch: 44 rows
+    X = (rng.random((N, V)) < 0.3).astype(np.float32)
+    os.environ["DBN_B200_PERSISTENT"] = "0"
+    try:
+        np.random.seed(21)
+        m = BinaryRBM(n_hidden_units=H, learning_rate=0.1, n_epochs=2, batch_size=bs, verbose=False,
+                      precision=precision, rng="numpy").fit(X)
+    finally:
+        os.environ.pop("DBN_B200_PERSISTENT", None)
+    np.random.seed(21)
+    W, b, c = orc.rbm_fit_replay(X, H, "sigmoid", 0.1, 2, 1, bs)
+    np.random.seed(21)
+    W0, b0, c0 = orc.rbm_init(V, H, "sigmoid")
+    for got, ref, init, name in ((m.W, W, W0, "W"), (m.b, b, b0, "b"), (m.c, c, c0, "c")):
+        upd = np.linalg.norm(ref - init)
+        assert np.linalg.norm(got - ref) < tol * upd + 1e-6, (name, np.linalg.norm(got - ref), upd)
