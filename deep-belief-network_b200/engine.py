@@ -97,6 +97,8 @@ def dp_global_row0(step, batch_size, rank, bl):
 def dp_chunks(H, n_chunks):
     """Row blocks (multiples of 256 rows = one CTA-pair tile) in which the raw delta is produced,
     all-reduced and applied."""
+    if n_chunks <= 1:
+        return [(0, H)]
     rows = max(256, (H + n_chunks - 1) // n_chunks // 256 * 256)
     return [(h0, min(H, h0 + rows)) for h0 in range(0, H, rows)]
 
@@ -170,7 +172,8 @@ class DeviceRbm:
 
     # -- operand staging ---------------------------------------------------------------------------
     def alloc_staged(self, n, cols):
-        """Uninitialised operand buffer for n rows of `cols` features in this precision's layout."""
+        """Operand buffer for n rows of `cols` features in this precision's layout (BF16: zero-filled, since
+        the padding columns are read by the tensor-core path; FP32: uninitialised)."""
         if self.prec == L.PREC_BF16:   # zero padding: the tensor-core path reads K tails up to the next 64 columns
             return torch.zeros(n, bf16_pitch(cols), dtype=torch.bfloat16, device=self.device)
         return torch.empty(n, cols, dtype=torch.float32, device=self.device)
@@ -279,28 +282,32 @@ class DeviceRbm:
 
 
 class RbmEpochRunner:
-    """One RBM layer + one dataset prepared for epoch-at-a-time training: the epoch array, the
-    workspace, the warm-up launch and the captured CUDA graph (gather + every mini-batch CD-k step).
-    `run()` = one epoch of dbn/models.py:105-119."""
+    """One RBM layer + one dataset prepared for epoch-at-a-time training.  `run()` = one epoch of
+    dbn/models.py:105-119, executed as
+      * ONE launch of the persistent on-chip cluster kernel when the layer fits (strict FP32), or
+      * the tiled path: gather (double shuffle) + four contractions per mini-batch, launched eagerly for the
+        first epoch (which doubles as warm-up) and as a captured CUDA graph from the second epoch on."""
 
     def __init__(self, layer, Xd, batch_size, k, lr, seed, rng_mode="philox"):
         self.layer, self.Xd = layer, Xd
         self.n, self.bs, self.k = int(Xd.shape[0]), int(batch_size), int(k)
         n, lib = self.n, layer.lib
         self.feeder = _IndexFeeder(n, layer.device)
-        self.Xp = layer.alloc_staged(n, int(Xd.shape[1]))  # epoch array; (re)written by the gather every epoch
-        self.ws = layer.make_workspace(min(self.bs, n))
         self.epoch_ctr = torch.zeros(1, dtype=torch.int32, device=layer.device)
         self.U = None
         if rng_mode == "numpy":
             self.U = torch.empty(n, k * layer.H, dtype=torch.float32, device=layer.device)
-        self.args = layer._step_args(self.Xp, k, lr / batch_size, self.ws, seed, self.epoch_ctr, self.U)
         # layers that fit on chip: one persistent cluster kernel per epoch, W resident in shared memory
         self.persistent = (os.environ.get("DBN_B200_PERSISTENT", "1") != "0" and Xd.dtype == torch.float32 and
                            Xd.is_contiguous() and
                            lib.dbn_rbm_persistent_plan(layer.prec, layer.V, layer.H, min(self.bs, n)) > 0)
-        if self.persistent:
-            self.args.X = mat(Xd)
+        if self.persistent:   # reads the un-permuted dataset through the index array: no epoch array, no workspace
+            self.Xp = Xd
+            self.ws = torch.empty(16, dtype=torch.uint8, device=layer.device)
+        else:
+            self.Xp = layer.alloc_staged(n, int(Xd.shape[1]))  # epoch array; (re)written by the gather every epoch
+            self.ws = layer.make_workspace(min(self.bs, n))
+        self.args = layer._step_args(self.Xp, k, lr / batch_size, self.ws, seed, self.epoch_ctr, self.U)
         self.graph = None
         self.launches_per_epoch = 0
         self.epochs_run = 0
@@ -343,12 +350,15 @@ class DpRbmEpochRunner:
     Every rank holds the dataset and draws the same shuffle; rank r computes rows
     [r*bl, (r+1)*bl) of each global mini-batch (bl = batch_size / world).  Philox counters are keyed
     by the GLOBAL row index, so the sampled states do not depend on the GPU count.  Per step the
-    Gibbs chain runs locally, then the raw delta [(H+1) x (V+1)] = dW | dc ; db is produced in
-    `n_chunks` row blocks: block i is all-reduced (NCCL sum over NVLink) and applied on a side stream
-    while the tensor cores produce block i+1, and the next step's first hidden phase on block i starts
-    as soon as block i has been applied.  Measured on 8 x B200 (profiles/r01_notes.md) the extra
-    launches and smaller contractions of the pipeline cost more than the overlap returns, so the
-    default is ONE block (plain step -> all-reduce -> apply); DBN_B200_DP_CHUNKS selects more."""
+    Gibbs chain runs locally and leaves the raw delta [(H+1) x (V+1)] = dW | dc ; db; then
+
+      * default in BF16 mode (`step_sharded`): reduce-scatter of the delta, every rank updates its H/world
+        rows of the fp32 master, all-gather of the refreshed bf16 shadow;
+      * otherwise: sum all-reduce of the delta and the identical update on every rank, optionally
+        pipelined in `n_chunks` row blocks (block i exchanged and applied on a side stream while block
+        i+1 is produced, the next step's first hidden phase started per block).  Measured on 8 x B200
+        (profiles/r01_notes.md) the pipeline's extra launches and smaller contractions cost more than
+        the overlap returns, so the default is ONE block; DBN_B200_DP_CHUNKS selects more."""
 
     def __init__(self, layer, Xd, batch_size, k, lr, seed, dp, n_chunks=1):
         import torch.distributed as dist

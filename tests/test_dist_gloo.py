@@ -81,5 +81,6 @@ def test_dp_partition_helpers():
     assert E.dp_global_row0(2, 8, 1, 4) == 20
     assert E.dp_chunks(4096, 2) == [(0, 2048), (2048, 4096)]
     assert E.dp_chunks(500, 8) == [(0, 256), (256, 500)]
+    assert E.dp_chunks(500, 1) == [(0, 500)] and E.dp_chunks(4096, 1) == [(0, 4096)]
     with pytest.raises(ValueError):
         E.dp_check_shapes(100, 32, 3)
