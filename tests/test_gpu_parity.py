@@ -294,3 +294,65 @@ def test_full_size_step_properties(B, V, H, precision):
     # probabilities are probabilities; samples are binary
     assert full["P0"].min() >= 0.0 and full["P0"].max() <= 1.0
     assert set(np.unique(full["H0s"])) <= {0.0, 1.0}
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("M,N,K", [(70, 50, 96), (256, 500, 784), (129, 193, 65), (513, 257, 128)])
+def test_epilogues_never_write_outside_the_logical_output(precision, M, N, K):
+    """Canary test (compute-sanitizer is closed on this pool): outputs live inside larger buffers filled with
+    a sentinel; rows >= M and columns >= N -- in particular the ones column and the zero padding the
+    tensor-core operands rely on -- must be untouched by the activation and the update epilogues."""
+    import ctypes as C
+    import torch
+    from dbn_b200 import _lib as L, engine as E
+    rng = np.random.default_rng(M + N)
+    dt = torch.float32 if precision == "fp32" else torch.bfloat16
+    SENT = 12345.0
+
+    def operand(rows, cols):
+        ld = cols if precision == "fp32" else E.bf16_pitch(cols)
+        t = torch.zeros(rows, ld, dtype=dt, device="cuda")
+        t[:, :cols] = torch.as_tensor(rng.standard_normal((rows, cols)).astype(np.float32)).cuda().to(dt)
+        return t
+
+    A, Bm = operand(M, K), operand(N, K)
+    ldo = E.bf16_pitch(N)
+    out = torch.full((M + 5, ldo), SENT, dtype=torch.float32, device="cuda")
+    out2 = torch.full((M + 5, ldo), SENT, dtype=torch.bfloat16, device="cuda")
+    smp = torch.full((M + 5, ldo), SENT, dtype=torch.bfloat16, device="cuda")
+    ops = L.Operands()
+    ops.A, ops.B, ops.K = E.mat(A), E.mat(Bm), K
+    epi = L.ActEpilogue()
+    epi.act = L.ACT_SIGMOID
+    epi.rng.mode, epi.rng.keep_p, epi.rng.seed = L.RNG_SAMPLE, 1.0, 9
+    epi.out, epi.out2, epi.sample = E.mat(out), E.mat(out2), E.mat(smp)
+    L.check(G.lib().dbn_gemm_act(E.stream_ptr(), E.PREC_IDS[precision], M, N, C.byref(ops), 1, C.byref(epi)))
+    torch.cuda.synchronize()
+    for t in (out, out2.float(), smp.float()):
+        t = t.cpu().numpy()
+        assert np.all(t[M:, :] == np.float32(torch.tensor(SENT, dtype=torch.bfloat16).float().item()) ) or np.all(t[M:, :] == SENT)
+        assert np.all((t[:M, N:] == SENT) | (t[:M, N:] == 12352.0)), "columns >= N were written"
+        assert np.all(np.isfinite(t[:M, :N])) and np.all(t[:M, :N] != SENT)
+    # update epilogue with the ones row/column: W (M x N) inside a larger fp32 buffer, bf16 shadow likewise
+    At, Bt = operand(K, M + 1), operand(K, N + 1)       # MN-major operands [K, M+1] / [K, N+1]
+    Wbuf = torch.full((M + 4, N + 7), SENT, dtype=torch.float32, device="cuda")
+    Wbuf[:M, :N] = 0.0
+    Wsh = torch.full((M + 4, E.bf16_pitch(N)), SENT, dtype=torch.bfloat16, device="cuda")
+    vM = torch.zeros(M + 3, device="cuda"); vM[M:] = SENT
+    vN = torch.zeros(N + 3, device="cuda"); vN[N:] = SENT
+    o2 = L.Operands()
+    o2.A, o2.B, o2.transA, o2.transB, o2.K = E.mat(At), E.mat(Bt), 1, 1, K
+    u = L.UpdateEpilogue()
+    u.W, u.ldw, u.Wb = Wbuf.data_ptr(), Wbuf.stride(0), E.mat(Wsh)
+    u.vecM, u.vecN, u.decay, u.scale = vM.data_ptr(), vN.data_ptr(), 1.0, 0.5
+    L.check(G.lib().dbn_gemm_update(E.stream_ptr(), E.PREC_IDS[precision], M, N, 1, 1, C.byref(o2), 1, C.byref(u)))
+    torch.cuda.synchronize()
+    Wn = Wbuf.cpu().numpy()
+    assert np.all(Wn[M:, :] == SENT) and np.all(Wn[:M, N:] == SENT) and np.all(Wn[:M, :N] != SENT)
+    Wsn = Wsh.float().cpu().numpy()
+    assert np.all(Wsn[M:, :] == 12352.0) and np.all(Wsn[:M, N:] == 12352.0)
+    assert np.all(vM.cpu().numpy()[M:] == SENT) and np.all(vN.cpu().numpy()[N:] == SENT)
+    # and the values are the contraction
+    Aq, Bq = At[:, :M].float().cpu().numpy().astype(np.float64), Bt[:, :N].float().cpu().numpy().astype(np.float64)
+    ref = 0.5 * (Aq.T @ Bq)
+    assert np.max(np.abs(Wn[:M, :N] - ref)) < 1e-3 * max(1.0, np.abs(ref).max())
