@@ -112,28 +112,46 @@ __device__ __forceinline__ void upd_epilogue_quad(const dbn_update_epilogue& e, 
   }
 }
 
-// ---- 32-column row segments (the tcgen05 epilogue: one thread = one accumulator row x 32 columns) ----
-// All loads are issued before any dependent math and all stores are 16-byte vectors, so the 32
-// independent element chains give the single epilogue warp per scheduler enough ILP; runtime switches
-// are hoisted to one branch per 32 columns.  Falls back to the generic quad path on ragged edges.
+// Out-of-line copies of the quad epilogues for the ragged edges of the tensor-core kernels: ONE copy of the
+// option tree per kernel instead of W/4 inlined ones.  The batch-256 launches run every instruction exactly once
+// per CTA, straight from a cold instruction cache, so code bytes on and around the hot path are latency.
+template <bool kFast>
+__device__ __noinline__ void act_epilogue_quad_ool(const dbn_act_epilogue& e, uint32_t epoch, int m, int n4, float a0,
+                                                   float a1, float a2, float a3, int M, int N) {
+  const float acc[4] = {a0, a1, a2, a3};
+  act_epilogue_quad<kFast>(e, epoch, m, n4, acc, M, N);
+}
+__device__ __noinline__ void upd_epilogue_quad_ool(const dbn_update_epilogue& e, int m, int n4, float a0, float a1, float a2,
+                                                   float a3, int M, int N, int augM, int augN) {
+  const float acc[4] = {a0, a1, a2, a3};
+  upd_epilogue_quad(e, m, n4, acc, M, N, augM, augN);
+}
+
+// ---- W-column row segments (the tcgen05 epilogues: one thread = one accumulator row x W columns) --------
+// W = 32: a thread drains 32 TMEM columns of its own lane.  W = 8: the split-K kernel's second phase, where
+// the reduced tile sits in shared memory and 8 consecutive lanes cover 64 columns of one row.
+// All loads are issued before any dependent math and all stores are 16-byte vectors, so the W independent
+// element chains give the epilogue warps enough ILP; runtime switches are hoisted to one branch per segment.
+// Falls back to the generic quad path on ragged edges.
 __device__ __forceinline__ bool mat_vec_ok(const dbn_mat& m) {
   if (m.ptr == nullptr) return true;
   const int per16 = (m.dtype == DBN_F32) ? 4 : 8;
   return (m.ld % per16) == 0 && (reinterpret_cast<uintptr_t>(m.ptr) & 15) == 0;
 }
-__device__ __forceinline__ void row32_load(const dbn_mat& m, int r, int c, float v[32]) {
+template <int W>
+__device__ __forceinline__ void row_load(const dbn_mat& m, int r, int c, float v[W]) {
   const size_t i = (size_t)r * (size_t)m.ld + (size_t)c;
   if (m.dtype == DBN_F32) {
     const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(m.ptr) + i);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < W / 4; ++j) {
       const float4 t = p[j];
       v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
     }
   } else {
     const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(m.ptr) + i);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < W / 8; ++j) {
       const uint4 t = p[j];
       const uint32_t w[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
@@ -145,16 +163,17 @@ __device__ __forceinline__ void row32_load(const dbn_mat& m, int r, int c, float
     }
   }
 }
-__device__ __forceinline__ void row32_store(const dbn_mat& m, int r, int c, const float v[32]) {
+template <int W>
+__device__ __forceinline__ void row_store(const dbn_mat& m, int r, int c, const float v[W]) {
   const size_t i = (size_t)r * (size_t)m.ld + (size_t)c;
   if (m.dtype == DBN_F32) {
     float4* p = reinterpret_cast<float4*>(reinterpret_cast<float*>(m.ptr) + i);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) p[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    for (int j = 0; j < W / 4; ++j) p[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
   } else {
     uint4* p = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(m.ptr) + i);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < W / 8; ++j) {
       uint32_t w[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
@@ -166,96 +185,123 @@ __device__ __forceinline__ void row32_store(const dbn_mat& m, int r, int c, cons
   }
 }
 
-template <bool kFast>
-__device__ __forceinline__ void act_epilogue_row32(const dbn_act_epilogue& e, uint32_t epoch, int m, int n0,
-                                                   const float acc[32], int M, int N) {
+// whole segment inside the logical output and every matrix it touches 16-byte addressable
+template <int W>
+__device__ __forceinline__ bool act_vec_ok(const dbn_act_epilogue& e, int m, int n0, int M, int N) {
+  return (m < M) && (n0 + W <= N) && mat_vec_ok(e.out) && mat_vec_ok(e.out2) && mat_vec_ok(e.sample) &&
+         (e.mul == DBN_MUL_NONE || mat_vec_ok(e.aux)) && (e.rng.injected.ptr == nullptr || mat_vec_ok(e.rng.injected)) &&
+         (e.bias == nullptr || (reinterpret_cast<uintptr_t>(e.bias) & 15) == 0);
+}
+
+// pre_bias: the segment's bias values if the caller already loaded them (only honoured on the vector path,
+// i.e. when act_vec_ok<W> held for the same arguments), else nullptr.
+template <int W, bool kFast>
+__device__ __forceinline__ void act_epilogue_row(const dbn_act_epilogue& e, uint32_t epoch, int m, int n0,
+                                                 const float acc[W], int M, int N, const float* pre_bias = nullptr) {
+  static_assert(W % 8 == 0, "segments are whole 16-byte bf16 vectors");
   const bool inj = e.rng.injected.ptr != nullptr;
-  const bool vec = (m < M) && (n0 + 32 <= N) && mat_vec_ok(e.out) && mat_vec_ok(e.out2) && mat_vec_ok(e.sample) &&
-                   (e.mul == DBN_MUL_NONE || mat_vec_ok(e.aux)) && (!inj || mat_vec_ok(e.rng.injected)) &&
-                   (e.bias == nullptr || (reinterpret_cast<uintptr_t>(e.bias) & 15) == 0);
+  const bool vec = act_vec_ok<W>(e, m, n0, M, N);
   if (!vec) {
+    if (m >= M) return;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) act_epilogue_quad<kFast>(e, epoch, m, n0 + 4 * j, acc + 4 * j, M, N);
+    for (int j = 0; j < W / 4; ++j)   // (unrolled: acc stays in registers; the callee is one shared copy)
+      if (n0 + 4 * j < N) act_epilogue_quad_ool<kFast>(e, epoch, m, n0 + 4 * j, acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3], M, N);
     return;
   }
-  float a[32];
-  if (e.bias != nullptr) {
+  float a[W];
+  if (e.bias != nullptr && pre_bias != nullptr) {
+#pragma unroll
+    for (int j = 0; j < W; ++j) a[j] = acc[j] + pre_bias[j];
+  } else if (e.bias != nullptr) {
     const float4* bp = reinterpret_cast<const float4*>(e.bias + n0);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < W / 4; ++j) {
       const float4 t = __ldg(bp + j);
       a[4 * j] = acc[4 * j] + t.x; a[4 * j + 1] = acc[4 * j + 1] + t.y;
       a[4 * j + 2] = acc[4 * j + 2] + t.z; a[4 * j + 3] = acc[4 * j + 3] + t.w;
     }
   } else {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) a[j] = acc[j];
+    for (int j = 0; j < W; ++j) a[j] = acc[j];
   }
   if (e.act == DBN_ACT_SIGMOID) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) a[j] = kFast ? sigmoid_fast(a[j]) : sigmoid_strict(a[j]);
+    for (int j = 0; j < W; ++j) a[j] = kFast ? sigmoid_fast(a[j]) : sigmoid_strict(a[j]);
   } else if (e.act == DBN_ACT_RELU) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) a[j] = fmaxf(a[j], 0.0f);
+    for (int j = 0; j < W; ++j) a[j] = fmaxf(a[j], 0.0f);
   }
   if (e.mul != DBN_MUL_NONE) {
-    float g[32];
-    row32_load(e.aux, m, n0, g);
+    float g[W];
+    row_load<W>(e.aux, m, n0, g);
     if (e.mul == DBN_MUL_PRIME_SIGMOID) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) a[j] *= g[j] * (1.0f - g[j]);
+      for (int j = 0; j < W; ++j) a[j] *= g[j] * (1.0f - g[j]);
     } else {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) a[j] = (g[j] > 0.0f) ? a[j] : 0.0f;
+      for (int j = 0; j < W; ++j) a[j] = (g[j] > 0.0f) ? a[j] : 0.0f;
     }
   }
-  float u[32];
+  float u[W];
   if (e.rng.mode != DBN_RNG_NONE) {
     if (inj) {
-      row32_load(e.rng.injected, m, n0, u);
+      row_load<W>(e.rng.injected, m, n0, u);
     } else {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) rng_uniform4(e.rng, epoch, m, n0 + 4 * j, u + 4 * j);
+      for (int j = 0; j < W / 4; ++j) rng_uniform4(e.rng, epoch, m, n0 + 4 * j, u + 4 * j);
     }
     if (e.rng.mode == DBN_RNG_MASK) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
+      for (int j = 0; j < W; ++j) {
         const bool keep = inj ? (u[j] != 0.0f) : (u[j] < e.rng.keep_p);
         a[j] = keep ? a[j] : 0.0f;
       }
     }
   }
-  if (e.out.ptr != nullptr) row32_store(e.out, m, n0, a);
-  if (e.out2.ptr != nullptr) row32_store(e.out2, m, n0, a);
+  if (e.out.ptr != nullptr) row_store<W>(e.out, m, n0, a);
+  if (e.out2.ptr != nullptr) row_store<W>(e.out2, m, n0, a);
   if (e.rng.mode == DBN_RNG_SAMPLE && e.sample.ptr != nullptr) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) u[j] = (u[j] < a[j]) ? 1.0f : 0.0f;
-    row32_store(e.sample, m, n0, u);
+    for (int j = 0; j < W; ++j) u[j] = (u[j] < a[j]) ? 1.0f : 0.0f;
+    row_store<W>(e.sample, m, n0, u);
   }
 }
 
-__device__ __forceinline__ void upd_epilogue_row32(const dbn_update_epilogue& e, int m, int n0, const float acc[32],
-                                                   int M, int N, int augM, int augN) {
-  const bool core = (m < M) && (n0 + 32 <= N);
-  const bool vec = core && mat_vec_ok(e.raw) && mat_vec_ok(e.Wb) &&
-                   (e.raw.ptr != nullptr || ((e.ldw & 3) == 0 && (reinterpret_cast<uintptr_t>(e.W) & 15) == 0));
+template <int W>
+__device__ __forceinline__ bool upd_vec_ok(const dbn_update_epilogue& e, int m, int n0, int M, int N) {
+  return (m < M) && (n0 + W <= N) && mat_vec_ok(e.raw) && mat_vec_ok(e.Wb) &&
+         (e.raw.ptr != nullptr || ((e.ldw & 3) == 0 && (reinterpret_cast<uintptr_t>(e.W) & 15) == 0));
+}
+
+// pre_w: the segment of the fp32 master weights if the caller already loaded it (vector path only), else nullptr.
+template <int W>
+__device__ __forceinline__ void upd_epilogue_row(const dbn_update_epilogue& e, int m, int n0, const float acc[W],
+                                                 int M, int N, int augM, int augN, const float* pre_w = nullptr) {
+  const bool vec = upd_vec_ok<W>(e, m, n0, M, N);
   if (!vec) {
+    if (m >= M + augM) return;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) upd_epilogue_quad(e, m, n0 + 4 * j, acc + 4 * j, M, N, augM, augN);
+    for (int j = 0; j < W / 4; ++j)
+      if (n0 + 4 * j < N + augN) upd_epilogue_quad_ool(e, m, n0 + 4 * j, acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3], M, N, augM, augN);
     return;
   }
   if (e.raw.ptr != nullptr) {
-    row32_store(e.raw, m, n0, acc);
+    row_store<W>(e.raw, m, n0, acc);
     return;
   }
   dbn_mat Wm;
   Wm.ptr = e.W; Wm.ld = e.ldw; Wm.dtype = DBN_F32;
-  float w[32];
-  row32_load(Wm, m, n0, w);   // all 8 loads in flight before the first store
+  float w[W];
+  if (pre_w != nullptr) {
 #pragma unroll
-  for (int j = 0; j < 32; ++j) w[j] = fmaf(e.scale, acc[j], e.decay * w[j]);
-  row32_store(Wm, m, n0, w);
-  if (e.Wb.ptr != nullptr) row32_store(e.Wb, m, n0, w);
+    for (int j = 0; j < W; ++j) w[j] = pre_w[j];
+  } else {
+    row_load<W>(Wm, m, n0, w);   // all loads in flight before the first store
+  }
+#pragma unroll
+  for (int j = 0; j < W; ++j) w[j] = fmaf(e.scale, acc[j], e.decay * w[j]);
+  row_store<W>(Wm, m, n0, w);
+  if (e.Wb.ptr != nullptr) row_store<W>(e.Wb, m, n0, w);
 }
 
 }  // namespace dbn

@@ -23,6 +23,7 @@
 // epilogue, so no operand is ever padded to a tile multiple.
 #pragma once
 #include <cuda.h>
+#include <cooperative_groups.h>
 
 #include "epilogue.cuh"
 
@@ -46,6 +47,7 @@ struct UmmaGemmParams {
   int rowA[2], rowB[2];
   int M, N;  // accumulator extent (incl. the ones row / column)
   int tiles_m, tiles_n, group_m;
+  int split, fs_per;   // split-K kernel: cluster size and fat stages per CTA
   long long* trace;  // debug: per-CTA phase timestamps (dbn_debug_set_trace), normally NULL
 };
 
@@ -53,13 +55,13 @@ struct UmmaGemmParams {
 // landed, mainloop of first tile issued, accumulator of first tile ready, first tile's epilogue done, 7 exit
 constexpr int UG_TRACE_SLOTS = 16;
 __device__ __forceinline__ void trace_mark(const UmmaGemmParams& p, int slot) {
-  if (p.trace != nullptr) p.trace[(size_t)blockIdx.x * UG_TRACE_SLOTS + slot] = clock64();
+  if (p.trace != nullptr) p.trace[(size_t)(blockIdx.x + blockIdx.y * gridDim.x) * UG_TRACE_SLOTS + slot] = clock64();
 }
 __device__ __forceinline__ void trace_mark_ns(const UmmaGemmParams& p, int slot) {  // slots 0, 8, 9: globaltimer
   if (p.trace != nullptr) {
     unsigned long long gt;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
-    p.trace[(size_t)blockIdx.x * UG_TRACE_SLOTS + slot] = (long long)gt;
+    p.trace[(size_t)(blockIdx.x + blockIdx.y * gridDim.x) * UG_TRACE_SLOTS + slot] = (long long)gt;
   }
 }
 inline long long*& umma_trace_ptr() {
@@ -169,6 +171,35 @@ __device__ __forceinline__ void tile_coords(const UmmaGemmParams& p, int tile, i
   nb = r / gm;
 }
 
+// The batch-256 launches run ONE tile per CTA: every kernel parameter is read exactly once per SM, out of a cold
+// constant cache, and the epilogue's option tree reads them one dependent branch at a time (load, test, branch,
+// next load ...).  Touching every 64-byte chunk of the parameter block up front, one chunk per idle epilogue warp
+// and all in flight together, turns that chain of serial misses into a single overlapped one during setup.
+template <class Epi>
+__device__ __forceinline__ void warm_param_cache(const UmmaGemmParams& p, const Epi& ea, int tail) {
+  const int w = threadIdx.x >> 5;
+  const uint32_t* p32 = reinterpret_cast<const uint32_t*>(&p) + 128;   // past the four tensor maps (TMA's own fetch)
+  const uint32_t* e32 = reinterpret_cast<const uint32_t*>(&ea);
+  constexpr int PW = (int)(sizeof(UmmaGemmParams) - 512) / 4, EW = (int)sizeof(Epi) / 4;
+  uint32_t v = (uint32_t)tail;
+  if (w == 2) v = p32[0];
+  if (w == 3) v = p32[PW > 16 ? 16 : PW - 1];
+  if (w == 4) v = p32[PW - 1];
+  if (w == 5) v = e32[0];
+  if (w == 6) v = e32[EW > 16 ? 16 : EW - 1];
+  if (w == 7) v = e32[EW > 32 ? 32 : EW - 1];
+  if (w == 8) v = e32[EW - 1];
+  asm volatile("" ::"r"(v));
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 template <int BN, int KS, class Epi>
 __global__ void __launch_bounds__(UG_THREADS, 1)
 umma_gemm_kernel(const __grid_constant__ UmmaGemmParams p, const __grid_constant__ Epi epi_args, int coreM, int coreN,
@@ -197,6 +228,7 @@ umma_gemm_kernel(const __grid_constant__ UmmaGemmParams p, const __grid_constant
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  warm_param_cache(p, epi_args, augN);
   const int n_tiles = p.tiles_m * p.tiles_n;
   if (threadIdx.x == 0) {
     trace_mark_ns(p, 0);
@@ -379,6 +411,15 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// relaxed: the closing cluster barrier of the split-K kernel only keeps CTAs alive, it orders no data
+// (a .release arrive costs ~800 cycles of fence on the critical path)
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.relaxed;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire;" ::: "memory"); }
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t cta) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta));
+  return r;
+}
 __device__ __forceinline__ void tma_load_3d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
   // the transaction bytes are credited to the LEADER CTA's barrier (peer bit cleared)
   asm volatile(
@@ -439,6 +480,7 @@ umma_gemm2_kernel(const __grid_constant__ UmmaGemmParams p, const __grid_constan
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  warm_param_cache(p, epi_args, augN);
   const uint32_t cta = cluster_ctarank();
   const bool leader = cta == 0;
   const int n_tiles = p.tiles_m * p.tiles_n;     // tiles_m counts 256-row blocks here
@@ -588,18 +630,311 @@ umma_gemm2_kernel(const __grid_constant__ UmmaGemmParams p, const __grid_constan
 }
 
 
+// =====================================================================================================
+// Split-K variant for SMALL outputs (the batch-256 layers of configs 2 and 3): a 256 x 500 output is 16
+// tiles, so the persistent kernel above leaves 130 SMs idle while 16 CTAs walk all of K at the pace of
+// their own TMA feed.  Here a cluster of S = 2 or 4 CTAs shares ONE 128 x BN tile: CTA r contracts a
+// contiguous K range (fat stages [r * fs_per, (r+1) * fs_per) of the pass list) into its own TMEM, then
+// the partial tiles are reduce-scattered by rows through distributed shared memory -- each CTA pushes
+// the 128/S accumulator rows owned by CTA j into j's buffer (16-byte DSMEM stores), one cluster barrier,
+// and every CTA sums the S partials of its rows and runs the fused epilogue on them, 8 columns per thread
+// (so the epilogue, too, is spread over S times the threads and stores whole 128-byte row segments).
+// One tile per cluster; no L2 atomics, deterministic summation order (source rank 0..S-1).
+// =====================================================================================================
+constexpr int SK_KS = 2;                    // k-slabs per stage: 1-2 stages per CTA is the regime here
+constexpr int SK_SMEM_MAX = 232448;         // 227 KB opt-in limit per CTA
+
+template <int BN>
+struct SkCfg {
+  static constexpr int A_SLAB = UG_BM * UG_BK * 2;
+  static constexpr int B_SLAB = BN * UG_BK * 2;
+  static constexpr int A_BYTES = SK_KS * A_SLAB;
+  static constexpr int B_BYTES = SK_KS * B_SLAB;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int RED_PITCH = BN * 4 + 16;          // +16 B: conflict-free 16-byte row-strided stores
+  static constexpr int RED_BYTES = UG_BM * RED_PITCH;    // S sources x 128/S owned rows
+  static constexpr int TAIL = 256;                       // barriers + TMEM slot
+  static constexpr int STAGES_FIT = (SK_SMEM_MAX - 1024 - RED_BYTES - TAIL) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_FIT > 4 ? 4 : STAGES_FIT;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + RED_BYTES + TAIL + 1024 /*align*/;
+  static_assert(STAGES >= 2, "pipeline too shallow");
+};
+
+template <int BN, class Epi>
+__global__ void __launch_bounds__(UG_THREADS, 1)
+umma_gemm_sk_kernel(const __grid_constant__ UmmaGemmParams p, const __grid_constant__ Epi epi_args, int coreM, int coreN,
+                    int augM, int augN) {
+  using Cfg = SkCfg<BN>;
+  constexpr int KS = SK_KS;
+  constexpr int BM = UG_BM;
+  constexpr int STAGES = Cfg::STAGES;
+  constexpr int STAGE_BYTES = Cfg::STAGE_BYTES;
+  constexpr int A_BYTES = Cfg::A_BYTES;
+  constexpr int A_SLAB = Cfg::A_SLAB, B_SLAB = Cfg::B_SLAB;
+  constexpr int TMEM_COLS = BN;
+  static_assert(BN == 64 || BN == 128, "two column halves of whole 32-column chunks; power-of-two TMEM allocation");
+  static_assert(STAGES * STAGE_BYTES >= Cfg::RED_BYTES, "the staging tile aliases the operand ring");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* red = smem + STAGES * STAGE_BYTES;            // [S sources][128/S rows][RED_PITCH]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(red + Cfg::RED_BYTES);
+  // bars[0..S) full, [S..2S) empty, [2S] tmem_full, [2S+1] partials received
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t bar_base = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  const uint32_t tfull_bar = bar_base + 8u * (2 * STAGES);
+  const uint32_t red_bar = bar_base + 8u * (2 * STAGES + 1);
+  const uint32_t red_base = smem_u32(red);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  warm_param_cache(p, epi_args, augN);
+  const int S = p.split;                                  // cluster size (2 or 4), == %cluster_nctaid.x
+  const int rank = (int)cluster_ctarank();
+  // grid = (tiles_n * S, tiles_m): no integer division on the way to the first instruction that matters
+  const int mb = (int)blockIdx.y, nb = (int)blockIdx.x >> (S == 4 ? 2 : 1);
+  // this CTA's share of the fat-stage list (pass 0 stages, then pass 1 stages)
+  const int nfs0 = (p.nslab[0] + KS - 1) / KS;
+  const int nfs_all = nfs0 + (p.n_ops > 1 ? (p.nslab[1] + KS - 1) / KS : 0);
+  const int g0 = rank * p.fs_per;
+  const int g1 = min(g0 + p.fs_per, nfs_all);            // host guarantees g0 < g1 for every rank
+  if (threadIdx.x == 0) {
+    trace_mark_ns(p, 0);
+    trace_mark(p, 1);
+  }
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < p.n_ops; ++i) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmA[i]) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&p.tmB[i]) : "memory");
+    }
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tfull_bar, 1);
+    mbar_init(red_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_expect_tx(red_bar, (uint32_t)((S - 1) * (BM / S) * Cfg::RED_PITCH));   // S-1 peers x owned rows
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();     // every peer is resident and its barriers are initialised before anyone stores into its shared memory (hidden by PDL)
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) pdl_launch_dependents();
+  pdl_wait();
+  if (threadIdx.x == 0) {
+    trace_mark(p, 2);
+    trace_mark_ns(p, 8);
+  }
+
+  if (warp == 0 || warp == UG_WARP_PB) {
+    // ===================== TMA producers: warp 0 feeds A, warp UG_WARP_PB feeds B =====================
+    const bool is_pa = warp == 0;
+    if (lane == 0) {
+      for (int g = g0; g < g1; ++g) {
+        const int it = g - g0;
+        const int s = it % STAGES;
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        const int pass = g >= nfs0 ? 1 : 0;
+        const int slab0 = (g - pass * nfs0) * KS;
+        const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + A_BYTES;
+        if (is_pa) {
+          mbar_expect_tx(full_bar(s), STAGE_BYTES);
+          if (!p.transA[pass]) tma_load_3d(sa, &p.tmA[pass], full_bar(s), 0, p.rowA[pass] + mb * BM, slab0);
+          else                 tma_load_3d(sa, &p.tmA[pass], full_bar(s), 0, p.rowA[pass] + slab0 * UG_BK, mb * (BM / 64));
+        } else {
+          if (!p.transB[pass]) tma_load_3d(sb, &p.tmB[pass], full_bar(s), 0, p.rowB[pass] + nb * BN, slab0);
+          else                 tma_load_3d(sb, &p.tmB[pass], full_bar(s), 0, p.rowB[pass] + slab0 * UG_BK, nb * (BN / 64));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      uint32_t accumulate = 0;
+      for (int g = g0; g < g1; ++g) {
+        const int it = g - g0;
+        const int s = it % STAGES;
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+        const int pass = g >= nfs0 ? 1 : 0;
+        const int f = g - pass * nfs0;
+        const int tA = p.transA[pass], tB = p.transB[pass];
+        const uint32_t idesc = make_idesc(BM, BN, tA, tB, pass == 1);
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        if (it == 0) trace_mark(p, 3);
+        const uint32_t sa = smem_base + s * STAGE_BYTES, sb = sa + A_BYTES;
+        const int slabs = min(KS, p.nslab[pass] - f * KS);
+#pragma unroll
+        for (int sl = 0; sl < KS; ++sl) {
+          if (sl < slabs) {
+#pragma unroll
+            for (int k4 = 0; k4 < UG_BK / UG_UK; ++k4) {
+              const uint64_t da = tA ? make_smem_desc(sa + sl * 8192 + k4 * 2048, KS * 8192, 1024)
+                                     : make_smem_desc(sa + sl * A_SLAB + k4 * 32, 16, 1024);
+              const uint64_t db = tB ? make_smem_desc(sb + sl * 8192 + k4 * 2048, KS * 8192, 1024)
+                                     : make_smem_desc(sb + sl * B_SLAB + k4 * 32, 16, 1024);
+              tc_mma_bf16(tmem_base, da, db, idesc, accumulate);
+              accumulate = 1;
+            }
+          }
+        }
+        tc_commit(empty_bar(s));
+      }
+      tc_commit(tfull_bar);   // this CTA's partial tile is complete
+      trace_mark(p, 4);
+    }
+  } else if (warp < UG_WARP_PB) {
+    // ============ phase 1 (epilogue warps): partial tile TMEM -> own staging -> bulk DSMEM copies ============
+    const int q = warp & 3;
+    const int R = BM / S;                                 // rows owned per CTA
+    constexpr int G = BN / 8;                             // 8-column segments per row
+    constexpr int UPT = BN / 32;                          // segments per thread in phase 2 (S = 2; half of it for S = 4)
+    uint32_t epoch = 0;
+    if constexpr (!Epi::kIsUpdate) epoch = epi_args.e.rng.epoch + (epi_args.e.rng.epoch_ptr ? *epi_args.e.rng.epoch_ptr : 0u);
+    // phase-2 work list of this thread; what the epilogue will read from global memory (bias / master weights)
+    // is requested NOW, so that its latency overlaps the mainloop and the exchange
+    const int units = R * G;
+    float pre[UPT][8];
+    bool has_pre[UPT];
+#pragma unroll
+    for (int i = 0; i < UPT; ++i) {
+      const int u = (int)threadIdx.x - 64 + i * 32 * UG_EPI_WARPS;
+      const int rowl = u / G, g = u - rowl * G;
+      has_pre[i] = u < units && epi_args.preload8(mb * BM + rank * R + rowl, nb * BN + g * 8, pre[i], coreM, coreN);
+    }
+
+    mbar_wait(tfull_bar, 0);
+    tc_fence_after();
+    if (warp == 2 && lane == 0) trace_mark(p, 5);
+    // staging tile [128 rows][RED_PITCH] aliases the operand ring: every MMA of this CTA has completed
+    const int row = q * 32 + lane;                        // accumulator row = TMEM lane
+    const uint32_t stg = smem_base + (uint32_t)(row * Cfg::RED_PITCH);
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    constexpr int CH_PER_WARP = (BN / 32) / 2;
+    const int ch0 = ((warp - 2) >> 2) * CH_PER_WARP;
+#pragma unroll 1
+    for (int ch = ch0; ch < ch0 + CH_PER_WARP; ++ch) {
+      if (nb * BN + ch * 32 >= p.N) break;  // warp-uniform; phase 2 skips the same columns
+      uint32_t v[32];
+      tc_ld32(trow + ch * 32, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        sts128(stg + ch * 128 + j * 16, __uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+               __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+    }
+    tc_fence_before();
+    if (threadIdx.x == 64) trace_mark(p, 12);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staging writes -> visible to the bulk-copy engine
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * UG_EPI_WARPS) : "memory");
+    if (lane == 0 && warp - 2 < S - 1) {
+      // rows owned by `peer` go to slot `rank` of peer's receive buffer; completion is counted on peer's barrier
+      const uint32_t peer = (uint32_t)((rank + 1 + (warp - 2)) % S);
+      const uint32_t bytes = (uint32_t)(R * Cfg::RED_PITCH);
+      const uint32_t src = smem_base + peer * bytes;
+      const uint32_t dst = mapa_shared(red_base + (uint32_t)rank * bytes, peer);
+      const uint32_t rbar = mapa_shared(red_bar, peer);
+      asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                   "r"(src), "r"(bytes), "r"(rbar)
+                   : "memory");
+    }
+    if (threadIdx.x == 64) trace_mark(p, 13);
+    mbar_wait(red_bar, 0);      // the S-1 partials of the owned rows have landed
+    if (threadIdx.x == 64) trace_mark(p, 14);
+    cluster_arrive();           // ... so every peer's copy INTO this CTA is done (peers may retire)
+    if (threadIdx.x == 64) trace_mark(p, 10);
+
+    // ============ phase 2: sum the S partials of the owned rows, fused epilogue on 8-column segments ============
+#pragma unroll
+    for (int i = 0; i < UPT; ++i) {
+      const int u = (int)threadIdx.x - 64 + i * 32 * UG_EPI_WARPS;
+      if (u < units) {
+        const int rowl = u / G, g = u - rowl * G;
+        const int m = mb * BM + rank * R + rowl;
+        const int n0 = nb * BN + g * 8;
+        if (m < p.M && n0 < p.N) {
+          float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int src = 0; src < 4; ++src) {               // fixed order: deterministic sums
+            if (src < S) {                                  // own partial: staging tile; the others: receive buffer
+              const uint32_t a = (src == rank ? smem_base : red_base) + (uint32_t)((src * R + rowl) * Cfg::RED_PITCH + g * 32);
+              const float4 x0 = lds128(a), x1 = lds128(a + 16);
+              acc[0] += x0.x; acc[1] += x0.y; acc[2] += x0.z; acc[3] += x0.w;
+              acc[4] += x1.x; acc[5] += x1.y; acc[6] += x1.z; acc[7] += x1.w;
+            }
+          }
+          if (threadIdx.x == 64 && i == 0) trace_mark(p, 11);
+          epi_args.apply8(epoch, m, n0, acc, has_pre[i] ? pre[i] : nullptr, coreM, coreN, augM, augN);
+        }
+      }
+    }
+    if (threadIdx.x == 64) trace_mark(p, 6);
+  }
+  if (warp < 2 || warp >= UG_WARP_PB) cluster_arrive();
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_wait();         // this CTA's outgoing copies have been received: its staging tile may go away
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
+                 : "memory");
+  }
+  if (threadIdx.x == 32) {
+    trace_mark(p, 7);
+    trace_mark_ns(p, 9);
+  }
+}
+
+
 struct UmmaActEpi {
   static constexpr bool kIsUpdate = false;
   dbn_act_epilogue e;
   __device__ __forceinline__ void apply(uint32_t epoch, int m, int n0, const float acc[32], int M, int N, int, int) const {
-    act_epilogue_row32<true>(e, epoch, m, n0, acc, M, N);
+    act_epilogue_row<32, true>(e, epoch, m, n0, acc, M, N);
+  }
+  // split-K kernel: 8-column segments; preload8 fetches early what apply8 would otherwise wait for (the bias)
+  __device__ __forceinline__ bool preload8(int m, int n0, float pre[8], int M, int N) const {
+    if (e.bias == nullptr || !act_vec_ok<8>(e, m, n0, M, N)) return false;
+    const float4* bp = reinterpret_cast<const float4*>(e.bias + n0);
+    const float4 t0 = __ldg(bp), t1 = __ldg(bp + 1);
+    pre[0] = t0.x; pre[1] = t0.y; pre[2] = t0.z; pre[3] = t0.w;
+    pre[4] = t1.x; pre[5] = t1.y; pre[6] = t1.z; pre[7] = t1.w;
+    return true;
+  }
+  __device__ __forceinline__ void apply8(uint32_t epoch, int m, int n0, const float acc[8], const float* pre, int M, int N,
+                                         int, int) const {
+    act_epilogue_row<8, true>(e, epoch, m, n0, acc, M, N, pre);
   }
 };
 struct UmmaUpdEpi {
   static constexpr bool kIsUpdate = true;
   dbn_update_epilogue e;
   __device__ __forceinline__ void apply(uint32_t, int m, int n0, const float acc[32], int M, int N, int augM, int augN) const {
-    upd_epilogue_row32(e, m, n0, acc, M, N, augM, augN);
+    upd_epilogue_row<32>(e, m, n0, acc, M, N, augM, augN);
+  }
+  __device__ __forceinline__ bool preload8(int m, int n0, float pre[8], int M, int N) const {   // master weights
+    if (e.raw.ptr != nullptr || !upd_vec_ok<8>(e, m, n0, M, N)) return false;
+    dbn_mat Wm;
+    Wm.ptr = e.W; Wm.ld = e.ldw; Wm.dtype = DBN_F32;
+    row_load<8>(Wm, m, n0, pre);
+    return true;
+  }
+  __device__ __forceinline__ void apply8(uint32_t, int m, int n0, const float acc[8], const float* pre, int M, int N,
+                                         int augM, int augN) const {
+    upd_epilogue_row<8>(e, m, n0, acc, M, N, augM, augN, pre);
   }
 };
 
@@ -711,6 +1046,83 @@ inline int umma_launch(cudaStream_t st, UmmaGemmParams& p, const Epi& epi, int c
   return DBN_OK;
 }
 
+// ---- split-K launch -------------------------------------------------------------------------------------
+inline bool umma_use_splitk() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DBN_B200_SPLITK");
+    v = (e == nullptr || e[0] != '0') ? 1 : 0;
+  }
+  return v == 1;
+}
+
+template <int BN, class Epi>
+inline void sk_launch_config(cudaLaunchConfig_t& cfg, cudaLaunchAttribute attr[2], int grid, int S, cudaStream_t st) {
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(UG_THREADS);
+  cfg.dynamicSmemBytes = SkCfg<BN>::SMEM;
+  cfg.stream = st;
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = S; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 2;
+}
+
+// Clusters of S CTAs of the split-K kernel the device can hold at once (GPC granularity makes this less than
+// SMs / S); 0 when the query fails, which disables the split plan.
+template <int BN, class Epi>
+inline int sk_max_clusters(int S) {
+  static int cache[9] = {-1, -1, -1, -1, -1, -1, -1, -1, -1};
+  if (S < 1 || S > 8) return 0;
+  if (cache[S] < 0) {
+    int n = 0;
+    if (cudaFuncSetAttribute(umma_gemm_sk_kernel<BN, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, SkCfg<BN>::SMEM) ==
+        cudaSuccess) {
+      cudaLaunchConfig_t cfg;
+      cudaLaunchAttribute attr[2];
+      sk_launch_config<BN, Epi>(cfg, attr, S, S, nullptr);
+      cfg.numAttrs = 1;   // the occupancy query only wants the cluster shape
+      if (cudaOccupancyMaxActiveClusters(&n, umma_gemm_sk_kernel<BN, Epi>, &cfg) != cudaSuccess) n = 0;
+    }
+    cudaGetLastError();
+    const int cap = umma_num_sms() / S;
+    cache[S] = n < cap ? n : cap;
+  }
+  return cache[S];
+}
+
+template <int BN, class Epi>
+inline int umma_launch_sk(cudaStream_t st, UmmaGemmParams& p, const Epi& epi, int coreM, int coreN, int augM, int augN) {
+  p.tiles_m = ceil_div(p.M, UG_BM);
+  p.tiles_n = ceil_div(p.N, BN);
+  p.group_m = std::max(1, std::min(p.tiles_m, 16));
+  const int n_tiles = p.tiles_m * p.tiles_n;
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[2];
+  sk_launch_config<BN, Epi>(cfg, attr, p.tiles_n * p.split, p.split, st);
+  cfg.gridDim = dim3(p.tiles_n * p.split, p.tiles_m);
+  (void)n_tiles;
+  DBN_CUDA_OK(cudaLaunchKernelEx(&cfg, umma_gemm_sk_kernel<BN, Epi>, p, epi, coreM, coreN, augM, augN));
+  DBN_LAUNCH_CHECK();
+  return DBN_OK;
+}
+
+// Cycle model of one batch-256 launch, fitted to the phase traces in profiles/r01_notes.md (B200, ~1.9 GHz):
+//   whole-K kernel : 216 + bytes/105 cycles per 64-wide k-slab (TMA feed of one SM) + ~3500 per 64 columns of epilogue
+//   split-K kernel : ~900 (BN=64) / 1100 (BN=128) per 2-slab stage, 530 + outgoing partial bytes / 12.8 for the
+//                    DSMEM exchange, ~2000 per 8-column segment a thread finalises
+inline long umma_slab_cycles(int bn) { return 216 + (long)(UG_BM + bn) * 128 / 105; }
+inline long umma_epi_cycles(int bn) { return 3500L * std::max(1, bn / 64); }
+inline long sk_cycles(int bn, int S, int per) {
+  const long stage = bn == 64 ? 900 : 1100;
+  const long out_bytes = (long)(S - 1) * (UG_BM / S) * (bn * 4 + 16);
+  const long units = std::max(1, (UG_BM / S) * (bn / 8) / (32 * UG_EPI_WARPS));
+  return per * stage + 530 + out_bytes * 10 / 128 + 2000 * units;
+}
+
 constexpr int UG2_KS = 2;   // CTA-pair kernel: 2 slabs (K = 128) per stage, 64 KB per CTA, 3 stages
 
 template <int BN, class Epi>
@@ -769,7 +1181,32 @@ inline int umma_gemm_run(cudaStream_t st, int M, int N, int augM, int augN, cons
   // operand bytes per MAC out of L2.  B boxes then cover half a tile.
   const bool two_cta = umma_use_2cta() && (long)ceil_div(p.M, 256) * ceil_div(p.N, 256) >= sms / 4;
   const int bm = UG_BM;
-  const int ks = two_cta ? UG2_KS : umma_ks(bm, bn);
+  // Small outputs: split K over a cluster of 2 or 4 CTAs per tile if the cycle model says the shorter K walk
+  // and the S-times wider epilogue beat the reduction (every CTA must get at least one stage of 2 slabs).
+  int sk_bn = 0, sk_S = 0, sk_per = 0;
+  if (!two_cta && umma_use_splitk()) {
+    long total_slabs = 0, fs_all = 0;
+    for (int i = 0; i < n_ops; ++i) {
+      total_slabs += ceil_div(ops[i].K, UG_BK);
+      fs_all += ceil_div(ceil_div(ops[i].K, UG_BK), SK_KS);
+    }
+    const long tiles_ns = (long)tm * ceil_div(p.N, bn);
+    long best_cost = ((tiles_ns + sms - 1) / sms) * (total_slabs * umma_slab_cycles(bn) + umma_epi_cycles(bn));
+    best_cost -= best_cost / 10;   // the split has to win by 10 %
+    for (int cand : {64, 128}) {
+      for (int S : {4, 2}) {
+        const int per = (int)((fs_all + S - 1) / S);
+        if ((fs_all + per - 1) / per != S) continue;             // some CTA would have nothing to contract
+        const long tiles = (long)tm * ceil_div(p.N, cand);
+        const int room = cand == 64 ? sk_max_clusters<64, Epi>(S) : sk_max_clusters<128, Epi>(S);
+        if (tiles > room) continue;
+        const long cost = sk_cycles(cand, S, per);
+        if (cost < best_cost) { best_cost = cost; sk_bn = cand; sk_S = S; sk_per = per; }
+      }
+    }
+  }
+  if (sk_S) bn = sk_bn;
+  const int ks = two_cta ? UG2_KS : sk_S ? SK_KS : umma_ks(bm, bn);
   const int b_rows = two_cta ? 128 : bn;        // B rows (K-major) / columns (MN-major) staged per CTA
   for (int i = 0; i < n_ops; ++i) {
     const dbn_operands& o = ops[i];
@@ -781,6 +1218,12 @@ inline int umma_gemm_run(cudaStream_t st, int M, int N, int augM, int augN, cons
     else           DBN_TRY(make_operand_map(&p.tmA[i], o.A, (uint64_t)o.row0_A + o.K, ceil_div(p.M, 64), ks * 64, bm / 64));
     if (!o.transB) DBN_TRY(make_operand_map(&p.tmB[i], o.B, (uint64_t)o.row0_B + p.N, p.nslab[i], b_rows, ks));
     else           DBN_TRY(make_operand_map(&p.tmB[i], o.B, (uint64_t)o.row0_B + o.K, ceil_div(p.N, 64), ks * 64, b_rows / 64));
+  }
+  if (sk_S) {
+    p.split = sk_S;
+    p.fs_per = sk_per;
+    if (bn == 128) return umma_launch_sk<128, Epi>(st, p, epi, M, N, augM, augN);
+    return umma_launch_sk<64, Epi>(st, p, epi, M, N, augM, augN);
   }
   if (two_cta) return umma_launch2<256, Epi>(st, p, epi, M, N, augM, augN);
   if (bn == 256) return umma_launch<256, Epi>(st, p, epi, M, N, augM, augN);

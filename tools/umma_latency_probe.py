@@ -43,13 +43,18 @@ def probe(label, fn, n_cta_hint=148):
                   t[:, 7] - t[:, 6], t[:, 7] - t[:, 1]], axis=1)
     med = np.median(d, axis=0)
     span_ns = t[:, 0].max() - t[:, 0].min()
-    print("%-34s ctas=%3d  " % (label, len(t)) + "  ".join("%s=%d" % (n, m) for n, m in zip(names, med)) +
+    extra = ""
+    if np.any(t[:, 10] != 0):   # split-K kernel: slot 10 = partial tiles exchanged (after the cluster barrier)
+        md = lambda a, b: np.median(t[:, a] - t[:, b])
+        extra = ("  [split-K: tmem->staging=%d, fence+bar+copy issue=%d, wait partials=%d, cluster arrive=%d, sum=%d, "
+                 "epilogue math+stores=%d]" % (md(12, 5), md(13, 12), md(14, 13), md(10, 14), md(11, 10), md(6, 11)))
+    print("%-34s ctas=%3d  " % (label, len(t)) + "  ".join("%s=%d" % (n, m) for n, m in zip(names, med)) + extra +
           "  | entry skew %d ns | kernel %d ns, next kernel entered %+d ns, passed its dependency wait %+d ns after this one's exit"
           % (span_ns, dur_a, gap_entry, gap_wait))
 
 
 rng = np.random.default_rng(0)
-for (V, H) in [(784, 500), (500, 2000)]:
+for (V, H) in [(784, 500), (500, 500), (500, 2000)]:
     B = 256
     W = rng.standard_normal((H, V)) / np.sqrt(V)
     layer = E.DeviceRbm(W, np.zeros(V), np.zeros(H), "sigmoid", "bf16", dev)
