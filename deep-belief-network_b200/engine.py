@@ -11,6 +11,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import threading
 
 import numpy as np
 import torch
@@ -111,15 +112,86 @@ def epoch_order(n):
     return first[second]
 
 
+class _PinnedPool:
+    """Process-wide cache of pinned staging buffers.  cudaHostAlloc / cudaFreeHost cost milliseconds and
+    synchronise the device, and a fit needs the same few sizes every time: buffers are handed out together
+    with the event of their last asynchronous copy and come back when their user is done."""
+    _free = []
+    _lock = threading.Lock()
+
+    @classmethod
+    def take(cls, nbytes):
+        nbytes = max(int(nbytes), 256)
+        with cls._lock:
+            pick = None
+            for i, (buf, ev) in enumerate(cls._free):
+                if nbytes <= buf.numel() <= 4 * nbytes + 65536:
+                    idle = ev is None or ev.query()
+                    if pick is None or (idle and not pick[1]) or (idle == pick[1] and buf.numel() < cls._free[pick[0]][0].numel()):
+                        pick = (i, idle)
+            if pick is not None:
+                buf, ev = cls._free.pop(pick[0])
+            else:
+                buf, ev = None, None
+        if buf is None:
+            return torch.empty(nbytes, dtype=torch.uint8).pin_memory(), torch.cuda.Event()
+        if ev is not None:
+            ev.synchronize()      # normally complete long ago
+        return buf, ev if ev is not None else torch.cuda.Event()
+
+    @classmethod
+    def give(cls, buf, ev):
+        with cls._lock:
+            if len(cls._free) < 64:
+                cls._free.append((buf, ev))
+
+
+_UPLOAD_STREAMS = {}
+
+
+def upload_f32(arr, device):
+    """Host array -> new fp32 device tensor WITHOUT waiting for the work already queued on the compute stream:
+    converted into a pinned staging buffer, copied on a dedicated upload stream, and the compute stream is
+    made to wait for that copy only.  (A pageable `.to(device)` blocks the host until everything queued before
+    it has run, which serialises the layers of a stacked fit.)"""
+    arr = np.asarray(arr)
+    key = (device.type, device.index)
+    up = _UPLOAD_STREAMS.get(key)
+    if up is None:
+        up = _UPLOAD_STREAMS[key] = torch.cuda.Stream(device=device)
+    buf, ev = _PinnedPool.take(arr.size * 4)
+    stage = buf[:arr.size * 4].view(torch.float32).view(arr.shape)
+    np.copyto(stage.numpy(), arr, casting="unsafe")     # converts float64 -> float32 on the way
+    cur = torch.cuda.current_stream(device)
+    with torch.cuda.stream(up):
+        dev = torch.empty(arr.shape, dtype=torch.float32, device=device)
+        dev.copy_(stage, non_blocking=True)
+        ev.record(up)
+    cur.wait_stream(up)
+    dev.record_stream(cur)        # allocated in the upload stream's pool, used on the compute stream
+    _PinnedPool.give(buf, ev)
+    return dev
+
+
 class _IndexFeeder:
-    """Double-buffered pinned staging of per-epoch permutation indices."""
+    """Double-buffered pinned staging of per-epoch permutation indices (the host runs at most two epochs
+    ahead of the device)."""
 
     def __init__(self, n, device):
-        self.host = [torch.empty(n, dtype=torch.int32).pin_memory() for _ in range(2)]
-        self.events = [torch.cuda.Event() for _ in range(2)]
+        pairs = [_PinnedPool.take(4 * n) for _ in range(2)]
+        self._bufs = [p[0] for p in pairs]
+        self.host = [b[:4 * n].view(torch.int32) for b in self._bufs]
+        self.events = [p[1] for p in pairs]
         self.used = [False, False]
         self.dev = torch.empty(n, dtype=torch.int32, device=device)
         self.slot = 0
+
+    def __del__(self):
+        try:
+            for b, e in zip(self._bufs, self.events):
+                _PinnedPool.give(b, e)
+        except Exception:      # interpreter shutdown
+            pass
 
     def push(self, order):
         s = self.slot
@@ -144,9 +216,9 @@ class DeviceRbm:
         self.act = ACT_IDS[activation]
         self.prec_name = precision
         self.prec = PREC_IDS[precision]
-        self.W = torch.as_tensor(np.ascontiguousarray(W), dtype=torch.float32).to(device).contiguous()
-        self.b = torch.as_tensor(np.asarray(b), dtype=torch.float32).to(device).contiguous()
-        self.c = torch.as_tensor(np.asarray(c), dtype=torch.float32).to(device).contiguous()
+        self.W = upload_f32(W, device)
+        self.b = upload_f32(b, device)
+        self.c = upload_f32(c, device)
         self.Wb = None
         if self.prec == L.PREC_BF16:
             self.Wb = torch.zeros(self.H, bf16_pitch(self.V), dtype=torch.bfloat16, device=device)
@@ -255,11 +327,14 @@ class DeviceRbm:
         ws.dbn_rows = int(bmax)   # the layout (and its ones columns) is fixed by this row count
         return ws
 
-    def fit(self, Xd, n_epochs, batch_size, k, lr, seed, rng_mode="philox", verbose=None, dp=None):
+    def fit(self, Xd, n_epochs, batch_size, k, lr, seed, rng_mode="philox", verbose=None, dp=None, orders=None,
+            sync=True):
         """BinaryRBM._stochastic_gradient_descent (dbn/models.py:96-122) on a device-resident fp32
         dataset Xd [N,V].  Each epoch = one CUDA graph: gather (double shuffle) + all mini-batch
         CD-k steps.  `verbose(epoch, err)` is called with the reconstruction error if given.
-        dp = (rank, world): data-parallel over mini-batch rows with a sum all-reduce of the deltas."""
+        dp = (rank, world): data-parallel over mini-batch rows with a sum all-reduce of the deltas.
+        orders: object whose get() returns the next epoch's row order (drawn ahead by the caller) instead of
+        drawing it here; sync=False returns with the work queued on the current stream."""
         n = int(Xd.shape[0])
         if n == 0 or n_epochs <= 0:
             return
@@ -267,10 +342,11 @@ class DeviceRbm:
             return self._fit_dp(Xd, n_epochs, batch_size, k, lr, seed, verbose, dp)
         runner = RbmEpochRunner(self, Xd, batch_size, k, lr, seed, rng_mode)
         for epoch in range(1, n_epochs + 1):
-            runner.run()
+            runner.run(orders.get() if orders is not None else None)
             if verbose is not None:
                 verbose(epoch, self.reconstruction_error(Xd))
-        torch.cuda.current_stream().synchronize()
+        if sync:
+            torch.cuda.current_stream().synchronize()
 
     def _fit_dp(self, Xd, n_epochs, batch_size, k, lr, seed, verbose, dp):
         runner = DpRbmEpochRunner(self, Xd, batch_size, k, lr, seed, dp)

@@ -15,7 +15,10 @@ the reference's `np.random` uniform / binomial stream (parity runs).
 """
 from __future__ import annotations
 
+import os
 import pickle
+import queue
+import threading
 
 import numpy as np
 from scipy.stats import truncnorm
@@ -41,6 +44,56 @@ def _draw_seed():
     """Philox key drawn from the global np.random stream, so `np.random.seed(...)` stays the
     user-facing reproducibility knob (reference: example_classification.py:3)."""
     return int(np.random.randint(0, 2 ** 31 - 1)) | (int(np.random.randint(0, 2 ** 31 - 1)) << 32)
+
+
+class _DrawAhead:
+    """Everything a greedy pre-training run takes from the global `np.random` stream -- per layer the
+    parameter initialisation (dbn/models.py:55-69), the Philox key, and one double shuffle per epoch
+    (:106 + utils.py:12) -- is data independent.  A helper thread draws it, in EXACTLY the order the
+    sequential code would (so a seeded fit gives the same model either way), while the caller uploads the
+    dataset and keeps the GPU busy with the previous layer: legacy `randn` costs ~16 ns per weight, which
+    at 784-[500,500,2000] is as long as the whole epoch takes on the device.  NumPy releases the GIL while
+    it fills; the queue is bounded so a many-epoch fit never holds more than a few permutations."""
+
+    def __init__(self, jobs, depth=4):
+        self._q = queue.Queue(maxsize=depth)
+        self._stop = False
+        self._t = threading.Thread(target=self._run, args=(jobs,), daemon=True)
+        self._t.start()
+
+    def _put(self, item):
+        while not self._stop:
+            try:
+                self._q.put(item, timeout=0.05)
+                return True
+            except queue.Full:
+                pass
+        return False
+
+    def _run(self, jobs):
+        try:
+            for item in jobs:
+                if not self._put(("ok", item)):
+                    return
+        except BaseException as e:   # surfaces in the caller, at the draw that failed
+            self._put(("err", e))
+
+    def get(self):
+        kind, v = self._q.get()
+        if kind == "err":
+            raise v
+        return v
+
+    def close(self):
+        """Stop drawing (after an error in the caller) and wait for the helper: nobody else touches the global
+        stream while it runs."""
+        self._stop = True
+        while self._t.is_alive():
+            try:
+                self._q.get_nowait()
+            except queue.Empty:
+                pass
+            self._t.join(timeout=0.01)
 
 
 class BaseModel(object):
@@ -74,21 +127,21 @@ class BinaryRBM(BaseEstimator, TransformerMixin, BaseModel):
         self.rng = rng
 
     # ---- parameter initialisation: same draws, same order as dbn/models.py:55-69 ----
-    def _init_params(self, n_visible):
-        self.n_visible_units = n_visible
+    def _draw_params(self, n_visible):
         h, s = self.n_hidden_units, np.sqrt(n_visible)
         if self.activation_function == 'sigmoid':
-            self.W = np.random.randn(h, n_visible) / s
-            self.c = np.random.randn(h) / s
-            self.b = np.random.randn(n_visible) / s
-            self._activation_function_class = SigmoidActivationFunction
-        elif self.activation_function == 'relu':
-            self.W = truncnorm.rvs(-0.2, 0.2, size=[h, n_visible]) / s
-            self.c = np.full(h, 0.1) / s
-            self.b = np.full(n_visible, 0.1) / s
-            self._activation_function_class = ReLUActivationFunction
-        else:
-            raise ValueError("Invalid activation function.")
+            W = np.random.randn(h, n_visible) / s
+            c = np.random.randn(h) / s
+            b = np.random.randn(n_visible) / s
+            return W, c, b, SigmoidActivationFunction
+        if self.activation_function == 'relu':
+            W = truncnorm.rvs(-0.2, 0.2, size=[h, n_visible]) / s
+            return W, np.full(h, 0.1) / s, np.full(n_visible, 0.1) / s, ReLUActivationFunction
+        raise ValueError("Invalid activation function.")
+
+    def _init_params(self, n_visible, drawn=None):
+        self.n_visible_units = n_visible
+        self.W, self.c, self.b, self._activation_function_class = drawn if drawn is not None else self._draw_params(n_visible)
 
     def _resolved_precision(self):
         return E.resolve_precision(self.precision, self.n_visible_units, self.n_hidden_units, self.batch_size)
@@ -97,20 +150,27 @@ class BinaryRBM(BaseEstimator, TransformerMixin, BaseModel):
         return E.DeviceRbm(self.W, self.b, self.c, self.activation_function,
                            precision or self._resolved_precision(), _device())
 
-    def _fit_device(self, Xd, dp=None):
+    def _fit_device(self, Xd, dp=None, draws=None, defer_export=False):
         """Initialise and train on a device-resident fp32 dataset; returns the DeviceRbm so a
-        stacked DBN can keep transforming on the device."""
-        self._init_params(int(Xd.shape[1]))
+        stacked DBN can keep transforming on the device.  `draws` (a _DrawAhead) supplies, in order, the
+        initial parameters, the Philox key and one shuffle per epoch instead of drawing them here;
+        `defer_export` leaves the layer's work queued on the stream and the fitted parameters on the device
+        (the caller assigns `W, b, c = layer.export()` later), so the host can go on to the next layer."""
+        self._init_params(int(Xd.shape[1]), draws.get() if draws is not None else None)
         if self.optimization_algorithm != 'sgd':
             raise ValueError("Invalid optimization algorithm.")
         layer = self._device_layer()
-        seed = _draw_seed() if self.rng == 'philox' else 0   # 'numpy' replays the reference stream untouched
+        if draws is not None:
+            seed = draws.get()
+        else:
+            seed = _draw_seed() if self.rng == 'philox' else 0   # 'numpy' replays the reference stream untouched
         cb = None
         if self.verbose:
             cb = lambda it, err: print(">> Epoch %d finished \tRBM Reconstruction error %f" % (it, err))
         layer.fit(Xd, self.n_epochs, self.batch_size, self.contrastive_divergence_iter, self.learning_rate, seed,
-                  rng_mode=self.rng, verbose=cb, dp=dp)
-        self.W, self.b, self.c = layer.export()
+                  rng_mode=self.rng, verbose=cb, dp=dp, orders=draws, sync=not defer_export)
+        if not defer_export:
+            self.W, self.b, self.c = layer.export()
         return layer
 
     def fit(self, X):
@@ -169,12 +229,39 @@ class UnsupervisedDBN(BaseEstimator, TransformerMixin, BaseModel):
         if self.verbose:
             print("[START] Pre-training step:")
         data = Xd
-        for rbm in self.rbm_layers:      # strictly sequential: layer l+1 sees layer l's final features
-            layer = rbm._fit_device(data)
-            data = layer.transform(data)  # stays in HBM between layers
+        ahead = (self.rbm_class is BinaryRBM and self.rng == 'philox' and
+                 os.environ.get("DBN_B200_DRAW_AHEAD", "1") != "0")
+        if not ahead:
+            for rbm in self.rbm_layers:      # strictly sequential: layer l+1 sees layer l's final features
+                layer = rbm._fit_device(data)
+                data = layer.transform(data)  # stays in HBM between layers
+        else:
+            # same draws in the same order, made by a helper thread that runs ahead of the device; every
+            # layer's launches are queued without waiting for the previous layer, parameters come back at the end
+            draws = _DrawAhead(self._draw_jobs(int(Xd.shape[0]), int(Xd.shape[1])))
+            try:
+                fitted = []
+                for rbm in self.rbm_layers:
+                    layer = rbm._fit_device(data, draws=draws, defer_export=True)
+                    fitted.append((rbm, layer))
+                    data = layer.transform(data)
+                for rbm, layer in fitted:
+                    rbm.W, rbm.b, rbm.c = layer.export()
+            finally:
+                draws.close()
         if self.verbose:
             print("[END] Pre-training step")
         return self
+
+    def _draw_jobs(self, n, n_features):
+        """The np.random draws of one greedy pre-training run, in sequential order (generator for _DrawAhead)."""
+        v = n_features
+        for rbm in self.rbm_layers:
+            yield rbm._draw_params(v)
+            yield _draw_seed()
+            for _ in range(rbm.n_epochs if n > 0 else 0):
+                yield E.epoch_order(n)
+            v = rbm.n_hidden_units
 
     def fit(self, X, y=None):
         """Pre-train every layer on the previous layer's features (dbn/models.py:248-276)."""

@@ -106,3 +106,59 @@ def test_precision_auto_policy():
 def test_public_names():
     assert set(dbn_b200.__all__) == {"BinaryRBM", "UnsupervisedDBN", "SupervisedDBNClassification",
                                      "SupervisedDBNRegression"}
+
+
+def test_draw_ahead_thread_takes_the_same_draws_in_the_same_order():
+    """The helper thread of the stacked pre-training consumes np.random exactly like the sequential code:
+    per layer W, c, b (dbn/models.py:55-69), the Philox key, one double shuffle per epoch."""
+    from dbn_b200 import UnsupervisedDBN, BinaryRBM
+    from dbn_b200 import models as M, engine as E
+
+    def make():
+        m = UnsupervisedDBN(hidden_layers_structure=[7, 5], n_epochs_rbm=3, batch_size=4, verbose=False)
+        m.rbm_layers = [BinaryRBM(n_hidden_units=h, n_epochs=3, verbose=False) for h in (7, 5)]
+        return m
+
+    np.random.seed(3)
+    seq, v = [], 9
+    for h in (7, 5):
+        r = BinaryRBM(n_hidden_units=h)
+        seq.append(r._draw_params(v))
+        seq.append(M._draw_seed())
+        seq += [E.epoch_order(11) for _ in range(3)]
+        v = h
+    tail_seq = np.random.random_sample()
+
+    np.random.seed(3)
+    d = M._DrawAhead(make()._draw_jobs(11, 9), depth=2)
+    got = [d.get() for _ in range(len(seq))]
+    d.close()
+    tail_thr = np.random.random_sample()
+    assert tail_seq == tail_thr
+    for a, b in zip(seq, got):
+        if isinstance(a, tuple):
+            assert all(np.array_equal(x, y) for x, y in zip(a[:3], b[:3])) and a[3] is b[3]
+        else:
+            assert np.array_equal(a, b)
+
+
+def test_draw_ahead_reports_errors_at_the_failing_draw_and_stops():
+    from dbn_b200 import models as M
+
+    def jobs():
+        yield 1
+        raise ValueError("Invalid activation function.")
+
+    d = M._DrawAhead(jobs())
+    assert d.get() == 1
+    with pytest.raises(ValueError):
+        d.get()
+    d.close()
+
+    def endless():
+        while True:
+            yield np.random.random_sample()
+    d = M._DrawAhead(endless(), depth=2)
+    d.get()
+    d.close()          # must not hang although the generator never ends
+    assert not d._t.is_alive()
