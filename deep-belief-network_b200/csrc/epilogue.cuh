@@ -28,14 +28,18 @@ __device__ __forceinline__ float apply_act(int act, float x) {
 }
 
 // Activation epilogue on 4 columns.  M, N = logical output extent (stores are masked to it).
+// pre_bias: bias[n4..n4+3] if the caller already holds it (split-K kernel: requested before the exchange), else nullptr
 template <bool kFast = false>
 __device__ __forceinline__ void act_epilogue_quad(const dbn_act_epilogue& e, uint32_t epoch, int m, int n4,
-                                                  const float acc[4], int M, int N) {
+                                                  const float acc[4], int M, int N, const float* pre_bias = nullptr) {
   if (m >= M || n4 >= N) return;
   const int nvalid = min(4, N - n4);
   float a[4];
   float bv[4] = {0.f, 0.f, 0.f, 0.f};
-  if (e.bias != nullptr) {
+  if (e.bias != nullptr && pre_bias != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) bv[j] = pre_bias[j];
+  } else if (e.bias != nullptr) {
     if (nvalid == 4 && (reinterpret_cast<uintptr_t>(e.bias + n4) & 15) == 0) {
       const float4 t = __ldg(reinterpret_cast<const float4*>(e.bias + n4));
       bv[0] = t.x; bv[1] = t.y; bv[2] = t.z; bv[3] = t.w;
@@ -80,8 +84,9 @@ __device__ __forceinline__ void act_epilogue_quad(const dbn_act_epilogue& e, uin
 }
 
 // Update epilogue on 4 columns of the (M+augM) x (N+augN) accumulator.
+// pre_w: W[m, n4..n4+3] if the caller already holds it (whole quad inside the core block), else nullptr
 __device__ __forceinline__ void upd_epilogue_quad(const dbn_update_epilogue& e, int m, int n4, const float acc[4],
-                                                  int M, int N, int augM, int augN) {
+                                                  int M, int N, int augM, int augN, const float* pre_w = nullptr) {
   const int Mt = M + augM, Nt = N + augN;
   if (m >= Mt || n4 >= Nt) return;
   const int nvalid = min(4, Nt - n4);
@@ -95,7 +100,12 @@ __device__ __forceinline__ void upd_epilogue_quad(const dbn_update_epilogue& e, 
       float w[4];
       dbn_mat Wm;
       Wm.ptr = e.W; Wm.ld = e.ldw; Wm.dtype = DBN_F32;
-      mat_load4(Wm, m, n4, w, ncore);
+      if (pre_w != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) w[j] = pre_w[j];
+      } else {
+        mat_load4(Wm, m, n4, w, ncore);
+      }
 #pragma unroll
       for (int j = 0; j < 4; ++j) w[j] = e.decay * w[j] + e.scale * acc[j];
       mat_store4(Wm, m, n4, w, ncore);

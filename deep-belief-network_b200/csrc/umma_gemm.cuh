@@ -137,6 +137,17 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t v[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t v[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 // Shared-memory matrix descriptor (sm_100 "version 1"), 128-byte swizzle.
 //   bits [0,14) start address >> 4 | [16,30) leading byte offset >> 4 | [32,46) stride byte offset >> 4
 //   bits [46,48) = 1 (Blackwell) | [61,64) layout type = 2 (SWIZZLE_128B)
@@ -171,26 +182,26 @@ __device__ __forceinline__ void tile_coords(const UmmaGemmParams& p, int tile, i
   nb = r / gm;
 }
 
-// The batch-256 launches run ONE tile per CTA: every kernel parameter is read exactly once per SM, out of a cold
-// constant cache, and the epilogue's option tree reads them one dependent branch at a time (load, test, branch,
-// next load ...).  Touching every 64-byte chunk of the parameter block up front, one chunk per idle epilogue warp
-// and all in flight together, turns that chain of serial misses into a single overlapped one during setup.
-template <class Epi>
-__device__ __forceinline__ void warm_param_cache(const UmmaGemmParams& p, const Epi& ea, int tail) {
-  const int w = threadIdx.x >> 5;
-  const uint32_t* p32 = reinterpret_cast<const uint32_t*>(&p) + 128;   // past the four tensor maps (TMA's own fetch)
-  const uint32_t* e32 = reinterpret_cast<const uint32_t*>(&ea);
-  constexpr int PW = (int)(sizeof(UmmaGemmParams) - 512) / 4, EW = (int)sizeof(Epi) / 4;
-  uint32_t v = (uint32_t)tail;
-  if (w == 2) v = p32[0];
-  if (w == 3) v = p32[PW > 16 ? 16 : PW - 1];
-  if (w == 4) v = p32[PW - 1];
-  if (w == 5) v = e32[0];
-  if (w == 6) v = e32[EW > 16 ? 16 : EW - 1];
-  if (w == 7) v = e32[EW > 32 ? 32 : EW - 1];
-  if (w == 8) v = e32[EW - 1];
-  asm volatile("" ::"r"(v));
+// Kernel parameters live in the constant bank; every use compiles to an LDC next to its consumer, and the
+// epilogue's option tree needs ~40 of them.  In a one-tile-per-CTA launch those loads sit between "partials
+// received" and the first store -- measured ~800 cycles before the first useful instruction.  Reading the whole
+// struct into registers BEFORE the epilogue warps wait for the accumulator moves them off the critical path.
+// The identity shuffle makes each word opaque to ptxas, which otherwise rematerialises a parameter load at its
+// use (an empty inline asm only hides the value from the front end).  Call with all 32 lanes converged.
+template <class T>
+__device__ __forceinline__ T params_to_registers(const T& src) {
+  static_assert(sizeof(T) % 4 == 0, "whole 32-bit words");
+  constexpr int NW = (int)sizeof(T) / 4;
+  uint32_t w[NW];
+  const uint32_t* s32 = reinterpret_cast<const uint32_t*>(&src);
+  const int self = (int)(threadIdx.x & 31);
+#pragma unroll
+  for (int i = 0; i < NW; ++i) w[i] = __shfl_sync(0xffffffffu, s32[i], self);
+  T out;
+  memcpy(&out, w, sizeof(T));
+  return out;
 }
+__device__ __forceinline__ int to_register(int v) { return __shfl_sync(0xffffffffu, v, (int)(threadIdx.x & 31)); }
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
@@ -228,7 +239,6 @@ umma_gemm_kernel(const __grid_constant__ UmmaGemmParams p, const __grid_constant
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  warm_param_cache(p, epi_args, augN);
   const int n_tiles = p.tiles_m * p.tiles_n;
   if (threadIdx.x == 0) {
     trace_mark_ns(p, 0);
@@ -480,7 +490,6 @@ umma_gemm2_kernel(const __grid_constant__ UmmaGemmParams p, const __grid_constan
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  warm_param_cache(p, epi_args, augN);
   const uint32_t cta = cluster_ctarank();
   const bool leader = cta == 0;
   const int n_tiles = p.tiles_m * p.tiles_n;     // tiles_m counts 256-row blocks here
@@ -635,13 +644,20 @@ umma_gemm2_kernel(const __grid_constant__ UmmaGemmParams p, const __grid_constan
 // tiles, so the persistent kernel above leaves 130 SMs idle while 16 CTAs walk all of K at the pace of
 // their own TMA feed.  Here a cluster of S = 2 or 4 CTAs shares ONE 128 x BN tile: CTA r contracts a
 // contiguous K range (fat stages [r * fs_per, (r+1) * fs_per) of the pass list) into its own TMEM, then
-// the partial tiles are reduce-scattered by rows through distributed shared memory -- each CTA pushes
-// the 128/S accumulator rows owned by CTA j into j's buffer (16-byte DSMEM stores), one cluster barrier,
-// and every CTA sums the S partials of its rows and runs the fused epilogue on them, 8 columns per thread
-// (so the epilogue, too, is spread over S times the threads and stores whole 128-byte row segments).
+// the partial tiles are reduce-scattered by rows through distributed shared memory -- each CTA stages its
+// accumulator in its own shared memory and pushes the 128/S rows owned by CTA j into j's receive buffer with
+// ONE bulk DSMEM copy that completes on j's mbarrier -- and every CTA sums the S partials of its rows and
+// runs the fused epilogue on them quad by quad, consecutive lanes on consecutive columns (so the epilogue,
+// too, is spread over S times the threads and stores whole 128-byte row segments).
 // One tile per cluster; no L2 atomics, deterministic summation order (source rank 0..S-1).
 // =====================================================================================================
 constexpr int SK_KS = 2;                    // k-slabs per stage: 1-2 stages per CTA is the regime here
+// 16 epilogue warps (four per TMEM lane quarter, a quarter of the columns each): the exchange and the epilogue of a
+// one-tile launch are chains of dependent instructions run ONCE, i.e. ~4 cycles per instruction per warp whatever
+// the issue width -- the way to shorten them is fewer instructions per thread and more warps per scheduler.
+constexpr int SK_EPI_WARPS = 16;
+constexpr int SK_THREADS = 64 + 32 * SK_EPI_WARPS + 32;
+constexpr int SK_WARP_PB = 2 + SK_EPI_WARPS;
 constexpr int SK_SMEM_MAX = 232448;         // 227 KB opt-in limit per CTA
 
 template <int BN>
@@ -661,7 +677,7 @@ struct SkCfg {
 };
 
 template <int BN, class Epi>
-__global__ void __launch_bounds__(UG_THREADS, 1)
+__global__ void __launch_bounds__(SK_THREADS, 1)
 umma_gemm_sk_kernel(const __grid_constant__ UmmaGemmParams p, const __grid_constant__ Epi epi_args, int coreM, int coreN,
                     int augM, int augN) {
   using Cfg = SkCfg<BN>;
@@ -690,7 +706,6 @@ umma_gemm_sk_kernel(const __grid_constant__ UmmaGemmParams p, const __grid_const
   const uint32_t red_base = smem_u32(red);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  warm_param_cache(p, epi_args, augN);
   const int S = p.split;                                  // cluster size (2 or 4), == %cluster_nctaid.x
   const int rank = (int)cluster_ctarank();
   // grid = (tiles_n * S, tiles_m): no integer division on the way to the first instruction that matters
@@ -738,8 +753,8 @@ umma_gemm_sk_kernel(const __grid_constant__ UmmaGemmParams p, const __grid_const
     trace_mark_ns(p, 8);
   }
 
-  if (warp == 0 || warp == UG_WARP_PB) {
-    // ===================== TMA producers: warp 0 feeds A, warp UG_WARP_PB feeds B =====================
+  if (warp == 0 || warp == SK_WARP_PB) {
+    // ===================== TMA producers: warp 0 feeds A, warp SK_WARP_PB feeds B =====================
     const bool is_pa = warp == 0;
     if (lane == 0) {
       for (int g = g0; g < g1; ++g) {
@@ -796,25 +811,24 @@ umma_gemm_sk_kernel(const __grid_constant__ UmmaGemmParams p, const __grid_const
       tc_commit(tfull_bar);   // this CTA's partial tile is complete
       trace_mark(p, 4);
     }
-  } else if (warp < UG_WARP_PB) {
+  } else if (warp < SK_WARP_PB) {
     // ============ phase 1 (epilogue warps): partial tile TMEM -> own staging -> bulk DSMEM copies ============
     const int q = warp & 3;
+    const Epi ea = params_to_registers(epi_args);         // ... and everything else phase 2 reads from the constant bank
+    const int pM = to_register(p.M), pN = to_register(p.N);
+    coreM = to_register(coreM); coreN = to_register(coreN); augM = to_register(augM); augN = to_register(augN);
     const int R = BM / S;                                 // rows owned per CTA
-    constexpr int G = BN / 8;                             // 8-column segments per row
-    constexpr int UPT = BN / 32;                          // segments per thread in phase 2 (S = 2; half of it for S = 4)
+    constexpr int QPR = BN / 4;                           // 4-column quads per row
+    constexpr int ETHREADS = 32 * SK_EPI_WARPS;
     uint32_t epoch = 0;
-    if constexpr (!Epi::kIsUpdate) epoch = epi_args.e.rng.epoch + (epi_args.e.rng.epoch_ptr ? *epi_args.e.rng.epoch_ptr : 0u);
-    // phase-2 work list of this thread; what the epilogue will read from global memory (bias / master weights)
-    // is requested NOW, so that its latency overlaps the mainloop and the exchange
-    const int units = R * G;
-    float pre[UPT][8];
-    bool has_pre[UPT];
-#pragma unroll
-    for (int i = 0; i < UPT; ++i) {
-      const int u = (int)threadIdx.x - 64 + i * 32 * UG_EPI_WARPS;
-      const int rowl = u / G, g = u - rowl * G;
-      has_pre[i] = u < units && epi_args.preload8(mb * BM + rank * R + rowl, nb * BN + g * 8, pre[i], coreM, coreN);
-    }
+    if constexpr (!Epi::kIsUpdate) epoch = ea.e.rng.epoch + (ea.e.rng.epoch_ptr ? *ea.e.rng.epoch_ptr : 0u);
+    // Phase-2 work list of this thread: quads tid, tid + 256, ... of the owned rows (16+ consecutive lanes cover a
+    // row: coalesced stores).  What the first quad's epilogue reads from global memory (bias / master weights) is
+    // requested NOW, so that its latency overlaps the mainloop and the exchange.
+    const int quads = R * QPR;
+    const int tid = (int)threadIdx.x - 64;
+    float pre[4];
+    bool has_pre = tid < quads && ea.preload4(mb * BM + rank * R + tid / QPR, nb * BN + (tid % QPR) * 4, pre, coreM, coreN);
 
     mbar_wait(tfull_bar, 0);
     tc_fence_after();
@@ -823,22 +837,21 @@ umma_gemm_sk_kernel(const __grid_constant__ UmmaGemmParams p, const __grid_const
     const int row = q * 32 + lane;                        // accumulator row = TMEM lane
     const uint32_t stg = smem_base + (uint32_t)(row * Cfg::RED_PITCH);
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-    constexpr int CH_PER_WARP = (BN / 32) / 2;
-    const int ch0 = ((warp - 2) >> 2) * CH_PER_WARP;
-#pragma unroll 1
-    for (int ch = ch0; ch < ch0 + CH_PER_WARP; ++ch) {
-      if (nb * BN + ch * 32 >= p.N) break;  // warp-uniform; phase 2 skips the same columns
-      uint32_t v[32];
-      tc_ld32(trow + ch * 32, v);
+    constexpr int CW = BN / (SK_EPI_WARPS / 4);           // columns drained by this warp: 16 (BN = 64) or 32
+    const int col0 = ((warp - 2) >> 2) * CW;
+    if (nb * BN + col0 < pN) {                            // warp-uniform; phase 2 skips the same columns
+      uint32_t v[CW];
+      if constexpr (CW == 32) tc_ld32(trow + col0, v);
+      else tc_ld16(trow + col0, v);
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        sts128(stg + ch * 128 + j * 16, __uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+      for (int j = 0; j < CW / 4; ++j)
+        sts128(stg + col0 * 4 + j * 16, __uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
                __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
     }
     tc_fence_before();
     if (threadIdx.x == 64) trace_mark(p, 12);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // staging writes -> visible to the bulk-copy engine
-    asm volatile("bar.sync 1, %0;" ::"n"(32 * UG_EPI_WARPS) : "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * SK_EPI_WARPS) : "memory");
     if (lane == 0 && warp - 2 < S - 1) {
       // rows owned by `peer` go to slot `rank` of peer's receive buffer; completion is counted on peer's barrier
       const uint32_t peer = (uint32_t)((rank + 1 + (warp - 2)) % S);
@@ -856,33 +869,37 @@ umma_gemm_sk_kernel(const __grid_constant__ UmmaGemmParams p, const __grid_const
     cluster_arrive();           // ... so every peer's copy INTO this CTA is done (peers may retire)
     if (threadIdx.x == 64) trace_mark(p, 10);
 
-    // ============ phase 2: sum the S partials of the owned rows, fused epilogue on 8-column segments ============
+    // ============ phase 2: sum the S partials of the owned rows, fused epilogue quad by quad ============
+    // A ROLLED loop on purpose: every CTA executes this code once, from a cold instruction cache, where straight-
+    // line code runs at ~4 cycles per instruction (profiles/r01_notes.md); a second trip through a small loop body
+    // is served from the instruction cache, a second unrolled copy is not.
+#pragma unroll 1
+    for (int q = tid; q < quads; q += ETHREADS) {
+      const int rowl = q / QPR, c4 = q - rowl * QPR;
+      const int m = mb * BM + rank * R + rowl;
+      const int n4 = nb * BN + c4 * 4;
+      float nxt[4];
+      const int qn = q + ETHREADS;
+      const bool has_nxt = qn < quads && ea.preload4(mb * BM + rank * R + qn / QPR, nb * BN + (qn % QPR) * 4, nxt, coreM, coreN);
+      if (m < pM && n4 < pN) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int i = 0; i < UPT; ++i) {
-      const int u = (int)threadIdx.x - 64 + i * 32 * UG_EPI_WARPS;
-      if (u < units) {
-        const int rowl = u / G, g = u - rowl * G;
-        const int m = mb * BM + rank * R + rowl;
-        const int n0 = nb * BN + g * 8;
-        if (m < p.M && n0 < p.N) {
-          float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-          for (int src = 0; src < 4; ++src) {               // fixed order: deterministic sums
-            if (src < S) {                                  // own partial: staging tile; the others: receive buffer
-              const uint32_t a = (src == rank ? smem_base : red_base) + (uint32_t)((src * R + rowl) * Cfg::RED_PITCH + g * 32);
-              const float4 x0 = lds128(a), x1 = lds128(a + 16);
-              acc[0] += x0.x; acc[1] += x0.y; acc[2] += x0.z; acc[3] += x0.w;
-              acc[4] += x1.x; acc[5] += x1.y; acc[6] += x1.z; acc[7] += x1.w;
-            }
+        for (int src = 0; src < 4; ++src) {                 // fixed order: deterministic sums
+          if (src < S) {                                    // own partial: staging tile; the others: receive buffer
+            const float4 x = lds128((src == rank ? smem_base : red_base) + (uint32_t)((src * R + rowl) * Cfg::RED_PITCH + c4 * 16));
+            acc[0] += x.x; acc[1] += x.y; acc[2] += x.z; acc[3] += x.w;
           }
-          if (threadIdx.x == 64 && i == 0) trace_mark(p, 11);
-          epi_args.apply8(epoch, m, n0, acc, has_pre[i] ? pre[i] : nullptr, coreM, coreN, augM, augN);
         }
+        if (threadIdx.x == 64 && q == tid) trace_mark(p, 11);
+        ea.apply4(epoch, m, n4, acc, has_pre ? pre : nullptr, coreM, coreN, augM, augN);
       }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) pre[j] = nxt[j];
+      has_pre = has_nxt;
     }
     if (threadIdx.x == 64) trace_mark(p, 6);
   }
-  if (warp < 2 || warp >= UG_WARP_PB) cluster_arrive();
+  if (warp < 2 || warp >= SK_WARP_PB) cluster_arrive();
 
   tc_fence_before();
   __syncthreads();
@@ -905,18 +922,16 @@ struct UmmaActEpi {
   __device__ __forceinline__ void apply(uint32_t epoch, int m, int n0, const float acc[32], int M, int N, int, int) const {
     act_epilogue_row<32, true>(e, epoch, m, n0, acc, M, N);
   }
-  // split-K kernel: 8-column segments; preload8 fetches early what apply8 would otherwise wait for (the bias)
-  __device__ __forceinline__ bool preload8(int m, int n0, float pre[8], int M, int N) const {
-    if (e.bias == nullptr || !act_vec_ok<8>(e, m, n0, M, N)) return false;
-    const float4* bp = reinterpret_cast<const float4*>(e.bias + n0);
-    const float4 t0 = __ldg(bp), t1 = __ldg(bp + 1);
-    pre[0] = t0.x; pre[1] = t0.y; pre[2] = t0.z; pre[3] = t0.w;
-    pre[4] = t1.x; pre[5] = t1.y; pre[6] = t1.z; pre[7] = t1.w;
+  // split-K kernel: one quad (4 columns) per loop iteration; preload4 requests early what apply4 would wait for
+  __device__ __forceinline__ bool preload4(int m, int n4, float pre[4], int M, int N) const {
+    if (e.bias == nullptr || m >= M || n4 + 4 > N || (reinterpret_cast<uintptr_t>(e.bias + n4) & 15) != 0) return false;
+    const float4 t = __ldg(reinterpret_cast<const float4*>(e.bias + n4));
+    pre[0] = t.x; pre[1] = t.y; pre[2] = t.z; pre[3] = t.w;
     return true;
   }
-  __device__ __forceinline__ void apply8(uint32_t epoch, int m, int n0, const float acc[8], const float* pre, int M, int N,
+  __device__ __forceinline__ void apply4(uint32_t epoch, int m, int n4, const float acc[4], const float* pre, int M, int N,
                                          int, int) const {
-    act_epilogue_row<8, true>(e, epoch, m, n0, acc, M, N, pre);
+    act_epilogue_quad<true>(e, epoch, m, n4, acc, M, N, pre);
   }
 };
 struct UmmaUpdEpi {
@@ -925,16 +940,16 @@ struct UmmaUpdEpi {
   __device__ __forceinline__ void apply(uint32_t, int m, int n0, const float acc[32], int M, int N, int augM, int augN) const {
     upd_epilogue_row<32>(e, m, n0, acc, M, N, augM, augN);
   }
-  __device__ __forceinline__ bool preload8(int m, int n0, float pre[8], int M, int N) const {   // master weights
-    if (e.raw.ptr != nullptr || !upd_vec_ok<8>(e, m, n0, M, N)) return false;
-    dbn_mat Wm;
-    Wm.ptr = e.W; Wm.ld = e.ldw; Wm.dtype = DBN_F32;
-    row_load<8>(Wm, m, n0, pre);
+  __device__ __forceinline__ bool preload4(int m, int n4, float pre[4], int M, int N) const {   // master weights
+    if (e.raw.ptr != nullptr || m >= M || n4 + 4 > N || (e.ldw & 3) != 0 || (reinterpret_cast<uintptr_t>(e.W) & 15) != 0)
+      return false;
+    const float4 t = *reinterpret_cast<const float4*>(e.W + (size_t)m * (size_t)e.ldw + (size_t)n4);
+    pre[0] = t.x; pre[1] = t.y; pre[2] = t.z; pre[3] = t.w;
     return true;
   }
-  __device__ __forceinline__ void apply8(uint32_t, int m, int n0, const float acc[8], const float* pre, int M, int N,
+  __device__ __forceinline__ void apply4(uint32_t, int m, int n4, const float acc[4], const float* pre, int M, int N,
                                          int augM, int augN) const {
-    upd_epilogue_row<8>(e, m, n0, acc, M, N, augM, augN, pre);
+    upd_epilogue_quad(e, m, n4, acc, M, N, augM, augN, pre);
   }
 };
 
@@ -1060,7 +1075,7 @@ template <int BN, class Epi>
 inline void sk_launch_config(cudaLaunchConfig_t& cfg, cudaLaunchAttribute attr[2], int grid, int S, cudaStream_t st) {
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(UG_THREADS);
+  cfg.blockDim = dim3(SK_THREADS);
   cfg.dynamicSmemBytes = SkCfg<BN>::SMEM;
   cfg.stream = st;
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -1110,17 +1125,19 @@ inline int umma_launch_sk(cudaStream_t st, UmmaGemmParams& p, const Epi& epi, in
   return DBN_OK;
 }
 
-// Cycle model of one batch-256 launch, fitted to the phase traces in profiles/r01_notes.md (B200, ~1.9 GHz):
-//   whole-K kernel : 216 + bytes/105 cycles per 64-wide k-slab (TMA feed of one SM) + ~3500 per 64 columns of epilogue
-//   split-K kernel : ~900 (BN=64) / 1100 (BN=128) per 2-slab stage, 530 + outgoing partial bytes / 12.8 for the
-//                    DSMEM exchange, ~2000 per 8-column segment a thread finalises
-inline long umma_slab_cycles(int bn) { return 216 + (long)(UG_BM + bn) * 128 / 105; }
-inline long umma_epi_cycles(int bn) { return 3500L * std::max(1, bn / 64); }
-inline long sk_cycles(int bn, int S, int per) {
-  const long stage = bn == 64 ? 900 : 1100;
+// Cycle model of one batch-256 launch after its prologue, fitted to the phase traces in profiles/r01_notes.md
+// (B200, cycles at ~1.9 GHz; "act" = activation epilogue, "upd" = update epilogue):
+//   whole-K kernel : 1000 + 600 per 64-wide k-slab (BN = 64; the TMA feed of ONE SM sustains ~30 B/clk on these
+//                    row-strided boxes) + epilogue 3500 (act) / 2300 (upd) per 64 columns
+//   split-K kernel : 1350 + 990 per 2-slab stage (BN = 64), exchange 700 + outgoing partial bytes / 16 (DSMEM),
+//                    epilogue 400 + 1270 per quad a thread finalises (act) / 430 + 500 (upd)
+inline long umma_whole_k_cycles(int bn, long slabs, bool upd) {
+  return 1000 + slabs * 600 * (UG_BM + bn) / 192 + (upd ? 2300L : 3500L) * std::max(1, bn / 64);
+}
+inline long sk_cycles(int bn, int S, int per, bool upd) {
   const long out_bytes = (long)(S - 1) * (UG_BM / S) * (bn * 4 + 16);
-  const long units = std::max(1, (UG_BM / S) * (bn / 8) / (32 * UG_EPI_WARPS));
-  return per * stage + 530 + out_bytes * 10 / 128 + 2000 * units;
+  const long quads = std::max(1, (UG_BM / S) * (bn / 4) / (32 * SK_EPI_WARPS));
+  return 1350 + (long)per * 990 * (UG_BM + bn) / 192 + 700 + out_bytes / 16 + (upd ? 430 + 500 * quads : 400 + 1270 * quads);
 }
 
 constexpr int UG2_KS = 2;   // CTA-pair kernel: 2 slabs (K = 128) per stage, 64 KB per CTA, 3 stages
@@ -1191,7 +1208,7 @@ inline int umma_gemm_run(cudaStream_t st, int M, int N, int augM, int augN, cons
       fs_all += ceil_div(ceil_div(ops[i].K, UG_BK), SK_KS);
     }
     const long tiles_ns = (long)tm * ceil_div(p.N, bn);
-    long best_cost = ((tiles_ns + sms - 1) / sms) * (total_slabs * umma_slab_cycles(bn) + umma_epi_cycles(bn));
+    long best_cost = ((tiles_ns + sms - 1) / sms) * umma_whole_k_cycles(bn, total_slabs, Epi::kIsUpdate);
     best_cost -= best_cost / 10;   // the split has to win by 10 %
     for (int cand : {64, 128}) {
       for (int S : {4, 2}) {
@@ -1200,7 +1217,7 @@ inline int umma_gemm_run(cudaStream_t st, int M, int N, int augM, int augN, cons
         const long tiles = (long)tm * ceil_div(p.N, cand);
         const int room = cand == 64 ? sk_max_clusters<64, Epi>(S) : sk_max_clusters<128, Epi>(S);
         if (tiles > room) continue;
-        const long cost = sk_cycles(cand, S, per);
+        const long cost = sk_cycles(cand, S, per, Epi::kIsUpdate);
         if (cost < best_cost) { best_cost = cost; sk_bn = cand; sk_S = S; sk_per = per; }
       }
     }
