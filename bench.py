@@ -308,7 +308,7 @@ def main():
         scaling = "weak"
 
         # dominant kernel alone: the v->h contraction + Bernoulli sampling of layer 1 (256 x 500, K = 784), the
-        # largest share of the step in the ncu launch list (profiles/r01_c2_launches.txt)
+        # largest share of the step in the ncu launch list (profiles/r01_c2_splitk_launches.txt)
         l1 = layers[0]
         ws = l1.make_workspace(C2_BS)
         a = l1._step_args(runners[0].Xp, 1, 0.0, ws, 1, None)
@@ -328,12 +328,14 @@ def main():
         torch.cuda.synchronize()
         dom_ms = e0.elapsed_time(e1) / reps
         dom_flops = 2.0 * C2_BS * l1.H * l1.V
-        roof = {"bound": "tensor", "kernel": "umma_gemm_kernel<64, act> v->h + sample of layer 1 (256x500, K=784)",
+        roof = {"bound": "tensor", "kernel": "umma_gemm_sk_kernel<64, act> (split-K, clusters of 4, 64 CTAs): v->h + sample "
+                                             "of layer 1 (256x500, K=784)",
                 "achieved": dom_flops / (dom_ms * 1e-3) / 1e12, "peak": pk["bf16_burst"], "unit": "TFLOP/s",
                 "peak_source": pk["source"] + " bf16 burst",
-                "traffic": 1.4e6, "traffic_source": "ncu dram__bytes_read+write per launch, profiles/r01_c2_umma_full.txt",
-                "note": "launch/latency-bound at batch 256: 0.2 GFLOP per launch, 16 CTAs; see step_roofline and "
-                        "profiles/r01_notes.md for the phase breakdown"}
+                "traffic": 1.3e6, "traffic_source": "ncu dram__bytes_read+write per launch, profiles/r01_c2_splitk_full.txt "
+                                                    "(algorithmic: 1.2 MB of operands; the outputs stay in L2)",
+                "note": "latency-bound at batch 256: 0.2 GFLOP per launch and a chain of four dependent launches per "
+                        "mini-batch; see step_roofline and profiles/r01_notes.md for the phase breakdown"}
 
         # ---------------- e2e through the estimator API, host buffers ----------------
         def e2e_step():
