@@ -356,3 +356,108 @@ def test_epilogues_never_write_outside_the_logical_output(precision, M, N, K):
     Aq, Bq = At[:, :M].float().cpu().numpy().astype(np.float64), Bt[:, :N].float().cpu().numpy().astype(np.float64)
     ref = 0.5 * (Aq.T @ Bq)
     assert np.max(np.abs(Wn[:M, :N] - ref)) < 1e-3 * max(1.0, np.abs(ref).max())
+
+
+# ---------------------------------------------------------------------------------------------------
+# split-K cluster kernel (the batch-256 launches of configs 2 and 3)
+# ---------------------------------------------------------------------------------------------------
+def _traced(fn):
+    """Run fn() with the kernel phase trace on; returns (#CTAs that traced, True if the split-K kernel ran)."""
+    import ctypes as C
+    import torch
+    buf = torch.zeros(148 * 16, dtype=torch.int64, device="cuda")
+    G.lib().dbn_debug_set_trace(C.c_void_p(buf.data_ptr()))
+    try:
+        fn()
+        torch.cuda.synchronize()
+    finally:
+        G.lib().dbn_debug_set_trace(None)
+    t = buf.cpu().numpy().reshape(148, 16)
+    return int((t[:, 7] != 0).sum()), bool((t[:, 10] != 0).any())
+
+
+@pytest.mark.parametrize("M,N,K,tB,want_ctas", [
+    (256, 500, 784, 0, 64),      # v->h of config-2 layer 1: 16 tiles x 4
+    (256, 784, 500, 1, 104),     # h->v (MN-major weights): 26 tiles x 4
+    (256, 500, 2000, 1, 64),     # h->v of layer 3: 4 stages per CTA through a 3-deep ring
+    (256, 2000, 2000, 0, None),  # 128-wide tiles or 64-wide pairs, whichever the plan picks
+    (200, 450, 700, 0, None),    # ragged rows, columns and K tail
+])
+def test_split_k_activation_kernel_matches_numpy(M, N, K, tB, want_ctas):
+    import ctypes as C
+    import torch
+    from dbn_b200 import _lib as L, engine as E
+    rng = np.random.default_rng(M + 3 * N + 7 * K)
+    A = rng.standard_normal((M, K)).astype(np.float32)
+    Bm = (rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
+    bias = rng.standard_normal(N).astype(np.float32)
+
+    def put(X):
+        r, c = X.shape
+        t = torch.zeros(r, E.bf16_pitch(c), dtype=torch.bfloat16, device="cuda")
+        t[:, :c] = torch.as_tensor(np.ascontiguousarray(X)).cuda().to(torch.bfloat16)
+        return t
+
+    Ad, Bd = put(A), put(Bm.T if tB else Bm)
+    Aq = Ad[:, :K].float().cpu().numpy().astype(np.float64)
+    Bq = Bd[:, :(N if tB else K)].float().cpu().numpy().astype(np.float64)
+    Bq = Bq.T if tB else Bq
+    ref = 1.0 / (1.0 + np.exp(-(Aq @ Bq.T + bias[None, :])))
+    U = G.philox_uniforms(21, 3, 5, 1000, M, N)
+    out = torch.full((M + 2, N + 3), -7.0, device="cuda")
+    smp = torch.full((M + 2, E.bf16_pitch(N)), -7.0, dtype=torch.bfloat16, device="cuda")
+    bd = torch.as_tensor(bias).cuda()
+    ops = L.Operands()
+    ops.A, ops.B, ops.transB, ops.K = E.mat(Ad), E.mat(Bd), tB, K
+    epi = L.ActEpilogue()
+    epi.bias, epi.act = bd.data_ptr(), L.ACT_SIGMOID
+    epi.rng.mode, epi.rng.keep_p, epi.rng.seed, epi.rng.stream, epi.rng.epoch, epi.rng.row0 = L.RNG_SAMPLE, 1.0, 21, 3, 5, 1000
+    epi.out, epi.sample = E.mat(out), E.mat(smp)
+    ctas, split = _traced(lambda: L.check(G.lib().dbn_gemm_act(E.stream_ptr(), L.PREC_BF16, M, N, C.byref(ops), 1, C.byref(epi))))
+    assert split, "the plan did not pick the split-K kernel for a batch-256 shape (%d CTAs)" % ctas
+    if want_ctas is not None:
+        assert ctas == want_ctas
+    o = out.cpu().numpy()
+    assert np.all(o[M:, :] == -7.0) and np.all(o[:, N:] == -7.0)
+    assert np.max(np.abs(o[:M, :N] - ref)) < 2e-5          # same bf16 operands, fp32 accumulation: only the sum order differs
+    s = smp.float().cpu().numpy()
+    assert np.all(s[M:, :] == -7.0) and np.all(s[:M, N:] == -7.0)
+    assert G.count_flips(s[:M, :N], (U < ref).astype(np.float64), U, ref, band=1e-4) == 0
+
+
+@pytest.mark.parametrize("M,N,K", [(500, 784, 256), (500, 500, 256), (500, 2000, 1024), (130, 300, 512)])
+def test_split_k_update_kernel_matches_numpy(M, N, K):
+    """dW = A0^T B0 - A1^T B1 with the ones row/column (two passes, MN-major operands): split over the passes."""
+    import ctypes as C
+    import torch
+    from dbn_b200 import _lib as L, engine as E
+    rng = np.random.default_rng(M + N + K)
+
+    def operand(cols):
+        t = torch.zeros(K, E.bf16_pitch(cols + 1), dtype=torch.bfloat16, device="cuda")
+        t[:, :cols] = torch.as_tensor(rng.random((K, cols)).astype(np.float32)).cuda().to(torch.bfloat16)
+        t[:, cols] = 1.0
+        return t
+
+    A0, B0, A1, B1 = operand(M), operand(N), operand(M), operand(N)
+    W0 = rng.standard_normal((M, N)).astype(np.float32)
+    Wd = torch.as_tensor(W0).cuda()
+    Wsh = torch.zeros(M, E.bf16_pitch(N), dtype=torch.bfloat16, device="cuda")
+    vM0, vN0 = rng.standard_normal(M).astype(np.float32), rng.standard_normal(N).astype(np.float32)
+    vM, vN = torch.as_tensor(vM0).cuda(), torch.as_tensor(vN0).cuda()
+    ops = (L.Operands * 2)()
+    for o, (a, b) in zip(ops, ((A0, B0), (A1, B1))):
+        o.A, o.B, o.transA, o.transB, o.K = E.mat(a), E.mat(b), 1, 1, K
+    u = L.UpdateEpilogue()
+    u.W, u.ldw, u.Wb = Wd.data_ptr(), Wd.stride(0), E.mat(Wsh)
+    u.vecM, u.vecN, u.decay, u.scale = vM.data_ptr(), vN.data_ptr(), 0.99, 0.01
+    ctas, split = _traced(lambda: L.check(G.lib().dbn_gemm_update(E.stream_ptr(), L.PREC_BF16, M, N, 1, 1, ops, 2, C.byref(u))))
+    f = lambda t, c: t[:, :c].float().cpu().numpy().astype(np.float64)
+    D = f(A0, M + 1).T @ f(B0, N + 1) - f(A1, M + 1).T @ f(B1, N + 1)
+    Wref = 0.99 * W0 + 0.01 * D[:M, :N]
+    Wn = Wd.cpu().numpy()
+    assert np.max(np.abs(Wn - Wref)) < 1e-4 * max(1.0, np.abs(Wref).max())
+    assert np.max(np.abs(Wsh[:, :N].float().cpu().numpy() - Wn)) <= np.abs(Wn).max() * 2 ** -8
+    assert np.max(np.abs(vM.cpu().numpy() - (vM0 + 0.01 * D[:M, N]))) < 1e-4 * max(1.0, np.abs(D[:M, N]).max())
+    assert np.max(np.abs(vN.cpu().numpy() - (vN0 + 0.01 * D[M, :N]))) < 1e-4 * max(1.0, np.abs(D[M, :N]).max())
+    assert ctas > 0
