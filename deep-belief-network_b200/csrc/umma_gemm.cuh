@@ -15,12 +15,17 @@
 // carries (4 KB or 32 KB; >100 B/clk per SM for 32 KB boxes), so the mainloop is paced by the NUMBER
 // of copies -- two per stage here, i.e. two per KS*64 of K.
 //
-// Kernel shape: persistent, one CTA per SM, 11 warps:
-//   warp 0    TMA producer (one elected lane)         -- ring of S smem stages, mbarrier full/empty
-//   warp 1    TMEM allocator + tcgen05.mma issuer      -- one elected lane issues 4 MMAs (K=16) per stage
-//   warps 2-5 epilogue (one TMEM lane quarter each)    -- double-buffered accumulator (2 x BN columns)
-// Tile 128 x BN x 64 (BN in {64,128,256}); ragged edges are zero-filled by TMA and masked in the
-// epilogue, so no operand is ever padded to a tile multiple.
+// Three kernels share the mainloop, the descriptors and the epilogues:
+//   umma_gemm_kernel     whole K per CTA, persistent over 128 x BN tiles (BN in {64,128,256}), 11 warps:
+//                          warp 0     TMA producer A (one elected lane)   -- ring of fat smem stages, mbarrier full/empty
+//                          warp 1     TMEM allocator + tcgen05.mma issuer -- one elected lane, 4 MMAs (K=16) per k-slab
+//                          warps 2-9  epilogue (two per TMEM lane quarter) -- double-buffered accumulator (2 x BN columns)
+//                          warp 10    TMA producer B
+//   umma_gemm2_kernel    cta_group::2: a CTA pair per 256 x 256 tile (the 4096-wide layers of config 5)
+//   umma_gemm_sk_kernel  split K over a cluster of 2/4 CTAs per tile + DSMEM reduce-scatter (the batch-256 launches
+//                        of configs 2 and 3, where the output is a handful of tiles and latency is everything)
+// Ragged edges are zero-filled by TMA and masked in the epilogue, so no operand is ever padded to a tile
+// multiple.  umma_gemm_run() picks kernel, tile width and split per launch from measured cycle models.
 #pragma once
 #include <cuda.h>
 #include <cooperative_groups.h>
