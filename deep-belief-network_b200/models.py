@@ -25,6 +25,7 @@ from scipy.stats import truncnorm
 from sklearn.base import BaseEstimator, ClassifierMixin, RegressorMixin, TransformerMixin
 
 from . import engine as E
+from ._hostrng import legacy_randn
 from .activations import ReLUActivationFunction, SigmoidActivationFunction
 
 
@@ -129,10 +130,10 @@ class BinaryRBM(BaseEstimator, TransformerMixin, BaseModel):
     # ---- parameter initialisation: same draws, same order as dbn/models.py:55-69 ----
     def _draw_params(self, n_visible):
         h, s = self.n_hidden_units, np.sqrt(n_visible)
-        if self.activation_function == 'sigmoid':
-            W = np.random.randn(h, n_visible) / s
-            c = np.random.randn(h) / s
-            b = np.random.randn(n_visible) / s
+        if self.activation_function == 'sigmoid':   # legacy_randn == np.random.randn, bit for bit (see _hostrng.py)
+            W = legacy_randn(h, n_visible) / s
+            c = legacy_randn(h) / s
+            b = legacy_randn(n_visible) / s
             return W, c, b, SigmoidActivationFunction
         if self.activation_function == 'relu':
             W = truncnorm.rvs(-0.2, 0.2, size=[h, n_visible]) / s

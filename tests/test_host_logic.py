@@ -162,3 +162,33 @@ def test_draw_ahead_reports_errors_at_the_failing_draw_and_stops():
     d.get()
     d.close()          # must not hang although the generator never ends
     assert not d._t.is_alive()
+
+
+def test_legacy_randn_is_np_random_randn_bit_for_bit():
+    """libdbn_hostrng.so restates NumPy's legacy Gaussian (MT19937 + polar method): same values, same state of the
+    GLOBAL generator afterwards, whatever the length parity, cached Gaussian or block position."""
+    from dbn_b200 import _hostrng as R
+    assert R.available(), "libdbn_hostrng.so missing or failed its self-check (python __graft_entry__.py build)"
+    for seed in (0, 7, 2024):
+        np.random.seed(seed)
+        ref = [np.random.randn(*s) for s in [(5000,), (3,), (129, 65), (4097,), (500, 784), (1,), (2000, 5)]]
+        tail_ref = (np.random.random_sample(), np.random.permutation(17), np.random.randn(3))
+        np.random.seed(seed)
+        got = [R.legacy_randn(*s) for s in [(5000,), (3,), (129, 65), (4097,), (500, 784), (1,), (2000, 5)]]
+        tail_got = (np.random.random_sample(), np.random.permutation(17), np.random.randn(3))
+        for a, b in zip(ref, got):
+            assert a.shape == b.shape and np.array_equal(a.view(np.uint64), b.view(np.uint64))
+        assert tail_ref[0] == tail_got[0] and np.array_equal(tail_ref[1], tail_got[1]) and np.array_equal(tail_ref[2], tail_got[2])
+
+
+def test_rbm_parameter_init_is_the_reference_stream():
+    """BinaryRBM._draw_params consumes np.random exactly like dbn/models.py:55-69 (W, then c, then b)."""
+    np.random.seed(11)
+    h, v = 96, 200                     # large enough for the fast path (>= 4096 draws)
+    W = np.random.randn(h, v) / np.sqrt(v)
+    c = np.random.randn(h) / np.sqrt(v)
+    b = np.random.randn(v) / np.sqrt(v)
+    np.random.seed(11)
+    m = BinaryRBM(n_hidden_units=h)
+    m._init_params(v)
+    assert np.array_equal(m.W, W) and np.array_equal(m.c, c) and np.array_equal(m.b, b)
