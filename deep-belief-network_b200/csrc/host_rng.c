@@ -18,6 +18,8 @@
  * -ffast-math and with -ffp-contract=off), and the generator state handed back is exactly the state NumPy would have.
  * tests/test_host_logic.py checks both against np.random for sizes and states of every parity.
  */
+#include "dbn_hostrng.h"
+
 #include <math.h>
 #include <pthread.h>
 #include <stdint.h>
