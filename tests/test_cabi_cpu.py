@@ -31,6 +31,16 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(L.SYMBOLS.keys())
 
 
+def test_host_helper_library_exports_its_header():
+    """include/dbn_hostrng.h <-> libdbn_hostrng.so (host-side C helper, no CUDA)."""
+    src = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "dbn_hostrng.h")).read(), flags=re.S)
+    declared = set(re.findall(r"\b(dbn_[a-z0-9_]+)\s*\(", src))
+    assert declared == {"dbn_host_legacy_randn"}
+    lib = C.CDLL(os.path.join(ROOT, "deep-belief-network_b200", "libdbn_hostrng.so"))
+    for name in declared:
+        assert hasattr(lib, name)
+
+
 def test_struct_layouts_match():
     lib = G.lib()
     for i, st in enumerate((L.Mat, L.Rng, L.Operands, L.ActEpilogue, L.UpdateEpilogue, L.RbmStepArgs, L.MlpStepArgs)):
