@@ -22,7 +22,11 @@ RNG_NONE, RNG_SAMPLE, RNG_MASK = 0, 1, 2
 HEAD_SOFTMAX, HEAD_LINEAR = 0, 1
 STEP_SKIP_UPDATE = 1
 STEP_SKIP_FIRST_HIDDEN = 2
+STEP_BIAS_STATS = 4
 MAX_LAYERS = 16
+MAX_PEERS = 8
+PEER_HANDLE_BYTES = 64
+ABI_VERSION = 2
 
 
 class Mat(C.Structure):
@@ -40,14 +44,26 @@ class Operands(C.Structure):
                 ("row0_A", C.c_int32), ("row0_B", C.c_int32), ("_pad", C.c_int32)]
 
 
+class ColSum(C.Structure):
+    _fields_ = [("acc", C.c_void_p), ("sign", C.c_float), ("ref_row0", C.c_int32), ("ref", Mat)]
+
+
 class ActEpilogue(C.Structure):
     _fields_ = [("bias", C.c_void_p), ("act", C.c_int32), ("mul", C.c_int32), ("aux", Mat), ("rng", Rng),
-                ("out", Mat), ("out2", Mat), ("sample", Mat)]
+                ("out", Mat), ("out2", Mat), ("sample", Mat), ("colsum", ColSum)]
 
 
 class UpdateEpilogue(C.Structure):
     _fields_ = [("W", C.c_void_p), ("ldw", C.c_int32), ("_pad", C.c_int32), ("Wb", Mat), ("vecM", C.c_void_p),
-                ("vecN", C.c_void_p), ("decay", C.c_float), ("scale", C.c_float), ("raw", Mat)]
+                ("vecN", C.c_void_p), ("decay", C.c_float), ("scale", C.c_float), ("raw", Mat),
+                ("statM", C.c_void_p), ("statN", C.c_void_p), ("raw_peers", C.c_void_p * MAX_PEERS),
+                ("rows_per_peer", C.c_int32), ("raw_slot", C.c_int32)]
+
+
+class DpExchange(C.Structure):
+    _fields_ = [("n_peers", C.c_int32), ("rank", C.c_int32), ("V", C.c_int32), ("H", C.c_int32),
+                ("rows_per_peer", C.c_int32), ("ld_recv", C.c_int32), ("recv", C.c_void_p * MAX_PEERS),
+                ("stats", C.c_void_p * MAX_PEERS), ("flags", C.c_void_p * MAX_PEERS), ("Wb", Mat * MAX_PEERS)]
 
 
 class RbmStepArgs(C.Structure):
@@ -104,6 +120,18 @@ SYMBOLS = {
     "dbn_rbm_delta_rows": (C.c_int, [C.c_void_p, _P(RbmStepArgs), C.c_int, C.c_int]),
     "dbn_rbm_apply_delta": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p,
                                       C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, _P(Mat)]),
+    "dbn_rbm_workspace_stats": (C.c_void_p, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "dbn_peer_alloc": (C.c_int, [C.c_size_t, _P(C.c_void_p), C.c_void_p]),
+    "dbn_peer_free": (C.c_int, [C.c_void_p]),
+    "dbn_peer_open": (C.c_int, [C.c_void_p, _P(C.c_void_p)]),
+    "dbn_peer_close": (C.c_int, [C.c_void_p]),
+    "dbn_rbm_delta_scatter": (C.c_int, [C.c_void_p, _P(RbmStepArgs), _P(DpExchange)]),
+    "dbn_dp_signal": (C.c_int, [C.c_void_p, _P(DpExchange), C.c_void_p, C.c_uint64]),
+    "dbn_dp_apply": (C.c_int, [C.c_void_p, _P(DpExchange), C.c_float, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                               C.c_void_p, C.c_void_p, C.c_uint64]),
+    "dbn_dp_wait": (C.c_int, [C.c_void_p, _P(DpExchange), C.c_int, C.c_uint64]),
+    "dbn_gather_rows_peer": (C.c_int, [C.c_void_p, _P(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                       _P(Mat)]),
     "dbn_mlp_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, _P(C.c_int32), C.c_int, C.c_int]),
     "dbn_mlp_workspace_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, _P(C.c_int32), C.c_int, C.c_int,
                                          C.c_void_p]),
@@ -138,9 +166,9 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the .so is stale
         fn.restype = res
         fn.argtypes = args
-    if lib.dbn_abi_version() != 1:
+    if lib.dbn_abi_version() != ABI_VERSION:
         raise DbnB200Error("libdbn_b200.so ABI version mismatch; rebuild")
-    for i, st in enumerate((Mat, Rng, Operands, ActEpilogue, UpdateEpilogue, RbmStepArgs, MlpStepArgs)):
+    for i, st in enumerate((Mat, Rng, Operands, ActEpilogue, UpdateEpilogue, RbmStepArgs, MlpStepArgs, ColSum, DpExchange)):
         if lib.dbn_struct_size(i) != C.sizeof(st):
             raise DbnB200Error("struct layout mismatch for %s: C %d vs ctypes %d"
                                % (st.__name__, lib.dbn_struct_size(i), C.sizeof(st)))

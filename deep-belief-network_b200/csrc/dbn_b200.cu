@@ -7,6 +7,7 @@
 #include "umma_gemm.cuh"
 #include "misc_kernels.cuh"
 #include "rbm_persistent.cuh"
+#include "dp_kernels.cuh"
 
 using namespace dbn;
 
@@ -70,6 +71,7 @@ inline int bf16_pitch(int cols) { return (int)align_up((size_t)cols + 1, 64); }
 
 struct RbmWorkspace {
   dbn_mat P0, Hs, Vt, Pk;
+  unsigned long long* stats;   // [H + V] fixed-point bias statistics dc | db (dbn_colsum)
 };
 size_t rbm_ws_layout(int precision, int Bmax, int V, int H, char* base, RbmWorkspace* ws) {
   const int dt = precision == DBN_PREC_BF16 ? DBN_BF16 : DBN_F32;
@@ -83,8 +85,20 @@ size_t rbm_ws_layout(int precision, int Bmax, int V, int H, char* base, RbmWorks
   };
   RbmWorkspace w;
   w.P0 = carve(ldH); w.Hs = carve(ldH); w.Vt = carve(ldV); w.Pk = carve(ldH);
+  w.stats = reinterpret_cast<unsigned long long*>(base ? base + off : nullptr);
+  off = align_up(off + (size_t)(H + V) * sizeof(unsigned long long), 1024);
   if (ws) *ws = w;
   return off;
+}
+
+// Bias statistics by column sums in the Gibbs-chain epilogues instead of the ones row / column of dW: on request,
+// or -- for an in-place update -- when the extra row / column would cost the dW contraction a whole tile row /
+// column (H or V a multiple of 64: 4096 -> 17 x 17 instead of 16 x 16 CTA-pair tiles, +12.9 % MMA work).
+inline bool rbm_use_stats(const dbn_rbm_step_args* a) {
+  if (a->precision != DBN_PREC_BF16) return false;
+  if (a->flags & DBN_STEP_BIAS_STATS) return true;
+  if (a->flags & DBN_STEP_SKIP_UPDATE) return false;   // deltas come later from dbn_rbm_delta_rows (ones row / column)
+  return (a->H % 64) == 0 || (a->V % 64) == 0;
 }
 
 struct MlpWorkspace {
@@ -156,6 +170,8 @@ size_t dbn_struct_size(int which) {
     case 4: return sizeof(dbn_update_epilogue);
     case 5: return sizeof(dbn_rbm_step_args);
     case 6: return sizeof(dbn_mlp_step_args);
+    case 7: return sizeof(dbn_colsum);
+    case 8: return sizeof(dbn_dp_exchange);
     default: return 0;
   }
 }
@@ -249,6 +265,10 @@ static int rbm_first_hidden_impl(void* stream, const dbn_rbm_step_args* a, int h
   e.out = offset_cols(ws.P0, h0);
   e.out2 = offset_cols(a->P0, h0);
   e.sample = offset_cols(ws.Hs, h0);
+  if (rbm_use_stats(a)) {   // dc += sum_rows h_0 (dbn/models.py:144)
+    e.colsum.acc = ws.stats + h0;
+    e.colsum.sign = 1.0f;
+  }
   return dbn_gemm_act(stream, a->precision, a->B, h1 - h0, &o, 1, &e);
 }
 
@@ -274,6 +294,7 @@ int dbn_rbm_cd_step(void* stream, const dbn_rbm_step_args* a) {
   rbm_ws_layout(a->precision, rbm_ws_rows(a), a->V, a->H, static_cast<char*>(a->workspace), &ws);
   const dbn_mat Wop = tc ? a->Wb : make_mat(a->W, a->ldw, DBN_F32);
   const int B = a->B, V = a->V, H = a->H;
+  const bool stats = rbm_use_stats(a);
 
   for (int t = 0; t < a->k; ++t) {
     // h_t ~ P(h | v_t): dbn/models.py:135 -> :148-155
@@ -296,13 +317,25 @@ int dbn_rbm_cd_step(void* stream, const dbn_rbm_step_args* a) {
     dbn_operands o2 = make_ops(ws.Hs, 0, 0, Wop, 1, 0, H);
     dbn_act_epilogue e2 = blank_act();
     e2.bias = a->b; e2.act = a->act; e2.out = ws.Vt;
-    if (t == a->k - 1) e2.out2 = a->Vk;
+    if (t == a->k - 1) {
+      e2.out2 = a->Vk;
+      if (stats) {   // db = sum_rows (v_0 - v_k) (dbn/models.py:143): v_0 re-read from the (L2-hot) mini-batch
+        e2.colsum.acc = ws.stats + H;
+        e2.colsum.sign = 1.0f;
+        e2.colsum.ref = a->X;
+        e2.colsum.ref_row0 = a->row0;
+      }
+    }
     DBN_TRY(dbn_gemm_act(stream, a->precision, B, V, &o2, 1, &e2));
   }
   {  // h_k = P(h | v_k): dbn/models.py:141
     dbn_operands o = make_ops(ws.Vt, 0, 0, Wop, 0, 0, V);
     dbn_act_epilogue e = blank_act();
     e.bias = a->c; e.act = a->act; e.out = ws.Pk; e.out2 = a->Pk;
+    if (stats) {   // dc -= sum_rows h_k
+      e.colsum.acc = ws.stats;
+      e.colsum.sign = -1.0f;
+    }
     DBN_TRY(dbn_gemm_act(stream, a->precision, B, H, &o, 1, &e));
   }
   if (a->flags & DBN_STEP_SKIP_UPDATE) return DBN_OK;
@@ -313,7 +346,18 @@ int dbn_rbm_cd_step(void* stream, const dbn_rbm_step_args* a) {
     dbn_update_epilogue u = blank_upd();
     u.W = a->W; u.ldw = a->ldw; u.Wb = tc ? a->Wb : null_mat();
     u.vecM = a->c; u.vecN = a->b; u.decay = 1.0f; u.scale = a->lr_over_bs; u.raw = a->raw_delta;
-    DBN_TRY(dbn_gemm_update(stream, a->precision, H, V, 1, 1, o, 2, &u));
+    if (!stats) {
+      DBN_TRY(dbn_gemm_update(stream, a->precision, H, V, 1, 1, o, 2, &u));
+    } else {
+      // the statistics were taken in the chain's epilogues: H x V accumulator, no ones row / column; the update
+      // epilogue's owner threads fold them into b and c (and clear them)
+      u.statM = ws.stats; u.statN = ws.stats + H;
+      DBN_TRY(dbn_gemm_update(stream, a->precision, H, V, 0, 0, o, 2, &u));
+      if (a->raw_delta.ptr) {
+        stats_to_raw_kernel<<<ceil_div(H + V, 256), 256, 0, as_stream(stream)>>>(ws.stats, H, V, a->raw_delta);
+        DBN_LAUNCH_CHECK();
+      }
+    }
   }
   return DBN_OK;
 }
@@ -387,6 +431,125 @@ int dbn_rbm_apply_delta(void* stream, int V, int H, int h0, int h1, int with_db,
   const int blocks = (int)std::min<long>((total + 255) / 256, 148L * 8);
   apply_delta_kernel<<<blocks, 256, 0, as_stream(stream)>>>(V, H, h0, h1 - h0, with_db, scale, raw, ld, raw_row0, W, ldw, b,
                                                            c, Wb ? *Wb : null_mat());
+  DBN_LAUNCH_CHECK();
+  return DBN_OK;
+}
+
+unsigned long long* dbn_rbm_workspace_stats(int precision, int Bmax, int V, int H, void* workspace) {
+  RbmWorkspace ws;
+  rbm_ws_layout(precision, Bmax, V, H, static_cast<char*>(workspace), &ws);
+  return ws.stats;
+}
+
+// ---- data-parallel exchange over peer memory ---------------------------------------------------------
+int dbn_peer_alloc(size_t bytes, void** ptr_out, void* handle_out) {
+  DBN_NEED_DEVICE();
+  DBN_REQUIRE(bytes > 0 && ptr_out && handle_out, "bad argument");
+  void* p = nullptr;
+  DBN_CUDA_OK(cudaMalloc(&p, bytes));
+  DBN_CUDA_OK(cudaMemset(p, 0, bytes));
+  DBN_CUDA_OK(cudaDeviceSynchronize());
+  cudaIpcMemHandle_t h;
+  static_assert(sizeof(h) == DBN_PEER_HANDLE_BYTES, "handle size");
+  cudaError_t e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {   // single-process use (one rank, emulation) works without a handle
+    (void)cudaGetLastError();
+    memset(&h, 0, sizeof(h));
+  }
+  memcpy(handle_out, &h, sizeof(h));
+  *ptr_out = p;
+  return DBN_OK;
+}
+int dbn_peer_free(void* ptr) {
+  if (ptr) DBN_CUDA_OK(cudaFree(ptr));
+  return DBN_OK;
+}
+int dbn_peer_open(const void* handle, void** ptr_out) {
+  DBN_NEED_DEVICE();
+  DBN_REQUIRE(handle && ptr_out, "bad argument");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  DBN_CUDA_OK(cudaIpcOpenMemHandle(ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+  return DBN_OK;
+}
+int dbn_peer_close(void* ptr) {
+  if (ptr) DBN_CUDA_OK(cudaIpcCloseMemHandle(ptr));
+  return DBN_OK;
+}
+
+static int dp_check(const dbn_dp_exchange* x) {
+  DBN_REQUIRE(x != nullptr, "null exchange");
+  DBN_REQUIRE(x->n_peers >= 1 && x->n_peers <= DBN_MAX_PEERS && x->rank >= 0 && x->rank < x->n_peers, "bad rank / peer count");
+  DBN_REQUIRE(x->H > 0 && x->V > 0 && x->rows_per_peer * x->n_peers == x->H, "H must be n_peers * rows_per_peer");
+  DBN_REQUIRE(x->ld_recv >= x->V && (x->ld_recv % 4) == 0, "ld_recv must be a multiple of 4 and >= V");
+  for (int j = 0; j < x->n_peers; ++j)
+    DBN_REQUIRE(x->recv[j] && x->stats[j] && x->flags[j] && x->Wb[j].ptr && x->Wb[j].dtype == DBN_BF16, "null peer pointer");
+  return DBN_OK;
+}
+
+int dbn_rbm_delta_scatter(void* stream, const dbn_rbm_step_args* a, const dbn_dp_exchange* x) {
+  DBN_NEED_DEVICE();
+  DBN_REQUIRE(a != nullptr, "null args");
+  DBN_TRY(dp_check(x));
+  DBN_REQUIRE(a->precision == DBN_PREC_BF16 && x->H == a->H && x->V == a->V, "exchange does not match the layer (BF16 mode only)");
+  if (a->k == 0) return DBN_OK;
+  RbmWorkspace ws;
+  rbm_ws_layout(a->precision, rbm_ws_rows(a), a->V, a->H, static_cast<char*>(a->workspace), &ws);
+  dbn_operands o[2];
+  o[0] = make_ops(ws.P0, 1, 0, a->X, 1, a->row0, a->B);
+  o[1] = make_ops(ws.Pk, 1, 0, ws.Vt, 1, 0, a->B);
+  dbn_update_epilogue u = blank_upd();
+  for (int j = 0; j < x->n_peers; ++j) u.raw_peers[j] = x->recv[j];
+  u.rows_per_peer = x->rows_per_peer;
+  u.raw_slot = x->rank;
+  u.raw.ld = x->ld_recv; u.raw.dtype = DBN_F32;
+  return dbn_gemm_update(stream, a->precision, a->H, a->V, 0, 0, o, 2, &u);
+}
+
+int dbn_dp_signal(void* stream, const dbn_dp_exchange* x, unsigned long long* local_stats, unsigned long long value) {
+  DBN_NEED_DEVICE();
+  DBN_TRY(dp_check(x));
+  DBN_REQUIRE(local_stats != nullptr, "null statistics");
+  dp_signal_kernel<<<x->n_peers, 512, 0, as_stream(stream)>>>(*x, local_stats, value);
+  DBN_LAUNCH_CHECK();
+  return DBN_OK;
+}
+
+int dbn_dp_apply(void* stream, const dbn_dp_exchange* x, float scale, float* W, int ldw, float* b, float* c,
+                 unsigned long long* local_stats, unsigned int* counter, unsigned long long value) {
+  DBN_NEED_DEVICE();
+  DBN_TRY(dp_check(x));
+  DBN_REQUIRE(W && b && c && local_stats && counter && ldw >= x->V, "bad argument");
+  const long total = (long)x->rows_per_peer * ((x->V + 7) / 8);
+  const int blocks = (int)std::max<long>(1, std::min<long>((total + 255) / 256, 148L * 4));
+  dp_apply_kernel<<<blocks, 256, 0, as_stream(stream)>>>(*x, scale, W, ldw, b, c, local_stats, counter, value);
+  DBN_LAUNCH_CHECK();
+  return DBN_OK;
+}
+
+int dbn_dp_wait(void* stream, const dbn_dp_exchange* x, int which, unsigned long long value) {
+  DBN_NEED_DEVICE();
+  DBN_TRY(dp_check(x));
+  DBN_REQUIRE(which == 0 || which == 1, "bad flag index");
+  dp_wait_kernel<<<1, 32, 0, as_stream(stream)>>>(*x, which, value);
+  DBN_LAUNCH_CHECK();
+  return DBN_OK;
+}
+
+int dbn_gather_rows_peer(void* stream, void* const* srcs, int n_srcs, int rows_per_src, int ld, const int32_t* idx,
+                         int n_rows, const dbn_mat* dst) {
+  DBN_NEED_DEVICE();
+  DBN_REQUIRE(srcs && idx && dst && dst->ptr && n_srcs >= 1 && n_srcs <= DBN_MAX_PEERS && rows_per_src > 0, "bad argument");
+  DBN_REQUIRE(dst->dtype == DBN_BF16 && dst->ld == ld && (ld % 8) == 0, "bf16 rows of the same pitch (multiple of 8) on both sides");
+  if (n_rows <= 0) return DBN_OK;
+  PeerSrcs ps;
+  memset(&ps, 0, sizeof(ps));
+  for (int j = 0; j < n_srcs; ++j) {
+    DBN_REQUIRE(srcs[j] != nullptr, "null source");
+    ps.p[j] = srcs[j];
+  }
+  const int blocks = std::min(ceil_div(n_rows, 8), 148 * 8);
+  gather_rows_peer_kernel<<<blocks, 256, 0, as_stream(stream)>>>(ps, rows_per_src, ld, idx, n_rows, *dst);
   DBN_LAUNCH_CHECK();
   return DBN_OK;
 }

@@ -58,6 +58,21 @@ inline std::atomic<uint64_t>& launch_counter() {
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// ---- per-device one-time state --------------------------------------------------------------------
+// Function attributes (opt-in shared memory), SM counts and occupancy answers belong to a DEVICE, not to the
+// process: a caller may fit on cuda:0 and then on cuda:1.  Caches are therefore indexed by the current device.
+constexpr int DBN_MAX_DEVICES = 64;
+inline int current_device() {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess) { (void)cudaGetLastError(); d = 0; }
+  return (d < 0 || d >= DBN_MAX_DEVICES) ? 0 : d;
+}
+// true exactly once per (mask, current device)
+inline bool first_use_on_device(std::atomic<uint64_t>& mask) {
+  const uint64_t bit = uint64_t(1) << current_device();
+  return (mask.fetch_or(bit, std::memory_order_acq_rel) & bit) == 0;
+}
+
 // ---- programmatic dependent launch (PDL) ---------------------------------------------------------
 // Every contraction kernel is launched with programmatic stream serialization: it may start (and run
 // its prologue: barrier init, TMEM allocation, tensor-map prefetch) while its predecessor in the

@@ -20,6 +20,41 @@ __device__ __forceinline__ float rcp_approx(float x) {
 }
 __device__ __forceinline__ float sigmoid_fast(float x) { return rcp_approx(1.0f + __expf(-x)); }
 
+// ---- fixed-point column statistics (dbn_colsum) ----------------------------------------------------
+// value * 2^32 as a two's-complement 64-bit integer: integer atomics commute, so the sums are deterministic
+__device__ __forceinline__ unsigned long long stat_fixed(float x) {
+  return (unsigned long long)__float2ll_rn(x * 4294967296.0f);     // exact scaling; |x| < 2^31
+}
+__device__ __forceinline__ float stat_value(unsigned long long v) {
+  return (float)((double)(long long)v * (1.0 / 4294967296.0));
+}
+__device__ __forceinline__ void stat_add(unsigned long long* acc, int n, float x) {
+  if (x != 0.0f) atomicAdd(acc + n, stat_fixed(x));
+}
+// Consume a statistic: the one thread that owns index i reads, clears and returns it.
+__device__ __forceinline__ float stat_take(unsigned long long* acc, int i) {
+  const unsigned long long v = acc[i];
+  acc[i] = 0ull;
+  return stat_value(v);
+}
+
+// Column sums of a 32 x 32 block held one ROW per lane (x[j] = element (lane, j)): a butterfly in which every
+// step halves the columns a lane still carries -- 31 shuffles in all instead of 32 five-step reductions.
+// Afterwards lane l holds the sum over the 32 rows of column l.
+__device__ __forceinline__ float colsum32(float x[32], int lane) {
+#pragma unroll
+  for (int step = 16; step >= 1; step >>= 1) {
+    const bool up = (lane & step) != 0;
+#pragma unroll
+    for (int j = 0; j < step; ++j) {
+      const float send = up ? x[j] : x[j + step];
+      const float keep = up ? x[j + step] : x[j];
+      x[j] = keep + __shfl_xor_sync(0xffffffffu, send, step);
+    }
+  }
+  return x[0];
+}
+
 template <bool kFast>
 __device__ __forceinline__ float apply_act(int act, float x) {
   if (act == DBN_ACT_SIGMOID) return kFast ? sigmoid_fast(x) : sigmoid_strict(x);
@@ -29,7 +64,7 @@ __device__ __forceinline__ float apply_act(int act, float x) {
 
 // Activation epilogue on 4 columns.  M, N = logical output extent (stores are masked to it).
 // pre_bias: bias[n4..n4+3] if the caller already holds it (split-K kernel: requested before the exchange), else nullptr
-template <bool kFast = false>
+template <bool kFast = false, bool kStats = true>
 __device__ __forceinline__ void act_epilogue_quad(const dbn_act_epilogue& e, uint32_t epoch, int m, int n4,
                                                   const float acc[4], int M, int N, const float* pre_bias = nullptr) {
   if (m >= M || n4 >= N) return;
@@ -75,6 +110,13 @@ __device__ __forceinline__ void act_epilogue_quad(const dbn_act_epilogue& e, uin
   }
   if (e.out.ptr != nullptr) mat_store4(e.out, m, n4, a, nvalid);
   if (e.out2.ptr != nullptr) mat_store4(e.out2, m, n4, a, nvalid);
+  if (kStats && e.colsum.acc != nullptr) {   // slow path of the column statistics: one atomic per element
+    float r[4] = {0.f, 0.f, 0.f, 0.f};
+    if (e.colsum.ref.ptr != nullptr) mat_load4(e.colsum.ref, e.colsum.ref_row0 + m, n4, r, nvalid);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (j < nvalid) stat_add(e.colsum.acc, n4 + j, e.colsum.sign * (e.colsum.ref.ptr != nullptr ? r[j] - a[j] : a[j]));
+  }
   if (e.rng.mode == DBN_RNG_SAMPLE && e.sample.ptr != nullptr) {
     float s[4];
 #pragma unroll
@@ -83,17 +125,46 @@ __device__ __forceinline__ void act_epilogue_quad(const dbn_act_epilogue& e, uin
   }
 }
 
+// Destination row of accumulator row m when the raw delta is scattered over peer GPUs (see dbn_update_epilogue).
+__device__ __forceinline__ float* scatter_row_ptr(const dbn_update_epilogue& e, int m) {
+  const int o = m / e.rows_per_peer;
+  void* base = e.raw_peers[0];      // select chain, not an indexed read: the table stays in registers / the constant bank
+#pragma unroll
+  for (int j = 1; j < DBN_MAX_PEERS; ++j)
+    if (o == j) base = e.raw_peers[j];
+  return reinterpret_cast<float*>(base) +
+         (size_t)(e.raw_slot * e.rows_per_peer + (m - o * e.rows_per_peer)) * (size_t)e.raw.ld;
+}
+// Bias statistics (dbn_colsum) consumed by the update: every index has exactly one owner thread in the launch.
+__device__ __forceinline__ void upd_take_stats(const dbn_update_epilogue& e, int m, int n0, int ncols, int M, int N) {
+  if (e.statM != nullptr && e.vecM != nullptr && n0 == 0 && m < M) e.vecM[m] += e.scale * stat_take(e.statM, m);
+  if (e.statN != nullptr && e.vecN != nullptr && m == 0) {
+    for (int j = 0; j < ncols; ++j)
+      if (n0 + j < N) e.vecN[n0 + j] += e.scale * stat_take(e.statN, n0 + j);
+  }
+}
+
 // Update epilogue on 4 columns of the (M+augM) x (N+augN) accumulator.
 // pre_w: W[m, n4..n4+3] if the caller already holds it (whole quad inside the core block), else nullptr
+template <bool kScatter = true>
 __device__ __forceinline__ void upd_epilogue_quad(const dbn_update_epilogue& e, int m, int n4, const float acc[4],
                                                   int M, int N, int augM, int augN, const float* pre_w = nullptr) {
   const int Mt = M + augM, Nt = N + augN;
   if (m >= Mt || n4 >= Nt) return;
   const int nvalid = min(4, Nt - n4);
+  if (kScatter && e.raw_peers[0] != nullptr) {   // scattered raw delta (no ones row / column on this path)
+    if (m < M && n4 < N) {
+      dbn_mat dst;
+      dst.ptr = scatter_row_ptr(e, m); dst.ld = e.raw.ld; dst.dtype = DBN_F32;
+      mat_store4(dst, 0, n4, acc, min(4, N - n4));
+    }
+    return;
+  }
   if (e.raw.ptr != nullptr) {
     mat_store4(e.raw, m, n4, acc, nvalid);
     return;
   }
+  upd_take_stats(e, m, n4, 4, M, N);
   if (m < M) {
     const int ncore = max(0, min(4, N - n4));
     if (ncore > 0) {
@@ -211,6 +282,12 @@ __device__ __forceinline__ void act_epilogue_row(const dbn_act_epilogue& e, uint
   static_assert(W % 8 == 0, "segments are whole 16-byte bf16 vectors");
   const bool inj = e.rng.injected.ptr != nullptr;
   const bool vec = act_vec_ok<W>(e, m, n0, M, N);
+  // column statistics: the butterfly needs the whole warp on the vector path (callers enter converged, one row
+  // per lane); a warp on a ragged edge falls back to one atomic per element
+  bool fast_stats = false;
+  if (e.colsum.acc != nullptr) {
+    if constexpr (W == 32) fast_stats = __all_sync(0xffffffffu, vec && mat_vec_ok(e.colsum.ref));
+  }
   if (!vec) {
     if (m >= M) return;
 #pragma unroll
@@ -275,10 +352,37 @@ __device__ __forceinline__ void act_epilogue_row(const dbn_act_epilogue& e, uint
     for (int j = 0; j < W; ++j) u[j] = (u[j] < a[j]) ? 1.0f : 0.0f;
     row_store<W>(e.sample, m, n0, u);
   }
+  if (e.colsum.acc != nullptr) {   // bias statistics while the values are in registers (dbn/models.py:143-144)
+    if (e.colsum.ref.ptr != nullptr) {
+      float r[W];
+      if (mat_vec_ok(e.colsum.ref)) {
+        row_load<W>(e.colsum.ref, e.colsum.ref_row0 + m, n0, r);
+      } else {
+#pragma unroll
+        for (int j = 0; j < W; ++j) r[j] = mat_load(e.colsum.ref, e.colsum.ref_row0 + m, n0 + j);
+      }
+#pragma unroll
+      for (int j = 0; j < W; ++j) a[j] = e.colsum.sign * (r[j] - a[j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < W; ++j) a[j] *= e.colsum.sign;
+    }
+    if constexpr (W == 32) {
+      if (fast_stats) {
+        const int lane = (int)(threadIdx.x & 31);
+        const float sum = colsum32(a, lane);
+        stat_add(e.colsum.acc, n0 + lane, sum);
+        return;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < W; ++j) stat_add(e.colsum.acc, n0 + j, a[j]);
+  }
 }
 
 template <int W>
 __device__ __forceinline__ bool upd_vec_ok(const dbn_update_epilogue& e, int m, int n0, int M, int N) {
+  if (e.raw_peers[0] != nullptr) return (m < M) && (n0 + W <= N) && (e.raw.ld & 3) == 0;   // peer buffers are 16-byte aligned
   return (m < M) && (n0 + W <= N) && mat_vec_ok(e.raw) && mat_vec_ok(e.Wb) &&
          (e.raw.ptr != nullptr || ((e.ldw & 3) == 0 && (reinterpret_cast<uintptr_t>(e.W) & 15) == 0));
 }
@@ -295,10 +399,17 @@ __device__ __forceinline__ void upd_epilogue_row(const dbn_update_epilogue& e, i
       if (n0 + 4 * j < N + augN) upd_epilogue_quad_ool(e, m, n0 + 4 * j, acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3], M, N, augM, augN);
     return;
   }
+  if (e.raw_peers[0] != nullptr) {
+    dbn_mat dst;
+    dst.ptr = scatter_row_ptr(e, m); dst.ld = e.raw.ld; dst.dtype = DBN_F32;
+    row_store<W>(dst, 0, n0, acc);
+    return;
+  }
   if (e.raw.ptr != nullptr) {
     row_store<W>(e.raw, m, n0, acc);
     return;
   }
+  upd_take_stats(e, m, n0, W, M, N);
   dbn_mat Wm;
   Wm.ptr = e.W; Wm.ld = e.ldw; Wm.dtype = DBN_F32;
   float w[W];

@@ -292,6 +292,7 @@ __global__ void __launch_bounds__(256) apply_delta_kernel(int V, int H, int h0, 
   const int rows = n_w_rows + (with_db ? 1 : 0);
   const long total = (long)rows * quads;
   dbn_update_epilogue e;
+  memset(&e, 0, sizeof(e));
   e.W = W; e.ldw = ldw; e.Wb = Wb; e.vecM = c; e.vecN = b; e.decay = 1.0f; e.scale = scale;
   e.raw.ptr = nullptr; e.raw.ld = 0; e.raw.dtype = DBN_F32;
   for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {

@@ -223,16 +223,16 @@ __global__ void __launch_bounds__(RP_THREADS, 1) rbm_persistent_kernel(RbmPersis
         *wp = w;   // padding columns: inputs are zero there, so they stay zero
       }
     }
-    float dcv = 0.0f, dbv = 0.0f;
-    if (threadIdx.x < Hc) {
-      for (int bi = 0; bi < Bc; ++bi) dcv += P0[(size_t)bi * Hc + threadIdx.x] - Pk[(size_t)bi * Hc + threadIdx.x];
-    }
     for (int v = threadIdx.x; v < V; v += RP_THREADS) {   // every CTA keeps its own identical copy of b
-      dbv = 0.0f;
+      float dbv = 0.0f;
       for (int bi = 0; bi < Bc; ++bi) dbv += V0[(size_t)bi * Vx + v] - Vt[(size_t)bi * Vx + v];
       bs[v] = fmaf(a.lr_over_bs, dbv, bs[v]);
     }
-    if (threadIdx.x < Hc) cs[threadIdx.x] = fmaf(a.lr_over_bs, dcv, cs[threadIdx.x]);
+    for (int hl = threadIdx.x; hl < Hc; hl += RP_THREADS) {   // strided: Hc may exceed the block (H up to 8192 over <= 8 CTAs)
+      float dcv = 0.0f;
+      for (int bi = 0; bi < Bc; ++bi) dcv += P0[(size_t)bi * Hc + hl] - Pk[(size_t)bi * Hc + hl];
+      cs[hl] = fmaf(a.lr_over_bs, dcv, cs[hl]);
+    }
     __syncthreads();
   }
 

@@ -616,6 +616,8 @@ umma_gemm2_kernel(const __grid_constant__ UmmaGemmParams p, const __grid_constan
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
       constexpr int CH_PER_WARP = (BN / 32) / (UG_EPI_WARPS / 4);
       const int ch0 = ((warp - 2) >> 2) * CH_PER_WARP;   // which column half this warp drains
+      // peer scatter: this warp's 32 x 32 transposition buffer behind the barriers (only allocated for such launches)
+      const uint32_t stage = smem_base + STAGES * STAGE_BYTES + 128 + (uint32_t)(warp - 2) * 4096u;
 #pragma unroll 1
       for (int ch = ch0; ch < ch0 + CH_PER_WARP; ++ch) {
         const int n0 = nb * BN + ch * 32;
@@ -625,7 +627,8 @@ umma_gemm2_kernel(const __grid_constant__ UmmaGemmParams p, const __grid_constan
         float acc[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(v[j]);
-        epi_args.apply(epoch, m, n0, acc, coreM, coreN, augM, augN);
+        if (epi_args.scatter()) epi_args.apply_scatter(stage, m, n0, acc, coreM, coreN);
+        else epi_args.apply(epoch, m, n0, acc, coreM, coreN, augM, augN);
       }
       tc_fence_before();
       __syncwarp();
@@ -924,9 +927,12 @@ umma_gemm_sk_kernel(const __grid_constant__ UmmaGemmParams p, const __grid_const
 struct UmmaActEpi {
   static constexpr bool kIsUpdate = false;
   dbn_act_epilogue e;
+  bool scatter_host() const { return false; }
   __device__ __forceinline__ void apply(uint32_t epoch, int m, int n0, const float acc[32], int M, int N, int, int) const {
     act_epilogue_row<32, true>(e, epoch, m, n0, acc, M, N);
   }
+  __device__ __forceinline__ bool scatter() const { return false; }
+  __device__ __forceinline__ void apply_scatter(uint32_t, int, int, const float*, int, int) const {}
   // split-K kernel: one quad (4 columns) per loop iteration; preload4 requests early what apply4 would wait for
   __device__ __forceinline__ bool preload4(int m, int n4, float pre[4], int M, int N) const {
     if (e.bias == nullptr || m >= M || n4 + 4 > N || (reinterpret_cast<uintptr_t>(e.bias + n4) & 15) != 0) return false;
@@ -942,8 +948,39 @@ struct UmmaActEpi {
 struct UmmaUpdEpi {
   static constexpr bool kIsUpdate = true;
   dbn_update_epilogue e;
+  bool scatter_host() const { return e.raw_peers[0] != nullptr; }
   __device__ __forceinline__ void apply(uint32_t, int m, int n0, const float acc[32], int M, int N, int augM, int augN) const {
     upd_epilogue_row<32>(e, m, n0, acc, M, N, augM, augN);
+  }
+  // Raw delta scattered over peer GPUs (reduce-scatter fused into the contraction).  A TMEM lane is an accumulator
+  // ROW, so a warp's natural store is 32 rows x 16 bytes -- over NVLink that is 32 small write packets.  The warp
+  // therefore transposes its 32 x 32 chunk through 4 KB of shared memory (XOR-swizzled, conflict-free both ways)
+  // and stores 4 rows x 128 contiguous bytes per instruction: full-line packets on the wire.
+  __device__ __forceinline__ bool scatter() const { return e.raw_peers[0] != nullptr; }
+  __device__ __forceinline__ void apply_scatter(uint32_t stage, int m, int n0, const float acc[32], int M, int N) const {
+    const int lane = (int)(threadIdx.x & 31);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      sts128(stage + (uint32_t)(lane * 128 + ((j ^ (lane & 7)) << 4)), acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+    __syncwarp();
+    const int m0 = m - lane, slot = lane & 7;
+    const int n = n0 + slot * 4;
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      const int r = i + (lane >> 3);
+      const float4 x = lds128(stage + (uint32_t)(r * 128 + ((slot ^ (r & 7)) << 4)));
+      const int mr = m0 + r;
+      if (mr < M && n < N) {
+        float* dst = scatter_row_ptr(e, mr) + n;
+        if (n + 4 <= N) {
+          asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(x.x), "f"(x.y), "f"(x.z), "f"(x.w) : "memory");
+        } else {
+          const float t[4] = {x.x, x.y, x.z, x.w};
+          for (int j = 0; j < N - n; ++j) dst[j] = t[j];
+        }
+      }
+    }
+    __syncwarp();   // the buffer is rewritten by the next chunk
   }
   __device__ __forceinline__ bool preload4(int m, int n4, float pre[4], int M, int N) const {   // master weights
     if (e.raw.ptr != nullptr || m >= M || n4 + 4 > N || (e.ldw & 3) != 0 || (reinterpret_cast<uintptr_t>(e.W) & 15) != 0)
@@ -954,7 +991,7 @@ struct UmmaUpdEpi {
   }
   __device__ __forceinline__ void apply4(uint32_t, int m, int n4, const float acc[4], const float* pre, int M, int N,
                                          int augM, int augN) const {
-    upd_epilogue_quad(e, m, n4, acc, M, N, augM, augN, pre);
+    upd_epilogue_quad<false>(e, m, n4, acc, M, N, augM, augN, pre);   // the split-K plan is never used for a peer scatter
   }
 };
 
@@ -1029,12 +1066,13 @@ inline int& umma_sm_reserve() {
   return r;
 }
 inline int umma_num_sms() {
-  static int n = 0;
+  static int cache[DBN_MAX_DEVICES] = {0};
+  const int dev = current_device();
+  int n = cache[dev];
   if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (n <= 0) n = 148;
+    cache[dev] = n;
   }
   return std::max(2, (n - umma_sm_reserve()) & ~1);
 }
@@ -1049,11 +1087,9 @@ inline int umma_launch(cudaStream_t st, UmmaGemmParams& p, const Epi& epi, int c
   constexpr int STAGE_BYTES = KS * (BM + BN) * UG_BK * 2;
   constexpr int STAGES = (UG_SMEM_BUDGET / STAGE_BYTES) > 8 ? 8 : (UG_SMEM_BUDGET / STAGE_BYTES);
   constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + (2 * STAGES + 4) * 8 + 16;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<uint64_t> attr_set{0};   // per device: a second GPU in the same process needs its own opt-in
+  if (first_use_on_device(attr_set))
     DBN_CUDA_OK(cudaFuncSetAttribute(umma_gemm_kernel<BN, KS, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    attr_set = true;
-  }
   p.tiles_m = ceil_div(p.M, BM);
   p.tiles_n = ceil_div(p.N, BN);
   // super-tile of group_m row blocks: A slab (group_m * BM rows) + all of B stay L2-resident
@@ -1095,9 +1131,10 @@ inline void sk_launch_config(cudaLaunchConfig_t& cfg, cudaLaunchAttribute attr[2
 // SMs / S); 0 when the query fails, which disables the split plan.
 template <int BN, class Epi>
 inline int sk_max_clusters(int S) {
-  static int cache[9] = {-1, -1, -1, -1, -1, -1, -1, -1, -1};
+  static int cache_all[DBN_MAX_DEVICES][9];   // per device; stores the answer + 1 (0 = not asked yet)
   if (S < 1 || S > 8) return 0;
-  if (cache[S] < 0) {
+  int* cache = cache_all[current_device()];
+  if (cache[S] == 0) {
     int n = 0;
     if (cudaFuncSetAttribute(umma_gemm_sk_kernel<BN, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, SkCfg<BN>::SMEM) ==
         cudaSuccess) {
@@ -1109,9 +1146,9 @@ inline int sk_max_clusters(int S) {
     }
     cudaGetLastError();
     const int cap = umma_num_sms() / S;
-    cache[S] = n < cap ? n : cap;
+    cache[S] = (n < cap ? n : cap) + 1;
   }
-  return cache[S];
+  return cache[S] - 1;
 }
 
 template <int BN, class Epi>
@@ -1151,12 +1188,13 @@ template <int BN, class Epi>
 inline int umma_launch2(cudaStream_t st, UmmaGemmParams& p, const Epi& epi, int coreM, int coreN, int augM, int augN) {
   constexpr int STAGE_BYTES = UG2_KS * (UG_BM + BN / 2) * UG_BK * 2;
   constexpr int STAGES = UG_SMEM_BUDGET / STAGE_BYTES;
-  constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + (2 * STAGES + 4) * 8 + 16;
-  static bool attr_set = false;
-  if (!attr_set) {
-    DBN_CUDA_OK(cudaFuncSetAttribute(umma_gemm2_kernel<BN, UG2_KS, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    attr_set = true;
-  }
+  constexpr int SMEM_PLAIN = STAGES * STAGE_BYTES + 1024 /*align*/ + 128 /*barriers*/;
+  constexpr int SMEM_MAX = SMEM_PLAIN + UG_EPI_WARPS * 4096;     // + one 32 x 32 fp32 transposition buffer per epilogue warp
+  static_assert((2 * STAGES + 4) * 8 + 16 <= 128 && SMEM_MAX <= 232448, "shared-memory budget");
+  const int SMEM = epi.scatter_host() ? SMEM_MAX : SMEM_PLAIN;
+  static std::atomic<uint64_t> attr_set{0};
+  if (first_use_on_device(attr_set))
+    DBN_CUDA_OK(cudaFuncSetAttribute(umma_gemm2_kernel<BN, UG2_KS, Epi>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_MAX));
   p.tiles_m = ceil_div(p.M, 256);
   p.tiles_n = ceil_div(p.N, BN);
   p.group_m = std::max(1, std::min(p.tiles_m, 8));
@@ -1206,7 +1244,7 @@ inline int umma_gemm_run(cudaStream_t st, int M, int N, int augM, int augN, cons
   // Small outputs: split K over a cluster of 2 or 4 CTAs per tile if the cycle model says the shorter K walk
   // and the S-times wider epilogue beat the reduction (every CTA must get at least one stage of 2 slabs).
   int sk_bn = 0, sk_S = 0, sk_per = 0;
-  if (!two_cta && umma_use_splitk()) {
+  if (!two_cta && umma_use_splitk() && !epi.scatter_host()) {
     long total_slabs = 0, fs_all = 0;
     for (int i = 0; i < n_ops; ++i) {
       total_slabs += ceil_div(ops[i].K, UG_BK);

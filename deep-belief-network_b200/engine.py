@@ -224,6 +224,32 @@ class DeviceRbm:
             self.Wb = torch.zeros(self.H, bf16_pitch(self.V), dtype=torch.bfloat16, device=device)
             self.refresh_shadow()
 
+    @classmethod
+    def blank(cls, H, V, activation, precision, device):
+        """Layer with uninitialised parameters allocated on the device (a data-parallel rank that receives its
+        initial weights by broadcast instead of drawing and uploading them)."""
+        self = cls.__new__(cls)
+        self.lib = require_device()
+        self.device = device
+        self.H, self.V = int(H), int(V)
+        self.act = ACT_IDS[activation]
+        self.prec_name = precision
+        self.prec = PREC_IDS[precision]
+        self.W = torch.empty(self.H, self.V, dtype=torch.float32, device=device)
+        self.b = torch.empty(self.V, dtype=torch.float32, device=device)
+        self.c = torch.empty(self.H, dtype=torch.float32, device=device)
+        self.Wb = None
+        if self.prec == L.PREC_BF16:
+            self.Wb = torch.zeros(self.H, bf16_pitch(self.V), dtype=torch.bfloat16, device=device)
+        return self
+
+    def move_shadow(self, Wb):
+        """Keep the bf16 shadow in caller-provided memory (a peer-visible arena) from now on."""
+        assert self.prec == L.PREC_BF16 and tuple(Wb.shape) == (self.H, bf16_pitch(self.V))
+        Wb.zero_()
+        self.Wb = Wb
+        self.refresh_shadow()
+
     # -- parameters -------------------------------------------------------------------------------
     def refresh_shadow(self):
         if self.Wb is not None:
@@ -327,19 +353,16 @@ class DeviceRbm:
         ws.dbn_rows = int(bmax)   # the layout (and its ones columns) is fixed by this row count
         return ws
 
-    def fit(self, Xd, n_epochs, batch_size, k, lr, seed, rng_mode="philox", verbose=None, dp=None, orders=None,
-            sync=True):
+    def fit(self, Xd, n_epochs, batch_size, k, lr, seed, rng_mode="philox", verbose=None, orders=None, sync=True):
         """BinaryRBM._stochastic_gradient_descent (dbn/models.py:96-122) on a device-resident fp32
         dataset Xd [N,V].  Each epoch = one CUDA graph: gather (double shuffle) + all mini-batch
         CD-k steps.  `verbose(epoch, err)` is called with the reconstruction error if given.
-        dp = (rank, world): data-parallel over mini-batch rows with a sum all-reduce of the deltas.
         orders: object whose get() returns the next epoch's row order (drawn ahead by the caller) instead of
-        drawing it here; sync=False returns with the work queued on the current stream."""
+        drawing it here; sync=False returns with the work queued on the current stream.
+        (Data-parallel training: fit_rbm_data_parallel below.)"""
         n = int(Xd.shape[0])
         if n == 0 or n_epochs <= 0:
             return
-        if dp is not None and dp[1] > 1:
-            return self._fit_dp(Xd, n_epochs, batch_size, k, lr, seed, verbose, dp)
         runner = RbmEpochRunner(self, Xd, batch_size, k, lr, seed, rng_mode)
         for epoch in range(1, n_epochs + 1):
             runner.run(orders.get() if orders is not None else None)
@@ -348,13 +371,65 @@ class DeviceRbm:
         if sync:
             torch.cuda.current_stream().synchronize()
 
-    def _fit_dp(self, Xd, n_epochs, batch_size, k, lr, seed, verbose, dp):
-        runner = DpRbmEpochRunner(self, Xd, batch_size, k, lr, seed, dp)
+
+def fit_rbm_data_parallel(layer, X_host, n_epochs, batch_size, k, lr, seed, dp, next_order, verbose=None):
+    """Data-parallel BinaryRBM._stochastic_gradient_descent (dbn/models.py:96-122) of one layer whose parameters are
+    already identical on every rank.  X_host: the whole dataset on the host (float32 [n, V], the same on every rank);
+    next_order(): on rank 0 returns the next epoch's row order (the reference's double shuffle), ignored elsewhere --
+    the order is broadcast, so the ranks cannot disagree about which rows a mini-batch holds.
+
+    BF16 layers with H % world == 0 take the peer-memory path (dp_peer.DpPeerRunner): a rank uploads only its
+    1/world of the rows and no NCCL call sits on the data path.  Everything else takes DpRbmEpochRunner (NCCL
+    reduce-scatter / all-reduce), for which every rank uploads the whole dataset."""
+    import torch.distributed as dist
+    from . import dp_peer
+    rank, world = dp
+    n, V = int(X_host.shape[0]), int(X_host.shape[1])
+    dp_check_shapes(n, batch_size, world)
+    dev = layer.device
+    runner, group = None, None
+    if dp_peer.peer_path_wanted(layer, world):
+        ok = torch.ones(1, dtype=torch.int32, device=dev)
+        try:
+            nl = n // world
+            group = dp_peer.RealPeerGroup(rank, world, dp_peer.ArenaLayout(world, V, layer.H, nl), dev)
+        except Exception as e:            # no CUDA IPC in this container, peers not reachable, ...
+            group = None
+            ok.zero_()
+            reason = str(e)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)   # all ranks take the same path
+        if int(ok.item()) == 1:
+            Xl = upload_f32(X_host[rank * nl:(rank + 1) * nl], dev)
+            runner = dp_peer.DpPeerRunner(layer, Xl, n, batch_size, k, lr, seed, group.member)
+        else:
+            if group is not None:
+                group.close()
+                group = None
+            if rank == 0:
+                import warnings
+                warnings.warn("dbn_b200: peer-memory exchange unavailable, falling back to NCCL collectives")
+    Xd = None
+    if runner is None:
+        Xd = upload_f32(X_host, dev)
+        runner = DpRbmEpochRunner(layer, Xd, batch_size, k, lr, seed, dp)
+    order_dev = torch.empty(n, dtype=torch.int32, device=dev)
+    try:
         for epoch in range(1, n_epochs + 1):
-            runner.run()
+            if rank == 0:
+                order_dev.copy_(torch.from_numpy(np.ascontiguousarray(next_order(), dtype=np.int32)))
+            dist.broadcast(order_dev, 0)
+            runner.run(order_dev.cpu().numpy())
             if verbose is not None:
-                verbose(epoch, self.reconstruction_error(Xd))
+                if Xd is None:
+                    Xd = upload_f32(X_host, dev)
+                verbose(epoch, layer.reconstruction_error(Xd))
         torch.cuda.current_stream().synchronize()
+    finally:
+        if group is not None:
+            if layer.Wb is not None:      # the shadow must outlive the arena it was moved into
+                layer.Wb = layer.Wb.clone()
+            group.close()
+    return runner
 
 
 class RbmEpochRunner:

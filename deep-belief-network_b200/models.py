@@ -36,9 +36,14 @@ def _device():
 
 
 def _to_device_f32(X):
+    """Host array -> fp32 device tensor.  A pinned source is copied asynchronously (the caller goes on preparing
+    the fit while the rows land); a pageable one goes through the driver's staging and blocks."""
     import torch
     X = np.ascontiguousarray(np.asarray(X), dtype=np.float32)
-    return torch.from_numpy(X).to(_device())
+    t = torch.from_numpy(X)
+    if t.is_pinned():
+        return t.to(_device(), non_blocking=True)
+    return t.to(_device())
 
 
 def _draw_seed():
@@ -151,7 +156,7 @@ class BinaryRBM(BaseEstimator, TransformerMixin, BaseModel):
         return E.DeviceRbm(self.W, self.b, self.c, self.activation_function,
                            precision or self._resolved_precision(), _device())
 
-    def _fit_device(self, Xd, dp=None, draws=None, defer_export=False):
+    def _fit_device(self, Xd, draws=None, defer_export=False):
         """Initialise and train on a device-resident fp32 dataset; returns the DeviceRbm so a
         stacked DBN can keep transforming on the device.  `draws` (a _DrawAhead) supplies, in order, the
         initial parameters, the Philox key and one shuffle per epoch instead of drawing them here;
@@ -169,14 +174,85 @@ class BinaryRBM(BaseEstimator, TransformerMixin, BaseModel):
         if self.verbose:
             cb = lambda it, err: print(">> Epoch %d finished \tRBM Reconstruction error %f" % (it, err))
         layer.fit(Xd, self.n_epochs, self.batch_size, self.contrastive_divergence_iter, self.learning_rate, seed,
-                  rng_mode=self.rng, verbose=cb, dp=dp, orders=draws, sync=not defer_export)
+                  rng_mode=self.rng, verbose=cb, orders=draws, sync=not defer_export)
         if not defer_export:
             self.W, self.b, self.c = layer.export()
         return layer
 
+    def _draw_jobs(self, n, n_features):
+        """The np.random draws of one fit, in sequential order (generator for _DrawAhead): parameters, Philox key,
+        one double shuffle per epoch."""
+        yield self._draw_params(n_features)
+        yield _draw_seed()
+        for _ in range(self.n_epochs if n > 0 else 0):
+            yield E.epoch_order(n)
+
+    def _fit_data_parallel(self, X, dp):
+        """One process per GPU (torchrun, DBN_B200_DATA_PARALLEL=1), same X on every rank.  Rank 0 alone consumes
+        np.random -- parameters, Philox key and every epoch's shuffle are BROADCAST, so replicas start identical and
+        agree on the rows of every mini-batch whatever the other ranks' generator state is."""
+        import torch
+        import torch.distributed as dist
+        rank, world = dp
+        if self.rng != 'philox':
+            raise ValueError("rng='numpy' replays one np.random stream sample by sample and cannot be data-parallel.")
+        if self.activation_function not in ('sigmoid', 'relu'):
+            raise ValueError("Invalid activation function.")
+        if self.optimization_algorithm != 'sgd':
+            raise ValueError("Invalid optimization algorithm.")
+        X = np.ascontiguousarray(np.asarray(X), dtype=np.float32)
+        n, v = int(X.shape[0]), int(X.shape[1])
+        E.dp_check_shapes(n, self.batch_size, world)
+        dev = _device()
+        self.n_visible_units = v
+        self._activation_function_class = (SigmoidActivationFunction if self.activation_function == 'sigmoid'
+                                           else ReLUActivationFunction)
+        precision = self._resolved_precision()
+        draws = None
+        seed_t = torch.zeros(1, dtype=torch.int64, device=dev)
+        try:
+            if rank == 0:
+                draws = _DrawAhead(self._draw_jobs(n, v))      # drawn while the rows upload
+                W, c, b, _cls = draws.get()
+                layer = E.DeviceRbm(W, b, c, self.activation_function, precision, dev)
+                seed = draws.get()
+                seed_t.fill_(seed - (1 << 64) if seed >= (1 << 63) else seed)
+            else:
+                layer = E.DeviceRbm.blank(self.n_hidden_units, v, self.activation_function, precision, dev)
+            for t in (layer.W, layer.b, layer.c, seed_t):
+                dist.broadcast(t, 0)
+            if rank != 0:
+                layer.refresh_shadow()
+            seed = int(seed_t.item()) & 0xFFFFFFFFFFFFFFFF
+            cb = None
+            if self.verbose and rank == 0:
+                cb = lambda it, err: print(">> Epoch %d finished \tRBM Reconstruction error %f" % (it, err))
+            elif self.verbose:
+                cb = lambda it, err: None
+            E.fit_rbm_data_parallel(layer, X, self.n_epochs, self.batch_size, self.contrastive_divergence_iter,
+                                    self.learning_rate, seed, dp, (draws.get if draws is not None else None), verbose=cb)
+        finally:
+            if draws is not None:
+                draws.close()
+        self.W, self.b, self.c = layer.export()
+        return layer
+
     def fit(self, X):
         """Fit the RBM to X (n_samples, n_features).  Returns self (dbn/models.py:49-75)."""
-        self._fit_device(_to_device_f32(X), dp=E.dp_context())
+        dp = E.dp_context()
+        if dp is not None:
+            self._fit_data_parallel(X, dp)
+            return self
+        draws = None
+        if self.rng == 'philox' and os.environ.get("DBN_B200_DRAW_AHEAD", "1") != "0":
+            X = np.asarray(X)   # parameters and shuffles are drawn by a helper thread while the rows upload
+            if X.ndim == 2 and X.shape[0] * self.n_hidden_units >= (1 << 16):
+                draws = _DrawAhead(self._draw_jobs(int(X.shape[0]), int(X.shape[1])))
+        try:
+            self._fit_device(_to_device_f32(X), draws=draws)
+        finally:
+            if draws is not None:
+                draws.close()
         return self
 
     def transform(self, X):
@@ -318,7 +394,7 @@ class AbstractSupervisedDBN(BaseEstimator, BaseModel):
         Xd = _to_device_f32(X)
         if pre_train:
             self.unsupervised_dbn._fit_device(Xd)
-        self._fine_tuning(Xd, np.asarray(y))
+        self._fine_tuning(Xd, y)   # labels as given: the label map's keys are the caller's elements (dbn/models.py:575-584)
         return self
 
     def pre_train(self, X):
@@ -401,12 +477,22 @@ class SupervisedDBNClassification(AbstractSupervisedDBN, ClassifierMixin):
         rows as the reference's per-sample loop, built from one sort of the labels (the loop costs ~40 ms per
         60000 labels, more than the fine-tune iteration it precedes)."""
         self.label_to_idx_map, self.idx_to_label_map = {}, {}
+        raw = labels
         labels = np.asarray(labels)
         onehot = np.zeros((len(labels), self.num_classes))
-        try:
-            uniq, first, inv = np.unique(labels, return_index=True, return_inverse=True)
-        except TypeError:            # labels without an order (mixed objects): the reference's loop
-            for i, label in enumerate(labels):
+        # np.asarray coerces a mixed list such as [1, 'a'] to strings and an object array has no total order:
+        # those take the reference's own loop, whose keys are the elements as given
+        mixed = labels.dtype == object or labels.ndim != 1 or (
+            labels.dtype.kind in "US" and not isinstance(raw, np.ndarray) and
+            not all(isinstance(x, (str, bytes, np.str_, np.bytes_)) for x in raw))
+        uniq = None
+        if not mixed:
+            try:
+                uniq, first, inv = np.unique(labels, return_index=True, return_inverse=True)
+            except TypeError:
+                uniq = None
+        if uniq is None:
+            for i, label in enumerate(raw if mixed else labels):
                 if label not in self.label_to_idx_map:
                     j = len(self.label_to_idx_map)
                     self.label_to_idx_map[label] = j
@@ -416,9 +502,11 @@ class SupervisedDBNClassification(AbstractSupervisedDBN, ClassifierMixin):
         order = np.argsort(first, kind="stable")          # classes in order of first appearance
         rank = np.empty(len(order), dtype=np.intp)
         rank[order] = np.arange(len(order))
+        src = raw if isinstance(raw, (list, tuple)) else labels   # keys are the caller's own elements, as in the loop
         for j, k in enumerate(order):
-            self.label_to_idx_map[uniq[k]] = j
-            self.idx_to_label_map[j] = uniq[k]
+            key = src[first[k]]
+            self.label_to_idx_map[key] = j
+            self.idx_to_label_map[j] = key
         onehot[np.arange(len(labels)), rank[np.asarray(inv).reshape(-1)]] = 1
         return onehot
 

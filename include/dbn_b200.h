@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define DBN_B200_ABI_VERSION 1
+#define DBN_B200_ABI_VERSION 2
 
 /* ---- status codes ---------------------------------------------------------------------- */
 enum {
@@ -67,6 +67,8 @@ enum {
 /* output head: softmax + cross-entropy (dbn/models.py:594-626) or linear + squared error
  * (dbn/models.py:696-720) */
 enum { DBN_HEAD_SOFTMAX = 0, DBN_HEAD_LINEAR = 1 };
+
+#define DBN_MAX_PEERS 8 /* GPUs of one NVSwitch box */
 
 /* ---- plain structs ------------------------------------------------------------------------ */
 typedef struct dbn_mat {
@@ -108,6 +110,21 @@ typedef struct dbn_operands {
   int32_t _pad;
 } dbn_operands;
 
+/* Column statistics of an activation epilogue: acc[n] += round(2^32 * sign * x[m,n]) summed over the rows m of
+ * the launch, where x = a[m,n] (the epilogue's output value) or, with `ref` set, x = ref[ref_row0 + m, n] - a[m,n].
+ * This is how the bias statistics of a CD step are taken where the values already sit in registers --
+ * dc = sum_rows(h_0 - h_k), db = sum_rows(v_0 - v_k) (dbn/models.py:143-144 summed by :115-116) -- instead of
+ * through an extra ones row / column of the dW contraction.  The accumulators are 64-bit FIXED POINT (2^-32):
+ * integer addition is associative, so the result does not depend on the order in which tiles, warps or GPUs
+ * contribute (deterministic, and partial sums of several GPUs add exactly). */
+#define DBN_STAT_ONE 4294967296.0 /* 2^32 */
+typedef struct dbn_colsum {
+  unsigned long long* acc; /* [N] fixed-point accumulators, or NULL = off */
+  float sign;              /* +1 / -1                                     */
+  int32_t ref_row0;
+  dbn_mat ref;             /* optional [rows, ld] matrix (bf16 / fp32)    */
+} dbn_colsum;
+
 /* Activation-type epilogue:
  *     x = acc + bias[n];  a = act(x);  a *= prime(aux[m,n]);  a *= mask;   out = a
  *     sample = (u < a)
@@ -123,6 +140,7 @@ typedef struct dbn_act_epilogue {
   dbn_mat out;       /* value, may be NULL          */
   dbn_mat out2;      /* second copy (other dtype), may be NULL */
   dbn_mat sample;    /* {0,1} sample, may be NULL   */
+  dbn_colsum colsum; /* column statistics of `out`, off when colsum.acc == NULL */
 } dbn_act_epilogue;
 
 /* Update-type epilogue over an (M+augM) x (N+augN) accumulator whose optional extra row / column
@@ -144,6 +162,18 @@ typedef struct dbn_update_epilogue {
   float decay;
   float scale;
   dbn_mat raw;   /* fp32, may be NULL */
+  /* Bias statistics taken by dbn_colsum instead of the ones row / column (augM = augN = 0 then): the thread
+   * that owns row m / column n applies vecM[m] += scale * statM[m] * 2^-32 and clears statM[m] (likewise N). */
+  unsigned long long* statM; /* [M] or NULL */
+  unsigned long long* statN; /* [N] or NULL */
+  /* Scatter of the raw accumulator over peer GPUs (data-parallel reduce-scatter fused into the epilogue):
+   * if raw_peers[0] != NULL, accumulator row m goes to the GPU that owns it, o = m / rows_per_peer, at
+   *   (float*)raw_peers[o] + (raw_slot * rows_per_peer + m - o * rows_per_peer) * raw.ld + n
+   * i.e. into slot `raw_slot` (= the sender's rank) of the owner's receive buffer [n_peers][rows_per_peer][raw.ld].
+   * raw_peers[] are device pointers valid on THIS device (peer mappings, or local memory for the owner itself). */
+  void* raw_peers[DBN_MAX_PEERS];
+  int32_t rows_per_peer;
+  int32_t raw_slot;
 } dbn_update_epilogue;
 
 /* ---- library / device ------------------------------------------------------------------- */
@@ -162,7 +192,8 @@ int dbn_set_sm_reserve(int n_sms);
  * the programmatic-dependency wait returned; [9] ns at exit.  NULL switches it off (default). */
 int dbn_debug_set_trace(void* device_buf);
 /* sizeof() of the structs above as compiled (0 dbn_mat, 1 dbn_rng, 2 dbn_operands, 3 dbn_act_epilogue,
- * 4 dbn_update_epilogue, 5 dbn_rbm_step_args, 6 dbn_mlp_step_args): lets a binding check its layout. */
+ * 4 dbn_update_epilogue, 5 dbn_rbm_step_args, 6 dbn_mlp_step_args, 7 dbn_colsum, 8 dbn_dp_exchange): lets a
+ * binding check its layout. */
 size_t dbn_struct_size(int which);
 
 /* The uniforms the kernels draw (see dbn_rng) computed on the HOST into out_host[rows*cols]: lets a
@@ -198,6 +229,10 @@ int dbn_rbm_visible_means(void* stream, int precision, const dbn_mat* Hm, int B,
 /* dbn_rbm_step_args.flags */
 #define DBN_STEP_SKIP_UPDATE 1 /* run the Gibbs chain only; deltas are produced later by dbn_rbm_delta_rows */
 #define DBN_STEP_SKIP_FIRST_HIDDEN 2 /* the t = 0 hidden phase was already run by dbn_rbm_first_hidden */
+#define DBN_STEP_BIAS_STATS 4 /* BF16 mode: take dc / db as column statistics in the Gibbs-chain epilogues (left in the
+                                 workspace, see dbn_rbm_workspace_stats) instead of the ones row / column of dW.  Without
+                                 the flag the library does so by itself when the extra row / column would cost a tile
+                                 (H or V a multiple of 64) and the step updates in place. */
 
 /* Workspace of one CD-k step for a batch of up to Bmax rows (bytes). */
 size_t dbn_rbm_workspace_bytes(int precision, int Bmax, int V, int H);
@@ -268,6 +303,65 @@ int dbn_rbm_delta_rows(void* stream, const dbn_rbm_step_args* args, int h0, int 
  * is passed with raw_row0 = h0 and a full buffer with raw_row0 = 0. */
 int dbn_rbm_apply_delta(void* stream, int V, int H, int h0, int h1, int with_db, float scale, const float* raw,
                         int ld, int raw_row0, float* W, int ldw, float* b, float* c, const dbn_mat* Wb);
+
+/* The fixed-point bias statistics of the step (DBN_STEP_BIAS_STATS): H + V accumulators inside the workspace,
+ * dc[0..H) then db[0..V), value = sum * 2^32 as a two's-complement 64-bit integer.  Zero after
+ * dbn_rbm_workspace_init; consumed (and cleared) by the in-place update, by the raw-delta output and by
+ * dbn_dp_signal. */
+unsigned long long* dbn_rbm_workspace_stats(int precision, int Bmax, int V, int H, void* workspace);
+
+/* ---- data-parallel exchange over NVLink peer memory (BF16 mode) ------------------------------------------
+ * One process per GPU.  Every rank allocates one peer-visible arena (dbn_peer_alloc), ships its 64-byte handle to
+ * the other ranks (any transport: the engine uses torch.distributed), and maps theirs (dbn_peer_open).  A step is
+ *   1. dbn_rbm_cd_step(flags = SKIP_UPDATE | BIAS_STATS)      Gibbs chain on the rank's rows of the mini-batch
+ *   2. dbn_rbm_delta_scatter                                    dW = P0^T V0 - Pk^T Vk; the epilogue stores every
+ *                                                               accumulator tile straight into the receive buffer of the
+ *                                                               GPU that owns those rows of W (reduce-scatter fused
+ *                                                               into the contraction: the wire time sits under the
+ *                                                               mainloop of the following tiles)
+ *   3. dbn_dp_signal                                            statistics -> every peer; "my deltas are out" flags
+ *   4. dbn_dp_apply                                             owner: ordered sum of the n_peers slots, update of its
+ *                                                               rows of the fp32 master, bf16 rows written into EVERY
+ *                                                               rank's shadow (all-gather fused into the update);
+ *                                                               b, c from the exact integer sum of the statistics
+ *   5. dbn_dp_wait (before the next step's first contraction)  every owner's rows have arrived
+ * No NCCL on the data path; summation order is fixed (rank 0..n-1), so all replicas hold bit-identical parameters
+ * and a run is reproducible.  Replaces the accumulate + update of dbn/models.py:114-119 across GPUs. */
+#define DBN_PEER_HANDLE_BYTES 64
+/* cudaMalloc'ed, zero-filled device memory that other processes of this box can map; handle_out[64]. */
+int dbn_peer_alloc(size_t bytes, void** ptr_out, void* handle_out);
+int dbn_peer_free(void* ptr);
+/* Map another process's arena from its handle (enables peer access); close when done. */
+int dbn_peer_open(const void* handle, void** ptr_out);
+int dbn_peer_close(void* ptr);
+
+typedef struct dbn_dp_exchange {
+  int32_t n_peers, rank;
+  int32_t V, H;
+  int32_t rows_per_peer;           /* H / n_peers rows of W owned by each rank                          */
+  int32_t ld_recv;                 /* row pitch of the receive buffers in floats (multiple of 4, >= V)  */
+  void* recv[DBN_MAX_PEERS];       /* rank j's receive buffer [n_peers][rows_per_peer][ld_recv] fp32    */
+  void* stats[DBN_MAX_PEERS];      /* rank j's statistics slots [n_peers][H + V] uint64                 */
+  void* flags[DBN_MAX_PEERS];      /* rank j's flag words [2][DBN_MAX_PEERS] uint64: deltas out / weights in */
+  dbn_mat Wb[DBN_MAX_PEERS];       /* rank j's bf16 shadow of W                                         */
+} dbn_dp_exchange;                 /* every pointer as mapped on THIS device; entry `rank` is local memory */
+
+/* Step 2: rows [0, H) of dW of the chain left in the workspace by dbn_rbm_cd_step, scattered by owner. */
+int dbn_rbm_delta_scatter(void* stream, const dbn_rbm_step_args* args, const dbn_dp_exchange* x);
+int dbn_dp_signal(void* stream, const dbn_dp_exchange* x, unsigned long long* local_stats, unsigned long long value);
+/* `local_stats`: the accumulators handed to dbn_dp_signal (cleared here for the next step).
+ * `counter`: one zero-initialised uint32 of local device memory (last-block detection; left at zero). */
+int dbn_dp_apply(void* stream, const dbn_dp_exchange* x, float scale, float* W, int ldw, float* b, float* c,
+                 unsigned long long* local_stats, unsigned int* counter, unsigned long long value);
+/* which = 0: deltas of every peer are out; 1: every owner's weight rows are in. */
+int dbn_dp_wait(void* stream, const dbn_dp_exchange* x, int which, unsigned long long value);
+
+/* Epoch shuffle over NVLink: dst[i, :] = row (idx[i] % rows_per_src) of srcs[idx[i] / rows_per_src], bf16 rows of
+ * `ld` elements copied whole (values, ones column and padding).  Each rank stages only ITS slice of the dataset
+ * (rows [r * rows_per_src, ...)) and the ranks read each other's slices through peer mappings, instead of every
+ * rank uploading the whole dataset (dbn/models.py:106-107 + dbn/utils.py:12-13 across GPUs). */
+int dbn_gather_rows_peer(void* stream, void* const* srcs, int n_srcs, int rows_per_src, int ld, const int32_t* idx,
+                         int n_rows, const dbn_mat* dst);
 
 /* ---- supervised fine-tune: _backpropagation + SGD update ------------------------------------ */
 #define DBN_MAX_LAYERS 16

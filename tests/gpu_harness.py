@@ -91,7 +91,7 @@ def stage_operand(X, precision):
 
 
 def run_cd_step(W, b, c, V0, k, act, precision="fp32", seed=0, raw=False, U=None, lr_over_bs=0.0, epoch=0,
-                row0=0):
+                row0=0, flags=0):
     """One dbn_rbm_cd_step.  Returns P0, H0s, Vk, Pk and either the raw deltas (raw=True) or the
     updated parameters."""
     import torch
@@ -103,6 +103,7 @@ def run_cd_step(W, b, c, V0, k, act, precision="fp32", seed=0, raw=False, U=None
     ws = layer.make_workspace(B)
     a = layer._step_args(Xop, k, lr_over_bs, ws, seed, None, None)
     a.B, a.row0 = B, 0
+    a.flags = flags
     a.rng.row0, a.rng.epoch = row0, epoch
     keep = []
     if U is not None:

@@ -43,7 +43,8 @@ def test_host_helper_library_exports_its_header():
 
 def test_struct_layouts_match():
     lib = G.lib()
-    for i, st in enumerate((L.Mat, L.Rng, L.Operands, L.ActEpilogue, L.UpdateEpilogue, L.RbmStepArgs, L.MlpStepArgs)):
+    for i, st in enumerate((L.Mat, L.Rng, L.Operands, L.ActEpilogue, L.UpdateEpilogue, L.RbmStepArgs, L.MlpStepArgs,
+                            L.ColSum, L.DpExchange)):
         assert lib.dbn_struct_size(i) == C.sizeof(st), st.__name__
 
 

@@ -33,7 +33,8 @@ def train(X, W, b, c, act, bs, k, lr, epochs, persistent, seed=77, orders=None):
                                             (300, 256, 256, 32, 1, "relu"),      # config 1, layer 2
                                             (404, 13, 100, 16, 10, "relu"),      # config 4, CD-10     (cluster of 2)
                                             (101, 40, 24, 16, 3, "sigmoid"),     # single CTA, ragged last batch
-                                            (64, 130, 70, 64, 2, "sigmoid")])
+                                            (64, 130, 70, 64, 2, "sigmoid"),
+                                            (48, 13, 5000, 16, 1, "sigmoid")])   # 628 hidden units per CTA > 512 threads
 def test_persistent_epoch_equals_tiled_path_and_oracle(N, V, H, bs, k, act):
     rng = np.random.default_rng(N + V)
     X = (rng.integers(0, 17, (N, V)) / 16.0).astype(np.float32)

@@ -68,6 +68,21 @@ def test_label_maps_first_appearance_order():
     assert l2i == clf.label_to_idx_map
 
 
+def test_label_maps_of_mixed_and_string_labels_follow_the_reference_loop():
+    """A mixed-type list keeps its elements as keys (np.asarray would coerce [1, 'a'] to strings), exactly like
+    the reference's per-sample loop (dbn/models.py:575-584); string and object labels work too."""
+    for y in ([1, 'a', 1, 'b', 'a'], ['x', 'y', 'x'], np.array(['u', 'v', 'u']), np.array([(1, 2), 'k', 'k'], dtype=object)):
+        clf = SupervisedDBNClassification(hidden_layers_structure=[4])
+        clf.num_classes = len(set(list(y)))
+        Y = clf._transform_labels_to_network_format(y)
+        ref_map = {}
+        for label in y:                       # the reference loop
+            ref_map.setdefault(label, len(ref_map))
+        assert clf.label_to_idx_map == ref_map
+        assert [type(k) for k in clf.label_to_idx_map] == [type(k) for k in ref_map]
+        assert Y.argmax(axis=1).tolist() == [ref_map[l] for l in y] and Y.sum() == len(y)
+
+
 def test_regression_output_width():
     r = SupervisedDBNRegression(hidden_layers_structure=[4])
     assert r._determine_num_output_neurons(np.zeros(5)) == 1
