@@ -407,7 +407,6 @@ int dbn_rbm_delta_rows(void* stream, const dbn_rbm_step_args* a, int h0, int h1)
   DBN_REQUIRE(a && a->raw_delta.ptr, "needs args with a raw_delta buffer");
   DBN_REQUIRE(h0 >= 0 && h0 < h1 && h1 <= a->H && (h0 % 64) == 0, "bad row range (h0 must be a multiple of 64)");
   if (a->k == 0) return DBN_OK;
-  const bool tc = a->precision == DBN_PREC_BF16;
   RbmWorkspace ws;
   rbm_ws_layout(a->precision, rbm_ws_rows(a), a->V, a->H, static_cast<char*>(a->workspace), &ws);
   dbn_operands o[2];
@@ -416,8 +415,15 @@ int dbn_rbm_delta_rows(void* stream, const dbn_rbm_step_args* a, int h0, int h1)
   dbn_update_epilogue u = blank_upd();
   u.raw = a->raw_delta;
   u.raw.ptr = static_cast<char*>(u.raw.ptr) + (size_t)h0 * u.raw.ld * sizeof(float);
-  (void)tc;
-  return dbn_gemm_update(stream, a->precision, h1 - h0, a->V, h1 == a->H ? 1 : 0, 1, o, 2, &u);
+  if (!(a->precision == DBN_PREC_BF16 && (a->flags & DBN_STEP_BIAS_STATS)))
+    return dbn_gemm_update(stream, a->precision, h1 - h0, a->V, h1 == a->H ? 1 : 0, 1, o, 2, &u);
+  // the chain took the bias statistics in its epilogues: plain H x V rows, then dc (column V of these rows) and,
+  // with the last block, db (row H) out of the accumulators
+  DBN_TRY(dbn_gemm_update(stream, a->precision, h1 - h0, a->V, 0, 0, o, 2, &u));
+  stats_rows_to_raw_kernel<<<ceil_div((h1 - h0) + a->V, 256), 256, 0, as_stream(stream)>>>(ws.stats, a->H, a->V, h0, h1,
+                                                                                         a->raw_delta);
+  DBN_LAUNCH_CHECK();
+  return DBN_OK;
 }
 
 int dbn_rbm_apply_delta(void* stream, int V, int H, int h0, int h1, int with_db, float scale, const float* raw, int ld,

@@ -165,6 +165,19 @@ __global__ void __launch_bounds__(256) stats_to_raw_kernel(unsigned long long* s
   else R[(size_t)H * raw.ld + (i - H)] = v;
 }
 
+// Row-block form: dc of rows [h0, h1) and, when h1 == H, db.
+__global__ void __launch_bounds__(256) stats_rows_to_raw_kernel(unsigned long long* stats, int H, int V, int h0, int h1,
+                                                                dbn_mat raw) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  float* R = reinterpret_cast<float*>(raw.ptr);
+  if (i < h1 - h0) {
+    R[(size_t)(h0 + i) * raw.ld + V] = stat_take(stats, h0 + i);
+  } else if (h1 == H && i - (h1 - h0) < V) {
+    const int v = i - (h1 - h0);
+    R[(size_t)H * raw.ld + v] = stat_take(stats, H + v);
+  }
+}
+
 struct PeerSrcs {
   const void* p[DBN_MAX_PEERS];
 };

@@ -547,6 +547,9 @@ class DpRbmEpochRunner:
         self.sharded = (layer.prec == L.PREC_BF16 and H % self.world == 0 and len(self.chunks) == 1 and
                         os.environ.get("DBN_B200_DP_SHARDED", "1") != "0")
         self.master_sharded = False
+        # BF16 mode: dc / db as fixed-point column statistics of the chain's epilogues (the single-GPU step does the
+        # same for these widths), written into the raw delta's last column / row by dbn_rbm_delta_rows
+        self.stats_flag = L.STEP_BIAS_STATS if layer.prec == L.PREC_BF16 else 0
         if self.sharded:
             self.hs = H // self.world
             self.shard = torch.zeros(self.hs, self.ldr, dtype=torch.float32, device=layer.device)
@@ -562,7 +565,7 @@ class DpRbmEpochRunner:
         a.row0 = s * self.bl
         a.rng.row0 = dp_global_row0(s, self.bs, self.rank, self.bl)
         main = torch.cuda.current_stream()
-        a.flags = L.STEP_SKIP_UPDATE | L.STEP_SKIP_FIRST_HIDDEN
+        a.flags = L.STEP_SKIP_UPDATE | L.STEP_SKIP_FIRST_HIDDEN | self.stats_flag
         for i, (h0, h1) in enumerate(self.chunks):
             if self.pending:
                 main.wait_event(self.ev_applied[i])
@@ -592,7 +595,7 @@ class DpRbmEpochRunner:
         H, V = layer.H, layer.V
         a.row0 = s * self.bl
         a.rng.row0 = dp_global_row0(s, self.bs, self.rank, self.bl)
-        a.flags = L.STEP_SKIP_UPDATE
+        a.flags = L.STEP_SKIP_UPDATE | self.stats_flag
         L.check(lib.dbn_rbm_cd_step(stream_ptr(), C.byref(a)))                     # whole Gibbs chain, local rows
         L.check(lib.dbn_rbm_delta_rows(stream_ptr(), C.byref(a), 0, H))           # raw = dW | dc ; db  (partial sums)
         h0, h1 = self.rank * self.hs, (self.rank + 1) * self.hs

