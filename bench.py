@@ -386,11 +386,18 @@ def step_roofline(c, flops_per_step, steps, ms):
 
 
 # ---------------------------------------------------------------------------------------------------
+def pick_precision(args, wl):
+    if args.precision != "auto":
+        return args.precision
+    return "bf16" if wl == "c3" else "fp16"
+
+
 def bench_c2(c, steps, warmup, with_e2e=True):
     import ctypes as C
     import torch
     from dbn_b200 import _lib as L, engine as E
     args, dev, lib = c.args, c.dev, c.lib
+    precision = pick_precision(args, "c2")
     rng = np.random.default_rng(0)
     np.random.seed(0)
     Xh = torch.empty(C2_ROWS, 784, dtype=torch.float32).pin_memory()
@@ -400,7 +407,7 @@ def bench_c2(c, steps, warmup, with_e2e=True):
     for v, h in zip(C2_DIMS[:-1], C2_DIMS[1:]):
         W = np.random.randn(h, v) / np.sqrt(v)
         layers.append(E.DeviceRbm(W, np.random.randn(v) / np.sqrt(v), np.random.randn(h) / np.sqrt(v), "sigmoid",
-                                  args.precision, dev))
+                                  precision, dev))
         feats.append(torch.empty(C2_ROWS, h, dtype=torch.float32, device=dev))
     for i, l in enumerate(layers):
         l.transform(feats[i], out=feats[i + 1])
@@ -455,6 +462,7 @@ def bench_c3(c, steps, warmup, with_e2e=True):
     import torch
     from dbn_b200 import _lib as L, engine as E
     args, dev, lib = c.args, c.dev, c.lib
+    precision = pick_precision(args, "c3")
     rng = np.random.default_rng(0)
     np.random.seed(0)
     Xh = torch.empty(C2_ROWS, 784, dtype=torch.float32).pin_memory()
@@ -465,9 +473,9 @@ def bench_c3(c, steps, warmup, with_e2e=True):
     layers = []
     for v, h in zip(C2_DIMS[:-1], C2_DIMS[1:]):
         layers.append(E.DeviceRbm(np.random.randn(h, v) / np.sqrt(v), np.zeros(v), np.random.randn(h) / np.sqrt(v),
-                                  "sigmoid", args.precision, dev))
+                                  "sigmoid", precision, dev))
     mlp = E.DeviceMlp(layers, np.random.randn(10, 2000) / np.sqrt(2000), np.zeros(10), "sigmoid", "softmax",
-                      args.precision, dev)
+                      precision, dev)
     runner = E.MlpIterRunner(mlp, Xd, Yd, C2_BS, 0.1, 1.0, 0.0, 77)
     ms, clocks, eager = timed(c, runner.run, steps, warmup)
     launches = eager + steps * runner.launches_per_iter * (1 if E._use_graphs() else 0)
@@ -476,8 +484,8 @@ def bench_c3(c, steps, warmup, with_e2e=True):
     # dominant kernel alone: the weight-gradient contraction + decayed SGD update of the widest layer
     # (2000 x 501 accumulator, K = 256 rows), timed back to back inside a CUDA graph
     l3 = layers[2]
-    Ad = torch.zeros(C2_BS, E.bf16_pitch(2000), dtype=torch.bfloat16, device=dev)
-    Bd = torch.zeros(C2_BS, E.bf16_pitch(500), dtype=torch.bfloat16, device=dev)
+    Ad = torch.zeros(C2_BS, E.bf16_pitch(2000), dtype=E.OP_DTYPE[E.PREC_IDS[precision]], device=dev)
+    Bd = torch.zeros(C2_BS, E.bf16_pitch(500), dtype=E.OP_DTYPE[E.PREC_IDS[precision]], device=dev)
     Ad[:, :2000] = 0.01
     Bd[:, :501] = 1.0
     ops = L.Operands()
@@ -488,7 +496,7 @@ def bench_c3(c, steps, warmup, with_e2e=True):
     scratchWb = torch.zeros_like(l3.Wb) if l3.Wb is not None else None
     u.W, u.ldw, u.Wb = scratchW.data_ptr(), 500, E.mat(scratchWb)
     u.vecM, u.decay, u.scale = scratchc.data_ptr(), 0.999, -1e-4
-    prec = E.PREC_IDS[args.precision]
+    prec = E.PREC_IDS[precision]
 
     def dom():
         L.check(lib.dbn_gemm_update(E.stream_ptr(), prec, 2000, 500, 0, 1, C.byref(ops), 1, C.byref(u)))
@@ -521,10 +529,11 @@ def bench_c5(c, steps, warmup, with_e2e=True):
     import torch
     from dbn_b200 import _lib as L, dp_peer, engine as E
     args, dev, lib, world, rank = c.args, c.dev, c.lib, c.world, c.rank
+    precision = pick_precision(args, "c5")
     n_rows = C5_BS * C5_STEPS_PER_EPOCH
     gen = torch.Generator(device="cpu").manual_seed(0)
     W = (torch.randn(C5_H, C5_V, generator=gen) / np.sqrt(C5_V)).numpy()
-    layer = E.DeviceRbm(W, np.zeros(C5_V), np.zeros(C5_H), "sigmoid", args.precision, dev)
+    layer = E.DeviceRbm(W, np.zeros(C5_V), np.zeros(C5_H), "sigmoid", precision, dev)
     order = np.arange(n_rows)
     group, exchange = None, "none (one GPU)"
     nvlink = None
@@ -535,7 +544,7 @@ def bench_c5(c, steps, warmup, with_e2e=True):
         if use_peer:
             ok = torch.ones(1, dtype=torch.int32, device=dev)
             try:
-                group = dp_peer.RealPeerGroup(rank, world, dp_peer.ArenaLayout(world, C5_V, C5_H, nl), dev)
+                group = dp_peer.RealPeerGroup(rank, world, dp_peer.ArenaLayout(world, C5_V, C5_H, nl, E.OP_DTYPE[layer.prec]), dev)
             except Exception:
                 group = None
                 ok.zero_()
@@ -588,7 +597,7 @@ def bench_c5(c, steps, warmup, with_e2e=True):
     flops_per_step = 10.0 * C5_V * C5_H * C5_BS
     # dominant kernel alone: v -> h contraction (+ bias, sigmoid, store) on this rank's rows
     bl = C5_BS // world
-    out = torch.empty(bl, E.bf16_pitch(C5_H), dtype=torch.bfloat16, device=dev) if args.precision == "bf16" else \
+    out = torch.empty(bl, E.bf16_pitch(C5_H), dtype=E.OP_DTYPE[layer.prec], device=dev) if layer.prec in E.TC_PRECS else \
         torch.empty(bl, C5_H, dtype=torch.float32, device=dev)
 
     def dom():
@@ -702,7 +711,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--workload", default=None, choices=[None, "c2", "c3", "c5"])
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default="auto", choices=["auto", "bf16", "fp16", "fp32"],
+                    help="auto = what the estimators pick: fp16 operands for the sigmoid RBM workloads (c2, c5), bf16 for the fine-tune (c3)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline legs")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-sub", action="store_true", help="headline workload only (no c1-c4 sub-records at N = 1)")
@@ -724,9 +734,10 @@ def main():
     out = {"metric": rec.pop("metric"), "value": rec.pop("value"), "unit": rec.pop("unit"), "n_gpus": c.world,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": rec.pop("ms_per_step"), "higher_is_better": True,
            "scaling": "strong" if wl == "c5" else "weak", "vs_baseline": None,
-           "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic", "config": rec.pop("config"),
-           "arithmetic": ("bf16 activations x fp16/bf16 weight shadow on tcgen05, fp32 accumulation in TMEM, fp32 master weights"
-                          if args.precision == "bf16" else "strict fp32 FFMA")}
+           "dtype": {"fp32": "f32"}.get(pick_precision(args, wl), pick_precision(args, wl)), "data": "synthetic",
+           "config": rec.pop("config"),
+           "arithmetic": ("%s operands on tcgen05, fp32 accumulation in TMEM, fp32 master weights" % pick_precision(args, wl)
+                          if pick_precision(args, wl) != "fp32" else "strict fp32 FFMA")}
     rec.pop("steps", None); rec.pop("warmup", None)
     out.update(rec)
     if c.rank == 0:

@@ -15,8 +15,8 @@ LIB_PATH = os.path.join(_HERE, "libdbn_b200.so")
 # enums (include/dbn_b200.h)
 OK, ERR_INVALID_ARG, ERR_CUDA, ERR_NO_DEVICE, ERR_UNSUPPORTED = 0, 1, 2, 3, 4
 ACT_IDENTITY, ACT_SIGMOID, ACT_RELU = 0, 1, 2
-F32, BF16 = 0, 1
-PREC_FP32, PREC_BF16 = 0, 1
+F32, BF16, F16 = 0, 1, 2
+PREC_FP32, PREC_BF16, PREC_F16 = 0, 1, 2
 MUL_NONE, MUL_PRIME_SIGMOID, MUL_PRIME_RELU = 0, 1, 2
 RNG_NONE, RNG_SAMPLE, RNG_MASK = 0, 1, 2
 HEAD_SOFTMAX, HEAD_LINEAR = 0, 1

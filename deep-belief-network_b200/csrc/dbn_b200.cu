@@ -14,6 +14,9 @@ using namespace dbn;
 namespace {
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+// the two tensor-core modes differ only in the 16-bit element type of every operand buffer
+inline bool is_tc(int precision) { return precision == DBN_PREC_BF16 || precision == DBN_PREC_F16; }
+inline int tc_dtype(int precision) { return precision == DBN_PREC_F16 ? DBN_F16 : DBN_BF16; }
 
 inline dbn_mat make_mat(void* p, int ld, int dtype) {
   dbn_mat m;
@@ -74,9 +77,9 @@ struct RbmWorkspace {
   unsigned long long* stats;   // [H + V] fixed-point bias statistics dc | db (dbn_colsum)
 };
 size_t rbm_ws_layout(int precision, int Bmax, int V, int H, char* base, RbmWorkspace* ws) {
-  const int dt = precision == DBN_PREC_BF16 ? DBN_BF16 : DBN_F32;
-  const int ldH = precision == DBN_PREC_BF16 ? bf16_pitch(H) : H;
-  const int ldV = precision == DBN_PREC_BF16 ? bf16_pitch(V) : V;
+  const int dt = is_tc(precision) ? tc_dtype(precision) : DBN_F32;
+  const int ldH = is_tc(precision) ? bf16_pitch(H) : H;
+  const int ldV = is_tc(precision) ? bf16_pitch(V) : V;
   size_t off = 0;
   auto carve = [&](int ld) {
     dbn_mat m = make_mat(base ? base + off : nullptr, ld, dt);
@@ -94,10 +97,19 @@ size_t rbm_ws_layout(int precision, int Bmax, int V, int H, char* base, RbmWorks
 // Bias statistics by column sums in the Gibbs-chain epilogues instead of the ones row / column of dW: on request,
 // or -- for an in-place update -- when the extra row / column would cost the dW contraction a whole tile row /
 // column (H or V a multiple of 64: 4096 -> 17 x 17 instead of 16 x 16 CTA-pair tiles, +12.9 % MMA work).
+inline int stats_override() {   // DBN_B200_BIAS_STATS=0/1 forces the choice (experiments); unset = automatic
+  static int v = -2;
+  if (v == -2) {
+    const char* e = getenv("DBN_B200_BIAS_STATS");
+    v = (e == nullptr || e[0] == 0) ? -1 : (e[0] != '0');
+  }
+  return v;
+}
 inline bool rbm_use_stats(const dbn_rbm_step_args* a) {
-  if (a->precision != DBN_PREC_BF16) return false;
+  if (!is_tc(a->precision)) return false;
   if (a->flags & DBN_STEP_BIAS_STATS) return true;
   if (a->flags & DBN_STEP_SKIP_UPDATE) return false;   // deltas come later from dbn_rbm_delta_rows (ones row / column)
+  if (stats_override() >= 0) return stats_override() == 1;
   return (a->H % 64) == 0 || (a->V % 64) == 0;
 }
 
@@ -110,10 +122,10 @@ struct MlpWorkspace {
 };
 size_t mlp_ws_layout(int precision, int Bmax, int n_in, const int32_t* dims, int L, int n_out, char* base,
                      MlpWorkspace* ws) {
-  const int dt = precision == DBN_PREC_BF16 ? DBN_BF16 : DBN_F32;
+  const int dt = is_tc(precision) ? tc_dtype(precision) : DBN_F32;
   size_t off = 0;
   auto carve = [&](int cols, int dtype, bool ones) {
-    const int ld = (dtype == DBN_BF16) ? bf16_pitch(cols) : cols;
+    const int ld = (dtype != DBN_F32) ? bf16_pitch(cols) : cols;
     (void)ones;
     dbn_mat m = make_mat(base ? base + off : nullptr, ld, dtype);
     off = align_up(off + (size_t)Bmax * ld * elt_size(dtype), 1024);
@@ -125,7 +137,7 @@ size_t mlp_ws_layout(int precision, int Bmax, int n_in, const int32_t* dims, int
   for (int l = 0; l < L; ++l) w.delta[l] = carve(dims[l], dt, false);
   w.Z = carve(n_out, DBN_F32, false);
   w.dO = carve(n_out, DBN_F32, false);
-  w.dOb = (precision == DBN_PREC_BF16) ? carve(n_out, DBN_BF16, false) : null_mat();
+  w.dOb = is_tc(precision) ? carve(n_out, dt, false) : null_mat();
   if (ws) *ws = w;
   return off;
 }
@@ -194,7 +206,7 @@ int dbn_gemm_act(void* stream, int precision, int M, int N, const dbn_operands* 
   DBN_NEED_DEVICE();
   DBN_REQUIRE(ops && epi && (n_ops == 1 || n_ops == 2), "bad operands");
   DBN_REQUIRE(M > 0 && N > 0, "empty output");
-  if (precision == DBN_PREC_BF16 && umma_gemm_supported(M, N, ops, n_ops))
+  if (is_tc(precision) && umma_gemm_supported(M, N, ops, n_ops))
     return umma_gemm_act(as_stream(stream), M, N, ops, n_ops, *epi);
   return simt_gemm_act(as_stream(stream), M, N, ops, n_ops, *epi);
 }
@@ -204,7 +216,7 @@ int dbn_gemm_update(void* stream, int precision, int M, int N, int augM, int aug
   DBN_NEED_DEVICE();
   DBN_REQUIRE(ops && epi && (n_ops == 1 || n_ops == 2), "bad operands");
   DBN_REQUIRE(M > 0 && N > 0, "empty output");
-  if (precision == DBN_PREC_BF16 && umma_gemm_supported(M + augM, N + augN, ops, n_ops))
+  if (is_tc(precision) && umma_gemm_supported(M + augM, N + augN, ops, n_ops))
     return umma_gemm_update(as_stream(stream), M, N, augM, augN, ops, n_ops, *epi);
   return simt_gemm_update(as_stream(stream), M, N, augM, augN, ops, n_ops, *epi);
 }
@@ -237,7 +249,7 @@ int dbn_rbm_workspace_init(void* stream, int precision, int Bmax, int V, int H, 
   RbmWorkspace ws;
   size_t bytes = rbm_ws_layout(precision, Bmax, V, H, static_cast<char*>(workspace), &ws);
   DBN_CUDA_OK(cudaMemsetAsync(workspace, 0, bytes, as_stream(stream)));
-  if (precision == DBN_PREC_BF16) {
+  if (is_tc(precision)) {
     DBN_TRY(dbn_fill_ones_column(stream, &ws.P0, Bmax, H));
     DBN_TRY(dbn_fill_ones_column(stream, &ws.Pk, Bmax, H));
     DBN_TRY(dbn_fill_ones_column(stream, &ws.Vt, Bmax, V));
@@ -251,7 +263,7 @@ static inline int rbm_ws_rows(const dbn_rbm_step_args* a) { return a->ws_rows > 
 // t = 0 hidden phase on hidden units [h0, h1): P0 (kept for dW == h_0 of dbn/models.py:140) and the
 // first sample (dbn/models.py:135 -> :148-155).
 static int rbm_first_hidden_impl(void* stream, const dbn_rbm_step_args* a, int h0, int h1) {
-  const bool tc = a->precision == DBN_PREC_BF16;
+  const bool tc = is_tc(a->precision);
   RbmWorkspace ws;
   rbm_ws_layout(a->precision, rbm_ws_rows(a), a->V, a->H, static_cast<char*>(a->workspace), &ws);
   const dbn_mat Wop = tc ? a->Wb : make_mat(a->W, a->ldw, DBN_F32);
@@ -287,8 +299,9 @@ int dbn_rbm_cd_step(void* stream, const dbn_rbm_step_args* a) {
   DBN_REQUIRE(a->act == DBN_ACT_SIGMOID || a->act == DBN_ACT_RELU, "Invalid activation function.");
   DBN_REQUIRE(a->ws_rows == 0 || a->ws_rows >= a->B, "ws_rows smaller than the mini-batch");
   DBN_REQUIRE(a->workspace_bytes >= dbn_rbm_workspace_bytes(a->precision, rbm_ws_rows(a), a->V, a->H), "workspace too small");
-  const bool tc = a->precision == DBN_PREC_BF16;
-  DBN_REQUIRE(!tc || (a->Wb.ptr && a->X.dtype == DBN_BF16), "BF16 mode needs bf16 X and the bf16 shadow of W");
+  const bool tc = is_tc(a->precision);
+  DBN_REQUIRE(!tc || (a->Wb.ptr && a->X.dtype == tc_dtype(a->precision) && a->Wb.dtype == a->X.dtype),
+              "a tensor-core mode needs X and the shadow of W in its 16-bit type (the two operands of an MMA share one format)");
   if (a->k == 0) return DBN_OK;  // v_k == v_0: all deltas are zero (dbn/models.py:134 loop is empty)
   RbmWorkspace ws;
   rbm_ws_layout(a->precision, rbm_ws_rows(a), a->V, a->H, static_cast<char*>(a->workspace), &ws);
@@ -415,7 +428,7 @@ int dbn_rbm_delta_rows(void* stream, const dbn_rbm_step_args* a, int h0, int h1)
   dbn_update_epilogue u = blank_upd();
   u.raw = a->raw_delta;
   u.raw.ptr = static_cast<char*>(u.raw.ptr) + (size_t)h0 * u.raw.ld * sizeof(float);
-  if (!(a->precision == DBN_PREC_BF16 && (a->flags & DBN_STEP_BIAS_STATS)))
+  if (!(is_tc(a->precision) && (a->flags & DBN_STEP_BIAS_STATS)))
     return dbn_gemm_update(stream, a->precision, h1 - h0, a->V, h1 == a->H ? 1 : 0, 1, o, 2, &u);
   // the chain took the bias statistics in its epilogues: plain H x V rows, then dc (column V of these rows) and,
   // with the last block, db (row H) out of the accumulators
@@ -489,7 +502,8 @@ static int dp_check(const dbn_dp_exchange* x) {
   DBN_REQUIRE(x->H > 0 && x->V > 0 && x->rows_per_peer * x->n_peers == x->H, "H must be n_peers * rows_per_peer");
   DBN_REQUIRE(x->ld_recv >= x->V && (x->ld_recv % 4) == 0, "ld_recv must be a multiple of 4 and >= V");
   for (int j = 0; j < x->n_peers; ++j)
-    DBN_REQUIRE(x->recv[j] && x->stats[j] && x->flags[j] && x->Wb[j].ptr && x->Wb[j].dtype == DBN_BF16, "null peer pointer");
+    DBN_REQUIRE(x->recv[j] && x->stats[j] && x->flags[j] && x->Wb[j].ptr &&
+                (x->Wb[j].dtype == DBN_BF16 || x->Wb[j].dtype == DBN_F16) && x->Wb[j].dtype == x->Wb[0].dtype, "bad peer pointer / shadow type");
   return DBN_OK;
 }
 
@@ -497,7 +511,7 @@ int dbn_rbm_delta_scatter(void* stream, const dbn_rbm_step_args* a, const dbn_dp
   DBN_NEED_DEVICE();
   DBN_REQUIRE(a != nullptr, "null args");
   DBN_TRY(dp_check(x));
-  DBN_REQUIRE(a->precision == DBN_PREC_BF16 && x->H == a->H && x->V == a->V, "exchange does not match the layer (BF16 mode only)");
+  DBN_REQUIRE(is_tc(a->precision) && x->H == a->H && x->V == a->V, "exchange does not match the layer (tensor-core modes only)");
   if (a->k == 0) return DBN_OK;
   RbmWorkspace ws;
   rbm_ws_layout(a->precision, rbm_ws_rows(a), a->V, a->H, static_cast<char*>(a->workspace), &ws);
@@ -546,7 +560,7 @@ int dbn_gather_rows_peer(void* stream, void* const* srcs, int n_srcs, int rows_p
                          int n_rows, const dbn_mat* dst) {
   DBN_NEED_DEVICE();
   DBN_REQUIRE(srcs && idx && dst && dst->ptr && n_srcs >= 1 && n_srcs <= DBN_MAX_PEERS && rows_per_src > 0, "bad argument");
-  DBN_REQUIRE(dst->dtype == DBN_BF16 && dst->ld == ld && (ld % 8) == 0, "bf16 rows of the same pitch (multiple of 8) on both sides");
+  DBN_REQUIRE(dst->dtype != DBN_F32 && dst->ld == ld && (ld % 8) == 0, "16-bit rows of the same pitch (multiple of 8) on both sides");
   if (n_rows <= 0) return DBN_OK;
   PeerSrcs ps;
   memset(&ps, 0, sizeof(ps));
@@ -572,7 +586,7 @@ int dbn_mlp_workspace_init(void* stream, int precision, int Bmax, int n_in, cons
   MlpWorkspace ws;
   size_t bytes = mlp_ws_layout(precision, Bmax, n_in, dims, n_layers, n_out, static_cast<char*>(workspace), &ws);
   DBN_CUDA_OK(cudaMemsetAsync(workspace, 0, bytes, as_stream(stream)));
-  if (precision == DBN_PREC_BF16) {
+  if (is_tc(precision)) {
     DBN_TRY(dbn_fill_ones_column(stream, &ws.a0, Bmax, n_in));
     for (int l = 0; l < n_layers; ++l) DBN_TRY(dbn_fill_ones_column(stream, &ws.act[l], Bmax, dims[l]));
   }
@@ -589,7 +603,7 @@ int dbn_mlp_train_step(void* stream, const dbn_mlp_step_args* a) {
   DBN_REQUIRE(ws_rows >= B, "ws_rows smaller than the mini-batch");
   DBN_REQUIRE(a->workspace_bytes >= dbn_mlp_workspace_bytes(a->precision, ws_rows, a->n_in, a->dims, L, a->n_out),
               "workspace too small");
-  const bool tc = a->precision == DBN_PREC_BF16;
+  const bool tc = is_tc(a->precision);
   const bool dropout = a->keep_p < 1.0f;
   const bool raw = a->raw_grads[0].ptr != nullptr;
   cudaStream_t st = as_stream(stream);
@@ -629,8 +643,7 @@ int dbn_mlp_train_step(void* stream, const dbn_mlp_step_args* a) {
     DBN_CUDA_OK(launch_pdl(head_fused_kernel, dim3(ceil_div(B * 32, 256)), dim3(256), 0, st, ws.act[L - 1], HL,
                            (const float*)a->Wo, a->ldwo, (const float*)a->bo, B, a->n_out, a->head,
                            a->Y + (size_t)a->row0 * a->ldy, a->ldy, static_cast<float*>(ws.Z.ptr), ws.Z.ld,
-                           static_cast<float*>(ws.dO.ptr), ws.dO.ld, static_cast<bf16*>(ws.dOb.ptr), ws.dOb.ld,
-                           a->loss_rows));
+                           static_cast<float*>(ws.dO.ptr), ws.dO.ld, ws.dOb, a->loss_rows));
     DBN_LAUNCH_CHECK();
   } else {
     // head scores (dbn/models.py:601 / :703), strict FP32

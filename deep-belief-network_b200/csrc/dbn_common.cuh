@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <atomic>
@@ -109,14 +110,34 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // ---- typed matrix access ------------------------------------------------------------------------
+// two floats <-> one 32-bit word of a 16-bit matrix (bf16 or fp16)
+__device__ __forceinline__ uint32_t pack16x2(int dtype, float a, float b) {
+  if (dtype == DBN_F16) {   // saturating: an out-of-range input loses precision instead of turning into inf
+    const __half2 h = __floats2half2_rn(fminf(fmaxf(a, -65504.0f), 65504.0f), fminf(fmaxf(b, -65504.0f), 65504.0f));
+    return *reinterpret_cast<const uint32_t*>(&h);
+  }
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ void unpack16x2(int dtype, uint32_t w, float& a, float& b) {
+  if (dtype == DBN_F16) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w));
+    a = f.x; b = f.y;
+  } else {
+    const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w);
+    a = __low2float(h); b = __high2float(h);
+  }
+}
 __device__ __forceinline__ float mat_load(const dbn_mat& m, int r, int c) {
   size_t i = (size_t)r * (size_t)m.ld + (size_t)c;
   if (m.dtype == DBN_F32) return reinterpret_cast<const float*>(m.ptr)[i];
+  if (m.dtype == DBN_F16) return __half2float(reinterpret_cast<const __half*>(m.ptr)[i]);
   return __bfloat162float(reinterpret_cast<const bf16*>(m.ptr)[i]);
 }
 __device__ __forceinline__ void mat_store(const dbn_mat& m, int r, int c, float v) {
   size_t i = (size_t)r * (size_t)m.ld + (size_t)c;
   if (m.dtype == DBN_F32) reinterpret_cast<float*>(m.ptr)[i] = v;
+  else if (m.dtype == DBN_F16) reinterpret_cast<__half*>(m.ptr)[i] = __float2half_rn(fminf(fmaxf(v, -65504.0f), 65504.0f));
   else reinterpret_cast<bf16*>(m.ptr)[i] = __float2bfloat16_rn(v);
 }
 // 4 consecutive columns starting at a multiple of 4; vectorised when the row pitch allows it.
@@ -132,11 +153,9 @@ __device__ __forceinline__ void mat_store4(const dbn_mat& m, int r, int c, const
     } else {
       bf16* p = reinterpret_cast<bf16*>(m.ptr) + i;
       if ((reinterpret_cast<uintptr_t>(p) & 7) == 0) {
-        __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]);
-        __nv_bfloat162 hi = __floats2bfloat162_rn(v[2], v[3]);
         uint2 pk;
-        pk.x = *reinterpret_cast<uint32_t*>(&lo);
-        pk.y = *reinterpret_cast<uint32_t*>(&hi);
+        pk.x = pack16x2(m.dtype, v[0], v[1]);
+        pk.y = pack16x2(m.dtype, v[2], v[3]);
         *reinterpret_cast<uint2*>(p) = pk;
         return;
       }
@@ -160,10 +179,8 @@ __device__ __forceinline__ void mat_load4(const dbn_mat& m, int r, int c, float 
       const bf16* p = reinterpret_cast<const bf16*>(m.ptr) + i;
       if ((reinterpret_cast<uintptr_t>(p) & 7) == 0) {
         uint2 pk = *reinterpret_cast<const uint2*>(p);
-        __nv_bfloat162 lo = *reinterpret_cast<__nv_bfloat162*>(&pk.x);
-        __nv_bfloat162 hi = *reinterpret_cast<__nv_bfloat162*>(&pk.y);
-        v[0] = __low2float(lo); v[1] = __high2float(lo);
-        v[2] = __low2float(hi); v[3] = __high2float(hi);
+        unpack16x2(m.dtype, pk.x, v[0], v[1]);
+        unpack16x2(m.dtype, pk.y, v[2], v[3]);
         return;
       }
     }

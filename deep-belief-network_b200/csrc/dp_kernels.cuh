@@ -66,11 +66,6 @@ __global__ void __launch_bounds__(512) dp_signal_kernel(dbn_dp_exchange x, const
   if (threadIdx.x == 0) st_release_sys(dp_flag(x, peer, 0, x.rank), value);
 }
 
-__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
-  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<const uint32_t*>(&h);
-}
-
 __global__ void __launch_bounds__(256) dp_apply_kernel(dbn_dp_exchange x, float scale, float* __restrict__ W, int ldw,
                                                        float* __restrict__ b, float* __restrict__ c,
                                                        unsigned long long* __restrict__ local_stats, unsigned int* counter,
@@ -116,14 +111,15 @@ __global__ void __launch_bounds__(256) dp_apply_kernel(dbn_dp_exchange x, float 
       }
     }
     // all-gather fused into the update: the bf16 row segment goes into every rank's shadow
-    const uint4 pk = make_uint4(pack_bf16x2(w[0], w[1]), pack_bf16x2(w[2], w[3]), pack_bf16x2(w[4], w[5]), pack_bf16x2(w[6], w[7]));
+    const int sdt = x.Wb[me].dtype;      // every rank's shadow has the same 16-bit type
+    const uint4 pk = make_uint4(pack16x2(sdt, w[0], w[1]), pack16x2(sdt, w[2], w[3]), pack16x2(sdt, w[4], w[5]),
+                                pack16x2(sdt, w[6], w[7]));
     for (int j = 0; j < n; ++j) {
       const dbn_mat& S = x.Wb[j];
-      bf16* sp = reinterpret_cast<bf16*>(S.ptr) + (size_t)row * S.ld + col;
       if (nv == 8 && (S.ld & 7) == 0) {
-        *reinterpret_cast<uint4*>(sp) = pk;
+        *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(S.ptr) + (size_t)row * S.ld + col) = pk;
       } else {
-        for (int i = 0; i < nv; ++i) sp[i] = __float2bfloat16_rn(w[i]);
+        for (int i = 0; i < nv; ++i) mat_store(S, row, col + i, w[i]);
       }
     }
   }

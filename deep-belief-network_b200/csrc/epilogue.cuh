@@ -236,11 +236,7 @@ __device__ __forceinline__ void row_load(const dbn_mat& m, int r, int c, float v
       const uint4 t = p[j];
       const uint32_t w[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[k]);
-        v[8 * j + 2 * k] = __low2float(h);
-        v[8 * j + 2 * k + 1] = __high2float(h);
-      }
+      for (int k = 0; k < 4; ++k) unpack16x2(m.dtype, w[k], v[8 * j + 2 * k], v[8 * j + 2 * k + 1]);
     }
   }
 }
@@ -257,10 +253,7 @@ __device__ __forceinline__ void row_store(const dbn_mat& m, int r, int c, const 
     for (int j = 0; j < W / 8; ++j) {
       uint32_t w[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const __nv_bfloat162 h = __floats2bfloat162_rn(v[8 * j + 2 * k], v[8 * j + 2 * k + 1]);
-        w[k] = *reinterpret_cast<const uint32_t*>(&h);
-      }
+      for (int k = 0; k < 4; ++k) w[k] = pack16x2(m.dtype, v[8 * j + 2 * k], v[8 * j + 2 * k + 1]);
       p[j] = make_uint4(w[0], w[1], w[2], w[3]);
     }
   }

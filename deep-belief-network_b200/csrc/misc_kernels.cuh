@@ -149,19 +149,14 @@ __device__ __forceinline__ void head_load8(const dbn_mat& A, int row, int k, flo
     const uint4 t = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(A.ptr) + (size_t)row * A.ld + k);
     const uint32_t w[4] = {t.x, t.y, t.z, t.w};
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[j]);
-      v[2 * j] = __low2float(h);
-      v[2 * j + 1] = __high2float(h);
-    }
+    for (int j = 0; j < 4; ++j) unpack16x2(A.dtype, w[j], v[2 * j], v[2 * j + 1]);
   }
 }
 
 __global__ void __launch_bounds__(256) head_fused_kernel(dbn_mat A, int K, const float* __restrict__ Wo, int ldwo,
                                                          const float* __restrict__ bo, int B, int C, int head,
                                                          const float* __restrict__ Y, int ldy, float* out, int ldo,
-                                                         float* delta, int ldd, bf16* delta_b, int lddb,
-                                                         float* loss_rows) {
+                                                         float* delta, int ldd, dbn_mat delta_b, float* loss_rows) {
   if (threadIdx.x == 0) pdl_launch_dependents();
   pdl_wait();
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -230,7 +225,7 @@ __global__ void __launch_bounds__(256) head_fused_kernel(dbn_mat A, int K, const
   if (valid) {
     out[(size_t)row * ldo + lane] = o_val;
     if (delta != nullptr) delta[(size_t)row * ldd + lane] = o_val - y;
-    if (delta_b != nullptr) delta_b[(size_t)row * lddb + lane] = __float2bfloat16_rn(o_val - y);   // tensor-core operand copy
+    if (delta_b.ptr != nullptr) mat_store(delta_b, row, lane, o_val - y);   // tensor-core operand copy (bf16 / fp16)
   }
   if (loss_rows != nullptr && Y != nullptr && lane == 0) loss_rows[row] = loss;
 }

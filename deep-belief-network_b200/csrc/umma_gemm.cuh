@@ -49,6 +49,7 @@ struct UmmaGemmParams {
   int K[2];
   int nslab[2];   // ceil(K / 64): 64-wide k-slabs per pass
   int transA[2], transB[2];
+  int fmtA[2], fmtB[2];   // tcgen05 kind::f16 operand format per pass: 0 = fp16, 1 = bf16
   int rowA[2], rowB[2];
   int M, N;  // accumulator extent (incl. the ones row / column)
   int tiles_m, tiles_n, group_m;
@@ -171,8 +172,9 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t lbo_b
 // Instruction descriptor of tcgen05.mma.kind::f16: D = F32, A = B = BF16.
 //   [4,6) D format (1 = F32) | [7,10) A format (1 = BF16) | [10,13) B format | 13 negate A | 15 A MN-major
 //   16 B MN-major | [17,23) N >> 3 | [24,29) M >> 4
-__device__ __forceinline__ uint32_t make_idesc(int bm, int bn, int transA, int transB, int negA) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)negA << 13) | ((uint32_t)transA << 15) |
+// fmtA / fmtB: 0 = F16, 1 = BF16 -- the two 16-bit formats may be mixed (one field per operand)
+__device__ __forceinline__ uint32_t make_idesc(int bm, int bn, int transA, int transB, int negA, int fmtA, int fmtB) {
+  return (1u << 4) | ((uint32_t)fmtA << 7) | ((uint32_t)fmtB << 10) | ((uint32_t)negA << 13) | ((uint32_t)transA << 15) |
          ((uint32_t)transB << 16) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(bm >> 4) << 24);
 }
 
@@ -328,7 +330,7 @@ umma_gemm_kernel(const __grid_constant__ UmmaGemmParams p, const __grid_constant
           const int nslab = p.nslab[pass];
           const int nfs = (nslab + KS - 1) / KS;
           const int tA = p.transA[pass], tB = p.transB[pass];
-          const uint32_t idesc = make_idesc(BM, BN, tA, tB, pass == 1);
+          const uint32_t idesc = make_idesc(BM, BN, tA, tB, pass == 1, p.fmtA[pass], p.fmtB[pass]);
           for (int f = 0; f < nfs; ++f, ++it) {
             const int s = it % STAGES;
             const uint32_t ph = (it / STAGES) & 1u;
@@ -463,8 +465,8 @@ __device__ __forceinline__ void mbar_arrive_cta(uint32_t bar, uint32_t cta) {
       "r"(cta)
       : "memory");
 }
-__device__ __forceinline__ uint32_t make_idesc_2sm(int bn, int transA, int transB, int negA) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)negA << 13) | ((uint32_t)transA << 15) |
+__device__ __forceinline__ uint32_t make_idesc_2sm(int bn, int transA, int transB, int negA, int fmtA, int fmtB) {
+  return (1u << 4) | ((uint32_t)fmtA << 7) | ((uint32_t)fmtB << 10) | ((uint32_t)negA << 13) | ((uint32_t)transA << 15) |
          ((uint32_t)transB << 16) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 }
 
@@ -571,7 +573,7 @@ umma_gemm2_kernel(const __grid_constant__ UmmaGemmParams p, const __grid_constan
           const int nslab = p.nslab[pass];
           const int nfs = (nslab + KS - 1) / KS;
           const int tA = p.transA[pass], tB = p.transB[pass];
-          const uint32_t idesc = make_idesc_2sm(BN, tA, tB, pass == 1);
+          const uint32_t idesc = make_idesc_2sm(BN, tA, tB, pass == 1, p.fmtA[pass], p.fmtB[pass]);
           for (int f = 0; f < nfs; ++f, ++it) {
             const int s = it % STAGES;
             const uint32_t ph = (it / STAGES) & 1u;
@@ -794,7 +796,7 @@ umma_gemm_sk_kernel(const __grid_constant__ UmmaGemmParams p, const __grid_const
         const int pass = g >= nfs0 ? 1 : 0;
         const int f = g - pass * nfs0;
         const int tA = p.transA[pass], tB = p.transB[pass];
-        const uint32_t idesc = make_idesc(BM, BN, tA, tB, pass == 1);
+        const uint32_t idesc = make_idesc(BM, BN, tA, tB, pass == 1, p.fmtA[pass], p.fmtB[pass]);
         mbar_wait(full_bar(s), ph);
         tc_fence_after();
         if (it == 0) trace_mark(p, 3);
@@ -1027,7 +1029,8 @@ inline int make_operand_map(CUtensorMap* map, const dbn_mat& X, uint64_t valid_r
   cuuint64_t gstride[2] = {(cuuint64_t)X.ld * 2, 128};
   cuuint32_t box[3] = {64, box_rows, box_slabs};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, X.ptr, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  const CUtensorMapDataType dt = X.dtype == DBN_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  CUresult r = enc(map, dt, 3, X.ptr, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     char buf[64];
@@ -1041,7 +1044,7 @@ inline bool umma_operand_ok(const dbn_mat& X, int cols) {
   // pitch: multiple of 64 elements and wide enough for every 64-column slab the 3-D map addresses; base 16-byte
   // aligned (TMA), 128-byte aligned in practice -- column-offset views (row blocks of P0 in the data-parallel
   // path) start at multiples of 64 columns
-  return X.ptr != nullptr && X.dtype == DBN_BF16 && (X.ld % 64) == 0 && X.ld >= (int)align_up((size_t)cols, 64) &&
+  return X.ptr != nullptr && (X.dtype == DBN_BF16 || X.dtype == DBN_F16) && (X.ld % 64) == 0 && X.ld >= (int)align_up((size_t)cols, 64) &&
          (reinterpret_cast<uintptr_t>(X.ptr) % 16) == 0;
 }
 
@@ -1052,6 +1055,7 @@ inline bool umma_gemm_supported(int M, int N, const dbn_operands* ops, int n_ops
     if (!umma_operand_ok(ops[i].A, ops[i].transA ? M : ops[i].K)) return false;
     if (!umma_operand_ok(ops[i].B, ops[i].transB ? N : ops[i].K)) return false;
     if (ops[i].K < 32) return false;
+    if (ops[i].A.dtype != ops[i].B.dtype) return false;   // one operand format per MMA (mixed bf16 / fp16 traps on sm_100a)
   }
   // worth a 128-row tile: a real row block, or a skinny output whose contraction is still large
   // (the narrow-head gradient: 10 x 2001 with K = batch)
@@ -1273,6 +1277,8 @@ inline int umma_gemm_run(cudaStream_t st, int M, int N, int augM, int augN, cons
     p.K[i] = o.K;
     p.nslab[i] = ceil_div(o.K, UG_BK);
     p.transA[i] = o.transA; p.transB[i] = o.transB;
+    p.fmtA[i] = o.A.dtype == DBN_F16 ? 0 : 1;
+    p.fmtB[i] = o.B.dtype == DBN_F16 ? 0 : 1;
     p.rowA[i] = o.row0_A; p.rowB[i] = o.row0_B;
     if (!o.transA) DBN_TRY(make_operand_map(&p.tmA[i], o.A, (uint64_t)o.row0_A + p.M, p.nslab[i], bm, ks));
     else           DBN_TRY(make_operand_map(&p.tmA[i], o.A, (uint64_t)o.row0_A + o.K, ceil_div(p.M, 64), ks * 64, bm / 64));

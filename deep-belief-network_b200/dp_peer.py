@@ -43,7 +43,7 @@ def device_view(ptr, shape, dtype, device):
     """torch tensor over raw device memory [ptr, ptr + prod(shape) * itemsize) (no copy, no ownership)."""
     if dtype == torch.bfloat16:
         return torch.as_tensor(_DevView(ptr, shape, "<i2"), device=device).view(torch.bfloat16)
-    typestr = {torch.float32: "<f4", torch.int64: "<i8", torch.int32: "<i4", torch.uint8: "|u1"}[dtype]
+    typestr = {torch.float32: "<f4", torch.float16: "<f2", torch.int64: "<i8", torch.int32: "<i4", torch.uint8: "|u1"}[dtype]
     return torch.as_tensor(_DevView(ptr, shape, typestr), device=device)
 
 
@@ -52,11 +52,13 @@ def _align(x, a=1024):
 
 
 class ArenaLayout:
-    """Offsets inside a rank's arena; identical on every rank."""
+    """Offsets inside a rank's arena; identical on every rank.  `op_dtype`: the 16-bit operand type of the layer's
+    tensor-core mode (weight shadow and staged rows)."""
 
-    def __init__(self, world, V, H, rows_local):
+    def __init__(self, world, V, H, rows_local, op_dtype=torch.bfloat16):
         assert H % world == 0
         self.world, self.V, self.H = world, V, H
+        self.op_dtype = op_dtype
         self.hs = H // world
         self.ldr = (V + 3) // 4 * 4
         self.pitch = E.bf16_pitch(V)
@@ -94,16 +96,16 @@ class PeerMember:
             x.recv[j] = b + lay.off_recv
             x.stats[j] = b + lay.off_stats
             x.flags[j] = b + lay.off_flags
-            x.Wb[j] = L.Mat(b + lay.off_wb, lay.pitch, L.BF16)
+            x.Wb[j] = L.Mat(b + lay.off_wb, lay.pitch, L.F16 if lay.op_dtype == torch.float16 else L.BF16)
         return x
 
     def shadow(self):
         lay = self.layout
-        return device_view(self.base + lay.off_wb, (lay.H, lay.pitch), torch.bfloat16, self.device)
+        return device_view(self.base + lay.off_wb, (lay.H, lay.pitch), lay.op_dtype, self.device)
 
     def staged_slice(self):
         lay = self.layout
-        return device_view(self.base + lay.off_xs, (max(lay.rows_local, 1), lay.pitch), torch.bfloat16, self.device)
+        return device_view(self.base + lay.off_xs, (max(lay.rows_local, 1), lay.pitch), lay.op_dtype, self.device)
 
     def staged_sources(self):
         arr = (C.c_void_p * L.MAX_PEERS)()
@@ -213,8 +215,8 @@ class DpPeerRunner:
         self.rank, self.world = member.rank, member.world
         self.n, self.bs, self.k = int(n_total), int(batch_size), int(k)
         E.dp_check_shapes(self.n, self.bs, self.world)
-        assert layer.prec == L.PREC_BF16 and layer.H % self.world == 0
         lay = member.layout
+        assert layer.prec in E.TC_PRECS and layer.H % self.world == 0 and lay.op_dtype == E.OP_DTYPE[layer.prec]
         assert lay.rows_local * self.world == self.n and int(X_local.shape[0]) == lay.rows_local
         self.bl = self.bs // self.world
         self.steps = self.n // self.bs
@@ -319,5 +321,5 @@ def run_epoch_lockstep(runners, order):
 
 
 def peer_path_wanted(layer, world):
-    return (layer.prec == L.PREC_BF16 and layer.H % world == 0 and world <= L.MAX_PEERS and
+    return (layer.prec in E.TC_PRECS and layer.H % world == 0 and world <= L.MAX_PEERS and
             os.environ.get("DBN_B200_DP_P2P", "1") != "0")

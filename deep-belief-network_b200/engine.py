@@ -19,7 +19,9 @@ import torch
 from . import _lib as L
 
 ACT_IDS = {"sigmoid": L.ACT_SIGMOID, "relu": L.ACT_RELU}
-PREC_IDS = {"fp32": L.PREC_FP32, "bf16": L.PREC_BF16}
+PREC_IDS = {"fp32": L.PREC_FP32, "bf16": L.PREC_BF16, "fp16": L.PREC_F16}
+TC_PRECS = (L.PREC_BF16, L.PREC_F16)     # the tensor-core modes: every operand buffer in one 16-bit type
+OP_DTYPE = {L.PREC_BF16: torch.bfloat16, L.PREC_F16: torch.float16, L.PREC_FP32: torch.float32}
 _CHUNK = 16384  # rows per inference / metric chunk
 
 
@@ -35,8 +37,8 @@ def mat(t, ld=None):
     """dbn_mat view of a 2-D (or 1-D) torch tensor."""
     if t is None:
         return L.Mat(None, 0, L.F32)
-    dt = L.BF16 if t.dtype == torch.bfloat16 else L.F32
-    assert t.dtype in (torch.bfloat16, torch.float32), t.dtype
+    assert t.dtype in (torch.bfloat16, torch.float16, torch.float32), t.dtype
+    dt = {torch.bfloat16: L.BF16, torch.float16: L.F16, torch.float32: L.F32}[t.dtype]
     if ld is None:
         ld = t.stride(0) if t.dim() == 2 else t.numel()
     return L.Mat(t.data_ptr(), int(ld), dt)
@@ -52,13 +54,17 @@ def bf16_pitch(cols):
     return (cols + 1 + 63) // 64 * 64
 
 
-def resolve_precision(precision, n_in, n_out, batch_size):
-    """'auto' -> tcgen05 BF16 where the tiles are worth it, strict FP32 otherwise."""
-    if precision not in ("auto", "fp32", "bf16"):
+def resolve_precision(precision, n_in, n_out, batch_size, activation="relu", phase="finetune"):
+    """'auto' -> a tensor-core mode where the tiles are worth it, strict FP32 otherwise.  Of the two 16-bit modes,
+    fp16 (11 significant bits) serves sigmoid RBM pre-training, where every operand is a probability, a binary state
+    or a weight; bf16 (fp32's range) serves relu layers and the back-propagated deltas of the fine-tune."""
+    if precision not in ("auto", "fp32", "bf16", "fp16"):
         raise ValueError("Invalid precision.")
     if precision != "auto":
         return precision
-    return "bf16" if (n_in >= 128 and n_out >= 128 and batch_size >= 64) else "fp32"
+    if not (n_in >= 128 and n_out >= 128 and batch_size >= 64):
+        return "fp32"
+    return "fp16" if (phase == "pretrain" and activation == "sigmoid") else "bf16"
 
 
 def require_device():
@@ -149,27 +155,58 @@ class _PinnedPool:
 _UPLOAD_STREAMS = {}
 
 
-def upload_f32(arr, device):
-    """Host array -> new fp32 device tensor WITHOUT waiting for the work already queued on the compute stream:
-    converted into a pinned staging buffer, copied on a dedicated upload stream, and the compute stream is
-    made to wait for that copy only.  (A pageable `.to(device)` blocks the host until everything queued before
-    it has run, which serialises the layers of a stacked fit.)"""
-    arr = np.asarray(arr)
+_STAGE_CHUNK = 32 << 20     # bytes of pinned staging per chunk of a large pageable upload
+
+
+def _upload_stream(device):
     key = (device.type, device.index)
     up = _UPLOAD_STREAMS.get(key)
     if up is None:
         up = _UPLOAD_STREAMS[key] = torch.cuda.Stream(device=device)
-    buf, ev = _PinnedPool.take(arr.size * 4)
-    stage = buf[:arr.size * 4].view(torch.float32).view(arr.shape)
-    np.copyto(stage.numpy(), arr, casting="unsafe")     # converts float64 -> float32 on the way
+    return up
+
+
+def upload_f32(arr, device):
+    """Host array -> new fp32 device tensor WITHOUT waiting for the work already queued on the compute stream:
+    copied on a dedicated upload stream, and the compute stream is made to wait for that copy only.  (A pageable
+    `.to(device)` blocks the host until everything queued before it has run, which serialises the layers of a
+    stacked fit.)
+      * float32, C-contiguous, page-locked source (a caller that pinned its dataset): one DMA straight from it;
+      * anything else: converted chunk by chunk into two pooled pinned buffers -- the conversion of chunk i+1
+        overlaps the DMA of chunk i, and no staging buffer of the array's size is ever pinned."""
+    arr = np.asarray(arr)
+    up = _upload_stream(device)
     cur = torch.cuda.current_stream(device)
     with torch.cuda.stream(up):
         dev = torch.empty(arr.shape, dtype=torch.float32, device=device)
-        dev.copy_(stage, non_blocking=True)
-        ev.record(up)
+    direct = None
+    if arr.dtype == np.float32 and arr.flags.c_contiguous and arr.size > 0:
+        t = torch.from_numpy(arr)
+        if t.is_pinned():
+            direct = t
+    if direct is not None:
+        with torch.cuda.stream(up):
+            dev.copy_(direct, non_blocking=True)
+    elif arr.size > 0:
+        flat_src = arr.reshape(-1) if arr.flags.c_contiguous else np.ascontiguousarray(arr).reshape(-1)
+        flat_dst = dev.view(-1)
+        per = max(1, _STAGE_CHUNK // 4)
+        n = flat_src.size
+        bufs = [_PinnedPool.take(min(n, per) * 4) for _ in range(1 if n <= per else 2)]
+        for i, s in enumerate(range(0, n, per)):
+            buf, ev = bufs[i % len(bufs)]
+            if i >= len(bufs):
+                ev.synchronize()                      # the DMA that last read this buffer has finished
+            m = min(per, n - s)
+            stage = buf[:m * 4].view(torch.float32)
+            np.copyto(stage.numpy(), flat_src[s:s + m], casting="unsafe")     # converts float64 -> float32 on the way
+            with torch.cuda.stream(up):
+                flat_dst[s:s + m].copy_(stage, non_blocking=True)
+                ev.record(up)
+        for buf, ev in bufs:
+            _PinnedPool.give(buf, ev)
     cur.wait_stream(up)
     dev.record_stream(cur)        # allocated in the upload stream's pool, used on the compute stream
-    _PinnedPool.give(buf, ev)
     return dev
 
 
@@ -220,8 +257,8 @@ class DeviceRbm:
         self.b = upload_f32(b, device)
         self.c = upload_f32(c, device)
         self.Wb = None
-        if self.prec == L.PREC_BF16:
-            self.Wb = torch.zeros(self.H, bf16_pitch(self.V), dtype=torch.bfloat16, device=device)
+        if self.prec in TC_PRECS:
+            self.Wb = torch.zeros(self.H, bf16_pitch(self.V), dtype=OP_DTYPE[self.prec], device=device)
             self.refresh_shadow()
 
     @classmethod
@@ -239,13 +276,13 @@ class DeviceRbm:
         self.b = torch.empty(self.V, dtype=torch.float32, device=device)
         self.c = torch.empty(self.H, dtype=torch.float32, device=device)
         self.Wb = None
-        if self.prec == L.PREC_BF16:
-            self.Wb = torch.zeros(self.H, bf16_pitch(self.V), dtype=torch.bfloat16, device=device)
+        if self.prec in TC_PRECS:
+            self.Wb = torch.zeros(self.H, bf16_pitch(self.V), dtype=OP_DTYPE[self.prec], device=device)
         return self
 
     def move_shadow(self, Wb):
         """Keep the bf16 shadow in caller-provided memory (a peer-visible arena) from now on."""
-        assert self.prec == L.PREC_BF16 and tuple(Wb.shape) == (self.H, bf16_pitch(self.V))
+        assert self.prec in TC_PRECS and tuple(Wb.shape) == (self.H, bf16_pitch(self.V)) and Wb.dtype == OP_DTYPE[self.prec]
         Wb.zero_()
         self.Wb = Wb
         self.refresh_shadow()
@@ -266,14 +303,14 @@ class DeviceRbm:
         return (self.W.double().cpu().numpy(), self.b.double().cpu().numpy(), self.c.double().cpu().numpy())
 
     def w_operand(self):
-        return mat(self.Wb) if self.prec == L.PREC_BF16 else mat(self.W)
+        return mat(self.Wb) if self.prec in TC_PRECS else mat(self.W)
 
     # -- operand staging ---------------------------------------------------------------------------
     def alloc_staged(self, n, cols):
         """Operand buffer for n rows of `cols` features in this precision's layout (BF16: zero-filled, since
         the padding columns are read by the tensor-core path; FP32: uninitialised)."""
-        if self.prec == L.PREC_BF16:   # zero padding: the tensor-core path reads K tails up to the next 64 columns
-            return torch.zeros(n, bf16_pitch(cols), dtype=torch.bfloat16, device=self.device)
+        if self.prec in TC_PRECS:   # zero padding: the tensor-core path reads K tails up to the next 64 columns
+            return torch.zeros(n, bf16_pitch(cols), dtype=OP_DTYPE[self.prec], device=self.device)
         return torch.empty(n, cols, dtype=torch.float32, device=self.device)
 
     def stage(self, Xd, idx=None, out=None, dropout=None):
@@ -283,7 +320,7 @@ class DeviceRbm:
         cols = int(Xd.shape[1])
         if out is None:
             out = self.alloc_staged(n, cols)
-        ones = cols if self.prec == L.PREC_BF16 else -1
+        ones = cols if self.prec in TC_PRECS else -1
         L.check(self.lib.dbn_gather_rows(stream_ptr(), mat(Xd), ptr(idx), n, cols, mat(out), ones,
                                          C.byref(dropout) if dropout is not None else None))
         return out
@@ -307,7 +344,7 @@ class DeviceRbm:
         for s in range(0, n, _CHUNK):
             m = min(_CHUNK, n - s)
             xs = Xd[s:s + m]
-            xop = self.stage(xs) if (self.prec == L.PREC_BF16 or xs.dtype != torch.float32) else xs
+            xop = self.stage(xs) if (self.prec in TC_PRECS or xs.dtype != torch.float32) else xs
             self.hidden_means(xop, 0, m, out[s:s + m])
         return out
 
@@ -315,12 +352,12 @@ class DeviceRbm:
         """mean_n sum_j (reconstruct(transform(x)) - x)^2 (dbn/models.py:212-220)."""
         n = int(Xd.shape[0])
         acc = torch.zeros(1, dtype=torch.float32, device=self.device)
-        hdt = torch.bfloat16 if self.prec == L.PREC_BF16 else torch.float32
-        hld = bf16_pitch(self.H) if self.prec == L.PREC_BF16 else self.H
+        hdt = OP_DTYPE[self.prec]
+        hld = bf16_pitch(self.H) if self.prec in TC_PRECS else self.H
         for s in range(0, n, _CHUNK):
             m = min(_CHUNK, n - s)
             xs = Xd[s:s + m]
-            xop = self.stage(xs) if self.prec == L.PREC_BF16 else xs
+            xop = self.stage(xs) if self.prec in TC_PRECS else xs
             hm = torch.zeros(m, hld, dtype=hdt, device=self.device)   # operand of the next contraction: finite padding
             self.hidden_means(xop, 0, m, hm)
             rec = torch.empty(m, self.V, dtype=torch.float32, device=self.device)
@@ -392,7 +429,7 @@ def fit_rbm_data_parallel(layer, X_host, n_epochs, batch_size, k, lr, seed, dp, 
         ok = torch.ones(1, dtype=torch.int32, device=dev)
         try:
             nl = n // world
-            group = dp_peer.RealPeerGroup(rank, world, dp_peer.ArenaLayout(world, V, layer.H, nl), dev)
+            group = dp_peer.RealPeerGroup(rank, world, dp_peer.ArenaLayout(world, V, layer.H, nl, OP_DTYPE[layer.prec]), dev)
         except Exception as e:            # no CUDA IPC in this container, peers not reachable, ...
             group = None
             ok.zero_()
@@ -544,12 +581,12 @@ class DpRbmEpochRunner:
         self.launches_per_epoch = 0
         # sharded update (reduce-scatter -> row-block update -> all-gather of the bf16 shadow): BF16 mode only,
         # because every contraction then reads the shadow and the fp32 master may stay sharded between steps
-        self.sharded = (layer.prec == L.PREC_BF16 and H % self.world == 0 and len(self.chunks) == 1 and
+        self.sharded = (layer.prec in TC_PRECS and H % self.world == 0 and len(self.chunks) == 1 and
                         os.environ.get("DBN_B200_DP_SHARDED", "1") != "0")
         self.master_sharded = False
         # BF16 mode: dc / db as fixed-point column statistics of the chain's epilogues (the single-GPU step does the
         # same for these widths), written into the raw delta's last column / row by dbn_rbm_delta_rows
-        self.stats_flag = L.STEP_BIAS_STATS if layer.prec == L.PREC_BF16 else 0
+        self.stats_flag = L.STEP_BIAS_STATS if layer.prec in TC_PRECS else 0
         if self.sharded:
             self.hs = H // self.world
             self.shard = torch.zeros(self.hs, self.ldr, dtype=torch.float32, device=layer.device)
@@ -716,13 +753,10 @@ class DeviceMlp:
                 verbose(it, float(runner.loss_rows.sum().item()) / n * scale)
         torch.cuda.current_stream().synchronize()
 
-    def forward(self, Xd):
-        """predict path: stacked transform (dbn/models.py:278-287) + output units (:607-615 / :705-711)."""
-        n = int(Xd.shape[0])
+    def head_outputs(self, A):
+        """_compute_output_units_matrix (dbn/models.py:607-615 / :705-711) on device-resident features [n, H_last]."""
+        n = int(A.shape[0])
         out = torch.empty(n, self.n_out, dtype=torch.float32, device=self.device)
-        A = Xd
-        for l in self.layers:
-            A = l.transform(A)
         ops = L.Operands()
         ops.A, ops.B = mat(A), mat(self.Wo)
         ops.K = self.dims[-1]
@@ -735,6 +769,13 @@ class DeviceMlp:
             L.check(self.lib.dbn_head_delta(stream_ptr(), self.head, ptr(out), self.n_out, None, 0, n, self.n_out,
                                             None, 0, None))
         return out
+
+    def forward(self, Xd):
+        """predict path: stacked transform (dbn/models.py:278-287) + output units (:607-615 / :705-711)."""
+        A = Xd
+        for l in self.layers:
+            A = l.transform(A)
+        return self.head_outputs(A)
 
 
 class MlpIterRunner:

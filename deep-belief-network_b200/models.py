@@ -9,8 +9,9 @@ Fitted parameters are exposed exactly like the reference's NumPy backend: `W (H,
 `W (out,H_last)`, `b (out,)` on the supervised estimators.
 
 Two extra, optional constructor arguments exist on every class (defaults keep the reference's
-behaviour): `precision` in {'auto','fp32','bf16'} selects the strict-FP32 FFMA kernels or the
-tcgen05 BF16 kernels, and `rng` in {'philox','numpy'} selects in-kernel Philox draws or a replay of
+behaviour): `precision` in {'auto','fp32','bf16','fp16'} selects the strict-FP32 FFMA kernels or the
+tcgen05 kernels with bf16 / fp16 operands ('auto': fp16 for sigmoid RBM pre-training, bf16 for relu layers and
+the fine-tune, fp32 for layers too small for a tensor-core tile), and `rng` in {'philox','numpy'} selects in-kernel Philox draws or a replay of
 the reference's `np.random` uniform / binomial stream (parity runs).
 """
 from __future__ import annotations
@@ -102,8 +103,29 @@ class _DrawAhead:
             self._t.join(timeout=0.01)
 
 
+def _signature(*arrays):
+    """Cheap fingerprint of host parameter arrays: identity, shape and a strided checksum.  Lets an estimator keep its
+    fitted layers on the device between fit / transform / predict calls and still notice when a caller has replaced
+    or edited `W`, `b`, `c` (they are plain ndarrays, as in the reference)."""
+    sig = []
+    for a in arrays:
+        a = np.asarray(a)
+        flat = a.reshape(-1)
+        step = max(1, flat.size // 4096)
+        sig.append((id(a), a.shape, a.dtype.str, float(flat[::step].sum()), float(flat[-1]) if flat.size else 0.0))
+    return tuple(sig)
+
+
 class BaseModel(object):
     """save / load by pickling the estimator (reference: dbn/models.py:11-23)."""
+
+    _DEVICE_STATE = ("_dev_cache",)      # device-resident copies of the fitted parameters: never pickled / cloned
+
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        for k in self._DEVICE_STATE:
+            state.pop(k, None)
+        return state
 
     def save(self, save_path):
         with open(save_path, "wb") as fp:
@@ -150,11 +172,26 @@ class BinaryRBM(BaseEstimator, TransformerMixin, BaseModel):
         self.W, self.c, self.b, self._activation_function_class = drawn if drawn is not None else self._draw_params(n_visible)
 
     def _resolved_precision(self):
-        return E.resolve_precision(self.precision, self.n_visible_units, self.n_hidden_units, self.batch_size)
+        return E.resolve_precision(self.precision, self.n_visible_units, self.n_hidden_units, self.batch_size,
+                                   activation=self.activation_function, phase="pretrain")
 
     def _device_layer(self, precision=None):
-        return E.DeviceRbm(self.W, self.b, self.c, self.activation_function,
-                           precision or self._resolved_precision(), _device())
+        """The layer on the device.  The fitted DeviceRbm is kept between calls (no re-upload, no re-cast of the
+        shadow) for as long as W, b, c are the arrays it was built from."""
+        precision = precision or self._resolved_precision()
+        sig = _signature(self.W, self.b, self.c)
+        cache = self.__dict__.setdefault("_dev_cache", {})
+        hit = cache.get(precision)
+        if hit is not None and hit[0] == sig:
+            return hit[1]
+        layer = E.DeviceRbm(self.W, self.b, self.c, self.activation_function, precision, _device())
+        cache[precision] = (sig, layer)
+        return layer
+
+    def _adopt(self, layer):
+        """Fitted parameters from the device; the device copy stays cached for transform / predict."""
+        self.W, self.b, self.c = layer.export()
+        self._dev_cache = {layer.prec_name: (_signature(self.W, self.b, self.c), layer)}
 
     def _fit_device(self, Xd, draws=None, defer_export=False):
         """Initialise and train on a device-resident fp32 dataset; returns the DeviceRbm so a
@@ -176,7 +213,7 @@ class BinaryRBM(BaseEstimator, TransformerMixin, BaseModel):
         layer.fit(Xd, self.n_epochs, self.batch_size, self.contrastive_divergence_iter, self.learning_rate, seed,
                   rng_mode=self.rng, verbose=cb, orders=draws, sync=not defer_export)
         if not defer_export:
-            self.W, self.b, self.c = layer.export()
+            self._adopt(layer)
         return layer
 
     def _draw_jobs(self, n, n_features):
@@ -234,7 +271,7 @@ class BinaryRBM(BaseEstimator, TransformerMixin, BaseModel):
         finally:
             if draws is not None:
                 draws.close()
-        self.W, self.b, self.c = layer.export()
+        self._adopt(layer)
         return layer
 
     def fit(self, X):
@@ -323,7 +360,7 @@ class UnsupervisedDBN(BaseEstimator, TransformerMixin, BaseModel):
                     fitted.append((rbm, layer))
                     data = layer.transform(data)
                 for rbm, layer in fitted:
-                    rbm.W, rbm.b, rbm.c = layer.export()
+                    rbm._adopt(layer)
             finally:
                 draws.close()
         if self.verbose:
@@ -411,19 +448,16 @@ class AbstractSupervisedDBN(BaseEstimator, BaseModel):
         return self._forward(_to_device_f32(X)).double().cpu().numpy()
 
     def _compute_output_units_matrix(self, matrix_visible_units):
-        """Head outputs for already-transformed features (dbn/models.py:607-615, :705-711)."""
-        A = np.asarray(matrix_visible_units, dtype=np.float64)
-        Z = A @ self.W.T + self.b[None, :]
-        if self._head == 'softmax':
-            Ez = np.exp(Z - Z.max(axis=1, keepdims=True))
-            return Ez / Ez.sum(axis=1, keepdims=True)
-        return Z
+        """Head outputs for already-transformed features (dbn/models.py:607-615, :705-711), on the device."""
+        A = _to_device_f32(np.atleast_2d(np.asarray(matrix_visible_units)))
+        return self._cached_mlp().head_outputs(A).double().cpu().numpy()
 
     # ---- device plumbing ----
     def _ft_precision(self):
         rbms = self.unsupervised_dbn.rbm_layers
         widths = [rbms[0].n_visible_units] + [r.n_hidden_units for r in rbms]
-        return E.resolve_precision(self.precision, min(widths), min(widths), self.batch_size)
+        return E.resolve_precision(self.precision, min(widths), min(widths), self.batch_size,
+                                   activation=self.unsupervised_dbn.activation_function, phase="finetune")
 
     def _device_mlp(self, precision):
         dev = _device()
@@ -432,8 +466,23 @@ class AbstractSupervisedDBN(BaseEstimator, BaseModel):
         return E.DeviceMlp(layers, self.W, self.b, self.unsupervised_dbn.activation_function, self._head,
                            precision, dev)
 
+    def _cached_mlp(self):
+        """The fitted network on the device, kept between predict calls while the host parameters are unchanged."""
+        rbms = self.unsupervised_dbn.rbm_layers
+        precision = self._ft_precision()
+        arrays = [self.W, self.b]
+        for r in rbms:
+            arrays += [r.W, r.c]
+        sig = (precision,) + _signature(*arrays)
+        cache = getattr(self, "_dev_cache", None)
+        if cache is not None and cache[0] == sig:
+            return cache[1]
+        mlp = self._device_mlp(precision)
+        self._dev_cache = (sig, mlp)
+        return mlp
+
     def _forward(self, Xd):
-        return self._device_mlp(self._ft_precision()).forward(Xd)
+        return self._cached_mlp().forward(Xd)
 
     def _fine_tuning(self, Xd, _labels):
         """Head init, 1/p pre-scale, SGD, p post-scale (dbn/models.py:517-551)."""
@@ -463,6 +512,10 @@ class AbstractSupervisedDBN(BaseEstimator, BaseModel):
         for rbm, layer in zip(rbms, mlp.layers):
             rbm.W, _b, rbm.c = layer.export()   # rbm.b is not touched by backprop (dbn/models.py:454-460)
         self.W, self.b = mlp.export_head()
+        arrays = [self.W, self.b]
+        for r in rbms:
+            arrays += [r.W, r.c]
+        self._dev_cache = ((mlp.prec_name,) + _signature(*arrays), mlp)     # predict reuses the trained device copy
         if self.verbose:
             print("[END] Fine tuning step")
 

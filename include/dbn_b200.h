@@ -46,12 +46,18 @@ enum {
  * dbn/activations.py:23-38, :43-58).  IDENTITY is the linear regression head (dbn/models.py:696). */
 enum { DBN_ACT_IDENTITY = 0, DBN_ACT_SIGMOID = 1, DBN_ACT_RELU = 2 };
 
-/* element types of a dbn_mat */
-enum { DBN_F32 = 0, DBN_BF16 = 1 };
+/* element types of a dbn_mat (the 16-bit type of a tensor-core operand follows the precision mode) */
+enum { DBN_F32 = 0, DBN_BF16 = 1, DBN_F16 = 2 };
 
-/* arithmetic of the contraction: strict FP32 FFMA (1e-5 parity mode) or tcgen05 BF16 with FP32
- * accumulation in TMEM (2e-3 parity mode). */
-enum { DBN_PREC_FP32 = 0, DBN_PREC_BF16 = 1 };
+/* arithmetic of the contraction: strict FP32 FFMA (1e-5 parity mode) or tcgen05 with 16-bit operands and FP32
+ * accumulation in TMEM (2e-3 parity mode).  The two tensor-core modes differ only in the element type of EVERY
+ * operand buffer (weight shadow, staged inputs, workspace): bf16 has fp32's range (unbounded inputs, relu outputs,
+ * back-propagated deltas), fp16 has 11 significant bits instead of 8 -- the better choice where every operand is a
+ * probability, a binary state or a weight, i.e. sigmoid RBM pre-training: weight quantisation is what bounds the
+ * parity of the 16-bit modes against float64 weights (profiles/r02_bf16_error_report.txt).  The hardware takes ONE
+ * format per MMA (mixing A = bf16 with B = fp16 traps as an illegal instruction on sm_100a), hence a mode, not a
+ * per-matrix choice.  Conversions to fp16 saturate at +-65504. */
+enum { DBN_PREC_FP32 = 0, DBN_PREC_BF16 = 1, DBN_PREC_F16 = 2 };
 
 /* multiplicative term of the activation epilogue: the activation derivative evaluated on the
  * (post-dropout) activation, dbn/activations.py:38 `a*(1-a)` and :58 `(a>0)`. */

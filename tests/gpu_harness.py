@@ -85,7 +85,7 @@ def stage_operand(X, precision):
     if precision == "fp32":
         return Xd
     n, cols = Xd.shape
-    out = torch.zeros(n, E.bf16_pitch(cols), dtype=torch.bfloat16, device="cuda")
+    out = torch.zeros(n, E.bf16_pitch(cols), dtype=E.OP_DTYPE[E.PREC_IDS[precision]], device="cuda")
     L.check(lib().dbn_gather_rows(E.stream_ptr(), E.mat(Xd), None, n, cols, E.mat(out), cols, None))
     return out
 
@@ -170,6 +170,12 @@ def run_mlp_step(layers, Wo, bo, X, Y, act, head, precision="fp32", masks=None, 
     res["layers"] = [(r.export()[0], r.export()[2]) for r in rbms]
     res["Wo"], res["bo"] = mlp.export_head()
     return res
+
+
+def shadow_round(W, precision="bf16"):
+    """float64 array rounded the way the device rounds the 16-bit weight shadow of a tensor-core mode."""
+    import torch
+    return torch.as_tensor(np.asarray(W)).float().to(E.OP_DTYPE[E.PREC_IDS[precision]]).double().numpy()
 
 
 def relF(a, b):

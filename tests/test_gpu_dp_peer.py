@@ -13,11 +13,11 @@ from dbn_b200 import dp_peer, engine as E
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("world,V,H,bl,steps", [(2, 640, 512, 128, 3),      # statistics path on both sides
-                                                (4, 1024, 1280, 64, 2),
-                                                (2, 600, 500, 128, 2),      # ragged: single GPU uses the ones row / column
-                                                (8, 4096, 4096, 256, 2)])   # config-5 widths: CTA-pair kernel, smem-transposed scatter
-def test_virtual_ranks_match_the_single_gpu_runner(world, V, H, bl, steps):
+@pytest.mark.parametrize("world,V,H,bl,steps,prec", [(2, 640, 512, 128, 3, "bf16"),      # statistics path on both sides
+                                                     (4, 1024, 1280, 64, 2, "fp16"),
+                                                     (2, 600, 500, 128, 2, "bf16"),      # ragged: single GPU uses the ones row / column
+                                                     (8, 4096, 4096, 256, 2, "fp16")])   # config-5 widths: CTA-pair kernel, smem-transposed scatter
+def test_virtual_ranks_match_the_single_gpu_runner(world, V, H, bl, steps, prec):
     dev = torch.device("cuda")
     rng = np.random.default_rng(world + V)
     bs = bl * world
@@ -28,11 +28,11 @@ def test_virtual_ranks_match_the_single_gpu_runner(world, V, H, bl, steps):
     orders = [np.random.default_rng(100 + e).permutation(n) for e in range(2)]
     lr, seed = 0.05, 4242
     nl = n // world
-    group = dp_peer.VirtualPeerGroup(world, dp_peer.ArenaLayout(world, V, H, nl), dev)
+    group = dp_peer.VirtualPeerGroup(world, dp_peer.ArenaLayout(world, V, H, nl, E.OP_DTYPE[E.PREC_IDS[prec]]), dev)
     try:
         runners = []
         for m in group.members():
-            layer = E.DeviceRbm(W0, b0, c0, "sigmoid", "bf16", dev)
+            layer = E.DeviceRbm(W0, b0, c0, "sigmoid", prec, dev)
             Xl = torch.from_numpy(X[m.rank * nl:(m.rank + 1) * nl]).to(dev)
             runners.append(dp_peer.DpPeerRunner(layer, Xl, n, bs, 1, lr, seed, m))
         for o in orders:
@@ -46,9 +46,9 @@ def test_virtual_ranks_match_the_single_gpu_runner(world, V, H, bl, steps):
     for (Wr, br, cr), sh in zip(res[1:], shadows[1:]):
         assert np.array_equal(Wr, res[0][0]) and np.array_equal(br, res[0][1]) and np.array_equal(cr, res[0][2])
         assert np.array_equal(sh, shadows[0])
-    assert np.array_equal(shadows[0], torch.as_tensor(res[0][0]).float().to(torch.bfloat16).float().numpy())
+    assert np.array_equal(shadows[0], G.shadow_round(res[0][0], prec).astype(np.float32))
     # single-GPU runner, same seed and shuffles: identical samples (Philox keyed by the global row), fp32 sums in another order
-    single = E.DeviceRbm(W0, b0, c0, "sigmoid", "bf16", dev)
+    single = E.DeviceRbm(W0, b0, c0, "sigmoid", prec, dev)
     r1 = E.RbmEpochRunner(single, torch.from_numpy(X).to(dev), bs, 1, lr, seed)
     for o in orders:
         r1.run(order=o)

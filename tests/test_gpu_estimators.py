@@ -250,3 +250,45 @@ def test_ragged_last_batch_whole_fit_against_oracle(precision, tol):
     for got, ref, init, name in ((m.W, W, W0, "W"), (m.b, b, b0, "b"), (m.c, c, c0, "c")):
         upd = np.linalg.norm(ref - init)
         assert np.linalg.norm(got - ref) < tol * upd + 1e-6, (name, np.linalg.norm(got - ref), upd)
+
+
+def test_converted_reference_model_predicts_on_the_gpu(tmp_path):
+    """SURVEY 8f-3 end to end: a model trained and pickled by the reference's NumPy backend (the unmodified package
+    under oracle/_ref, which travels to the GPU box) is loaded through interop and SERVED by the device path --
+    predict / predict_proba / transform / _compute_output_units_matrix -- with the reference's own outputs as the
+    expectation; a second call reuses the device-resident copy (no re-upload)."""
+    import sys
+    ref_root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref")
+    if not os.path.isdir(os.path.join(ref_root, "dbn")):
+        pytest.skip("oracle/_ref (the installed reference package) is not present")
+    sys.path.insert(0, ref_root)
+    try:
+        import dbn.models as R
+        from dbn_b200 import interop
+        rng = np.random.default_rng(0)
+        X = rng.random((90, 20)).astype(np.float32)
+        y = np.array(["b", "a", "c"])[rng.integers(0, 3, 90)]
+        np.random.seed(3)
+        r = R.SupervisedDBNClassification(hidden_layers_structure=[16, 12], n_epochs_rbm=2, n_iter_backprop=5, batch_size=16,
+                                          learning_rate=0.1, dropout_p=0.1, activation_function="sigmoid", verbose=False)
+        r.fit(X, y)
+        path = os.path.join(tmp_path, "ref.pkl")
+        r.save(path)
+        g = interop.load_reference_pickle(path)
+        P = g.predict_proba(X)
+        assert np.max(np.abs(P - r.predict_proba(X))) < 1e-5
+        assert g.predict(X) == r.predict(X)
+        assert np.max(np.abs(g.transform(X) - r.transform(X))) < 1e-5
+        feats = r.transform(X)
+        assert np.max(np.abs(g._compute_output_units_matrix(feats) - r.predict_proba(X))) < 1e-5
+        cached = g._dev_cache[1]
+        g.predict_proba(X[:5])
+        assert g._dev_cache[1] is cached, "the device copy of the model must be reused between predict calls"
+        g.W = g.W * 2.0                       # a caller edits the head: the cache must notice
+        assert np.max(np.abs(g.predict_proba(X) - P)) > 1e-3 and g._dev_cache[1] is not cached
+        # pickling drops the device state, and the copy predicts the same
+        import pickle
+        g2 = pickle.loads(pickle.dumps(g))
+        assert "_dev_cache" not in g2.__dict__ and np.array_equal(g2.predict_proba(X), g.predict_proba(X))
+    finally:
+        sys.path.remove(ref_root)

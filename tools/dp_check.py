@@ -42,8 +42,8 @@ def main():
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
     ok = True
-    cases = [(640, 512, 256 * world, 3, "bf16"), (200, 136, 64 * world, 2, "fp32"), (1024, 1280, 512 * world, 2, "bf16"),
-             (4096, 4096, 512 * world, 2, "bf16")]
+    cases = [(640, 512, 256 * world, 3, "bf16"), (200, 136, 64 * world, 2, "fp32"), (1024, 1280, 512 * world, 2, "fp16"),
+             (4096, 4096, 512 * world, 2, "fp16")]
     for (V, H, bs, steps, prec) in cases:
         rng = np.random.default_rng(1)
         n = bs * steps
@@ -54,14 +54,14 @@ def main():
         orders = [np.random.default_rng(100 + e).permutation(n) for e in range(2)]
         results = {}
         modes = ["chunked"]
-        if prec == "bf16" and H % world == 0:
+        if prec in ("bf16", "fp16") and H % world == 0:
             modes = ["peer", "sharded", "chunked"]
         for mode in modes:
             layer = E.DeviceRbm(W0, b0, c0, "sigmoid", prec, dev)
             group = None
             if mode == "peer":
                 nl = n // world
-                group = dp_peer.RealPeerGroup(rank, world, dp_peer.ArenaLayout(world, V, H, nl), dev)
+                group = dp_peer.RealPeerGroup(rank, world, dp_peer.ArenaLayout(world, V, H, nl, E.OP_DTYPE[layer.prec]), dev)
                 runner = dp_peer.DpPeerRunner(layer, Xd[rank * nl:(rank + 1) * nl].contiguous(), n, bs, 1, 0.05, 4242,
                                               group.member)
             else:
