@@ -31,6 +31,17 @@
 #define UPPER_MASK 0x80000000UL
 #define LOWER_MASK 0x7fffffffUL
 
+/* The array loops below are plain integer / double code with no cross-iteration dependency inside a vector's reach;
+ * function multi-versioning lets the compiler emit an AVX2 copy and pick it at load time on CPUs that have it (the
+ * library is built on one machine and runs on another).  Integer and IEEE double operations give identical results
+ * in either copy (no FMA contraction: -ffp-contract=off). */
+#if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__)
+#define DBN_CLONES __attribute__((target_clones("avx2", "default")))
+#else
+#define DBN_CLONES
+#endif
+
+DBN_CLONES
 static void mt_regenerate(uint32_t* mt) {
   int i;
   uint32_t y;
@@ -86,6 +97,36 @@ typedef struct {
   double x1[MT_N / 4 + 1], x2[MT_N / 4 + 1], r2[MT_N / 4 + 1];
 } pair_stream;
 
+/* temper `n` state words */
+DBN_CLONES
+static void temper_block(const uint32_t* key, uint32_t* w, int n) {
+  int i;
+  for (i = 0; i < n; i++) {
+    uint32_t y = key[i];
+    y ^= (y >> 11);
+    y ^= (y << 7) & 0x9d2c5680UL;
+    y ^= (y << 15) & 0xefc60000UL;
+    y ^= (y >> 18);
+    w[i] = y;
+  }
+}
+
+/* the polar loop's attempts t = 0 .. n_att-1, each from four consecutive words */
+DBN_CLONES
+static void eval_attempts(const uint32_t* w, int n_att, double* x1o, double* x2o, double* r2o) {
+  int t;
+  for (t = 0; t < n_att; t++) {
+    const int32_t a0 = (int32_t)(w[4 * t] >> 5), b0 = (int32_t)(w[4 * t + 1] >> 6);
+    const int32_t a1 = (int32_t)(w[4 * t + 2] >> 5), b1 = (int32_t)(w[4 * t + 3] >> 6);
+    const double u1 = (a0 * 67108864.0 + b0) / 9007199254740992.0;
+    const double u2 = (a1 * 67108864.0 + b1) / 9007199254740992.0;
+    const double x1 = 2.0 * u1 - 1.0, x2 = 2.0 * u2 - 1.0;
+    x1o[t] = x1;
+    x2o[t] = x2;
+    r2o[t] = x1 * x1 + x2 * x2;
+  }
+}
+
 static void stream_refill(pair_stream* s) {
   int avail, total, i, t;
   if (s->n_att > 0) {         /* the previous list is used up: keep its unconsumed tail words */
@@ -101,20 +142,12 @@ static void stream_refill(pair_stream* s) {
   s->block_p = s->p;
   s->block_carry = s->carry;
   avail = MT_N - s->p;
-  for (i = 0; i < avail; i++) s->w[s->carry + i] = mt_temper(s->key[s->p + i]);
+  temper_block(s->key + s->p, s->w + s->carry, avail);
   total = s->carry + avail;
   s->n_att = total / 4;
   s->t = 0;
-  for (t = 0; t < s->n_att; t++) {
-    const int32_t a0 = (int32_t)(s->w[4 * t] >> 5), b0 = (int32_t)(s->w[4 * t + 1] >> 6);
-    const int32_t a1 = (int32_t)(s->w[4 * t + 2] >> 5), b1 = (int32_t)(s->w[4 * t + 3] >> 6);
-    const double u1 = (a0 * 67108864.0 + b0) / 9007199254740992.0;
-    const double u2 = (a1 * 67108864.0 + b1) / 9007199254740992.0;
-    const double x1 = 2.0 * u1 - 1.0, x2 = 2.0 * u2 - 1.0;
-    s->x1[t] = x1;
-    s->x2[t] = x2;
-    s->r2[t] = x1 * x1 + x2 * x2;
-  }
+  eval_attempts(s->w, s->n_att, s->x1, s->x2, s->r2);
+  (void)t; (void)i;
   if (s->n_att == 0) {        /* fewer than four words in hand (only possible with a nearly exhausted block) */
     s->carry = total;
     s->p = MT_N;
@@ -149,45 +182,59 @@ static int stream_pos(const pair_stream* s) {
   return s->block_p + 4 * s->t - s->block_carry;
 }
 
-static void finish_range(double* pairs, const double* r2, size_t count, int nt) {
+/* The finishing pass of one chunk on up to 16 helper threads, started without waiting: the caller goes on with the
+ * (sequential) rejection pass of the next chunk and joins later. */
+typedef struct {
+  pthread_t th[16];
+  finish_job jobs[16];
+  int started[16];
+  int nt;
+} finish_batch;
+
+static void finish_start(finish_batch* fb, double* pairs, const double* r2, size_t count, int nt) {
   int t;
+  fb->nt = 0;
+  if (count == 0) return;
   if (count < 16384 || nt <= 1) {
     finish_job j = {pairs, r2, 0, count};
     finish_pairs(&j);
     return;
   }
-  {
-    pthread_t th[16];
-    finish_job jobs[16];
-    int started[16];
-    if (nt > 16) nt = 16;
-    for (t = 0; t < nt; t++) {
-      jobs[t].out = pairs;
-      jobs[t].r2 = r2;
-      jobs[t].begin = count * (size_t)t / (size_t)nt;
-      jobs[t].end = count * (size_t)(t + 1) / (size_t)nt;
-      started[t] = (t + 1 < nt) && pthread_create(&th[t], 0, finish_pairs, &jobs[t]) == 0;
-      if (!started[t]) finish_pairs(&jobs[t]);   /* the last share, or a share whose thread did not start */
-    }
-    for (t = 0; t < nt; t++)
-      if (started[t]) pthread_join(th[t], 0);
+  if (nt > 16) nt = 16;
+  fb->nt = nt;
+  for (t = 0; t < nt; t++) {
+    fb->jobs[t].out = pairs;
+    fb->jobs[t].r2 = r2;
+    fb->jobs[t].begin = count * (size_t)t / (size_t)nt;
+    fb->jobs[t].end = count * (size_t)(t + 1) / (size_t)nt;
+    fb->started[t] = pthread_create(&fb->th[t], 0, finish_pairs, &fb->jobs[t]) == 0;
+    if (!fb->started[t]) finish_pairs(&fb->jobs[t]);   /* a share whose thread did not start */
   }
+}
+
+static void finish_join(finish_batch* fb) {
+  int t;
+  for (t = 0; t < fb->nt; t++)
+    if (fb->started[t]) pthread_join(fb->th[t], 0);
+  fb->nt = 0;
 }
 
 /* Fills out[0..n) with what n consecutive legacy_gauss() calls would return, starting from the generator state
  * (key[624], *pos, *has_gauss, *gauss), and leaves that state exactly as those calls would.  Returns 0, or -1 if
  * scratch memory could not be allocated (nothing is consumed then).  Works in chunks of 64 Ki pairs so that the
  * scratch and the freshly written outputs are still in cache when the second pass reads them. */
-#define CHUNK_PAIRS 65536
+#define CHUNK_PAIRS 262144
 int dbn_host_legacy_randn(uint32_t* key, int* pos, int* has_gauss, double* gauss, double* out, size_t n, int n_threads) {
   size_t done = 0, full_pairs, taken = 0;
-  double* r2;
+  double* r2[2];
   pair_stream* s;
-  int odd;
+  finish_batch fb[2];
+  int odd, cur = 0;
   if (n == 0) return 0;
-  r2 = (double*)malloc(sizeof(double) * CHUNK_PAIRS + sizeof(pair_stream));
-  if (!r2) return -1;
-  s = (pair_stream*)(r2 + CHUNK_PAIRS);
+  r2[0] = (double*)malloc(2 * sizeof(double) * CHUNK_PAIRS + sizeof(pair_stream));
+  if (!r2[0]) return -1;
+  r2[1] = r2[0] + CHUNK_PAIRS;
+  s = (pair_stream*)(r2[1] + CHUNK_PAIRS);
   s->key = key;
   s->p = *pos;
   s->carry = 0;
@@ -195,6 +242,7 @@ int dbn_host_legacy_randn(uint32_t* key, int* pos, int* has_gauss, double* gauss
   s->t = 0;
   s->block_p = *pos;
   s->block_carry = 0;
+  fb[0].nt = fb[1].nt = 0;
   if (*has_gauss) {          /* the cached half of an earlier pair comes first */
     out[done++] = *gauss;
     *has_gauss = 0;
@@ -205,10 +253,14 @@ int dbn_host_legacy_randn(uint32_t* key, int* pos, int* has_gauss, double* gauss
   while (taken < full_pairs) {
     const size_t c = full_pairs - taken < CHUNK_PAIRS ? full_pairs - taken : CHUNK_PAIRS;
     double* dst = out + done + 2 * taken;
-    stream_take(s, c, dst, r2);
-    finish_range(dst, r2, c, n_threads);
+    finish_join(&fb[cur]);               /* the r2 buffer of this slot is free again */
+    stream_take(s, c, dst, r2[cur]);     /* sequential: rejection pass of chunk i ... */
+    finish_start(&fb[cur], dst, r2[cur], c, n_threads);   /* ... while chunk i-1 is still being finished */
     taken += c;
+    cur ^= 1;
   }
+  finish_join(&fb[0]);
+  finish_join(&fb[1]);
   if (odd) {
     double last[2], rr, f;
     stream_take(s, 1, last, &rr);
@@ -218,6 +270,6 @@ int dbn_host_legacy_randn(uint32_t* key, int* pos, int* has_gauss, double* gauss
     *has_gauss = 1;
   }
   *pos = stream_pos(s);
-  free(r2);
+  free(r2[0]);
   return 0;
 }

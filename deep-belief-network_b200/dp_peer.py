@@ -175,6 +175,35 @@ class RealPeerGroup:
         self._release()
 
 
+# A fit needs the same arena every time (same layer shape, same slice of the dataset), and setting one up costs
+# far more than training on it for an epoch: cudaMalloc + IPC export / import ~15 ms, unmapping and freeing it
+# ~110 ms (measured on 2 x B200, tools/e2e_dp_breakdown.py).  Groups are therefore kept per process and reused by
+# the next fit with the same layout; every rank takes the same decision because the key is the layout itself.
+_GROUPS = {}
+
+
+def acquire_group(rank, world, layout, device):
+    """A RealPeerGroup for this layout: the cached one (flags cleared, all ranks synchronised) or a new one."""
+    key = (rank, world, layout.V, layout.H, layout.rows_local, str(layout.op_dtype), device.index)
+    g = _GROUPS.get(key)
+    if g is not None and g.own is not None:
+        flags = device_view(g.member.base + layout.off_flags, (2 * L.MAX_PEERS,), torch.int64, device)
+        flags.zero_()
+        g.member.barrier()
+        return g
+    for k in [k for k in _GROUPS if k[0] == rank and k[1] == world and k != key]:
+        _GROUPS.pop(k).close()          # one cached arena per process: a different shape replaces it
+    g = RealPeerGroup(rank, world, layout, device)
+    _GROUPS[key] = g
+    return g
+
+
+def release_groups():
+    """Unmap and free every cached arena (collective: every rank calls it)."""
+    for k in list(_GROUPS):
+        _GROUPS.pop(k).close()
+
+
 class VirtualPeerGroup:
     """`world` virtual ranks in ONE process on ONE GPU: the arenas are ordinary allocations and the peer pointers are
     local.  The caller drives the ranks phase by phase in lockstep (see run_epoch), so every flag a kernel waits for

@@ -210,6 +210,37 @@ def upload_f32(arr, device):
     return dev
 
 
+_CAST_POOL = None
+
+
+def download_f64(t):
+    """fp32 device tensor -> float64 ndarray (the dtype of the reference's parameters): one DMA into pooled pinned
+    memory, then the widening cast on a few host threads (NumPy releases the GIL inside the cast loop).  The
+    obvious `t.double().cpu()` converts on the device and then moves twice the bytes through a pageable copy."""
+    global _CAST_POOL
+    n = t.numel()
+    if n < (1 << 20):
+        return t.detach().double().cpu().numpy()
+    buf, ev = _PinnedPool.take(n * 4)
+    stage = buf[:n * 4].view(torch.float32)
+    stage.copy_(t.detach().reshape(-1), non_blocking=True)
+    ev.record()
+    out = np.empty(n, dtype=np.float64)
+    ev.synchronize()
+    src = stage.numpy()
+    parts = 8
+    if _CAST_POOL is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _CAST_POOL = ThreadPoolExecutor(max_workers=parts)
+    step = (n + parts - 1) // parts
+
+    def cast(i):
+        out[i * step:(i + 1) * step] = src[i * step:(i + 1) * step]
+    list(_CAST_POOL.map(cast, range(parts)))
+    _PinnedPool.give(buf, ev)
+    return out.reshape(tuple(t.shape))
+
+
 class _IndexFeeder:
     """Double-buffered pinned staging of per-epoch permutation indices (the host runs at most two epochs
     ahead of the device)."""
@@ -299,8 +330,8 @@ class DeviceRbm:
         self.refresh_shadow()
 
     def export(self):
-        torch.cuda.synchronize()
-        return (self.W.double().cpu().numpy(), self.b.double().cpu().numpy(), self.c.double().cpu().numpy())
+        torch.cuda.current_stream().synchronize()
+        return (download_f64(self.W), download_f64(self.b), download_f64(self.c))
 
     def w_operand(self):
         return mat(self.Wb) if self.prec in TC_PRECS else mat(self.W)
@@ -429,7 +460,7 @@ def fit_rbm_data_parallel(layer, X_host, n_epochs, batch_size, k, lr, seed, dp, 
         ok = torch.ones(1, dtype=torch.int32, device=dev)
         try:
             nl = n // world
-            group = dp_peer.RealPeerGroup(rank, world, dp_peer.ArenaLayout(world, V, layer.H, nl, OP_DTYPE[layer.prec]), dev)
+            group = dp_peer.acquire_group(rank, world, dp_peer.ArenaLayout(world, V, layer.H, nl, OP_DTYPE[layer.prec]), dev)
         except Exception as e:            # no CUDA IPC in this container, peers not reachable, ...
             group = None
             ok.zero_()
@@ -440,7 +471,7 @@ def fit_rbm_data_parallel(layer, X_host, n_epochs, batch_size, k, lr, seed, dp, 
             runner = dp_peer.DpPeerRunner(layer, Xl, n, batch_size, k, lr, seed, group.member)
         else:
             if group is not None:
-                group.close()
+                dp_peer.release_groups()
                 group = None
             if rank == 0:
                 import warnings
@@ -462,10 +493,10 @@ def fit_rbm_data_parallel(layer, X_host, n_epochs, batch_size, k, lr, seed, dp, 
                 verbose(epoch, layer.reconstruction_error(Xd))
         torch.cuda.current_stream().synchronize()
     finally:
-        if group is not None:
-            if layer.Wb is not None:      # the shadow must outlive the arena it was moved into
-                layer.Wb = layer.Wb.clone()
-            group.close()
+        if group is not None and layer.Wb is not None:
+            # the arena stays cached for the next fit (dp_peer.acquire_group): the layer takes a private copy of its shadow
+            torch.cuda.current_stream().synchronize()
+            layer.Wb = layer.Wb.clone()
     return runner
 
 

@@ -166,10 +166,12 @@ def reconstruction_error(W, b, c, X, activation):
     return float(np.mean(np.sum((R - X) ** 2, axis=1)))
 
 
-def rbm_fit_replay(X, n_hidden, activation="sigmoid", lr=1e-3, n_epochs=10, k=1, batch_size=32):
+def rbm_fit_replay(X, n_hidden, activation="sigmoid", lr=1e-3, n_epochs=10, k=1, batch_size=32, epoch_errors=None):
     """Whole `BinaryRBM.fit` replayed on the global np.random stream in the reference's order
     (SURVEY.md A.3): init, then per epoch two permutations and `random_sample((N,k,H))`
-    (== k sequential `random_sample(H)` per row, dbn/models.py:134-135,155)."""
+    (== k sequential `random_sample(H)` per row, dbn/models.py:134-135,155).  `epoch_errors` (a list) receives what
+    the reference prints after every epoch with verbose=True: the reconstruction error of the whole data set under
+    the epoch's final weights (dbn/models.py:120-122; it consumes no random numbers)."""
     X = np.asarray(X)
     n, v = X.shape
     W, b, c = rbm_init(v, n_hidden, activation)
@@ -180,6 +182,8 @@ def rbm_fit_replay(X, n_hidden, activation="sigmoid", lr=1e-3, n_epochs=10, k=1,
         for s in range(0, n, batch_size):
             cd_step(W, b, c, data[s:s + batch_size].astype(np.float64), U[s:s + batch_size],
                     k, activation, lr, batch_size)
+        if epoch_errors is not None:
+            epoch_errors.append(reconstruction_error(W, b, c, X.astype(np.float64), activation))
     return W, b, c
 
 

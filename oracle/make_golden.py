@@ -196,9 +196,49 @@ def make_digits_anchor(ref, name, seed=1337):
     print("digits anchor: acc=%.4f recon=%s" % (acc, recon))
 
 
+def make_verbose_prints(ref, name, kind, act, dropout, seed, n=41, v=10, hs=(8, 6), bs=8, ep_rbm=3, it=4):
+    """What the reference PRINTS with verbose=True (the default): the per-epoch reconstruction error of every RBM
+    (dbn/models.py:120-122, :212-220) and the per-iteration 'ANN training loss' (:426-427, :448-451, :467-469) --
+    for a classifier that is num_classes x the mean cross-entropy, because the scalar loss of a sample is broadcast
+    into every column of the [N, num_classes] error matrix before its row sums are averaged (:450 with :680)."""
+    import io
+    import re
+    rng = np.random.default_rng(seed)
+    X = rng.random((n, v)).astype(np.float32)
+    if kind == "clf":
+        y = np.array([3, 7, 5, 9])[rng.integers(0, 4, n)]
+        cls = ref.SupervisedDBNClassification
+    else:
+        y = (X @ rng.standard_normal((v, 2)) + 0.05 * rng.standard_normal((n, 2)))
+        cls = ref.SupervisedDBNRegression
+    np.random.seed(seed)
+    m = cls(hidden_layers_structure=list(hs), learning_rate_rbm=0.05, learning_rate=0.1, n_epochs_rbm=ep_rbm,
+            n_iter_backprop=it, batch_size=bs, activation_function=act, dropout_p=dropout, verbose=True)
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        m.fit(X, y)
+    text = buf.getvalue()
+    rbm = [float(x) for x in re.findall(r"RBM Reconstruction error ([-0-9.eE+]+)", text)]
+    ann = [float(x) for x in re.findall(r"ANN training loss ([-0-9.eE+]+)", text)]
+    assert len(rbm) == ep_rbm * len(hs) and len(ann) == it, (len(rbm), len(ann))
+    np.savez(os.path.join(OUT, name + ".npz"), X=X, y=y, rbm_errors=np.array(rbm), ann_losses=np.array(ann),
+             dropout=dropout, act=act, kind=kind, meta=np.array([n, v, bs, ep_rbm, it, 1, seed]), hs=np.array(hs),
+             num_classes=(len(np.unique(y)) if kind == "clf" else y.shape[1]), Wo=m.W)
+    print(name, "rbm", rbm, "ann", ann)
+
+
 def main():
     ref = _import_reference()
     os.makedirs(OUT, exist_ok=True)
+    only = set(sys.argv[1:])
+    if only:      # regenerate selected fixtures only (np.savez archives carry timestamps: avoid churning the rest)
+        if "verbose_clf_sigmoid" in only:
+            make_verbose_prints(ref, "verbose_clf_sigmoid", "clf", "sigmoid", 0.0, 51)
+        if "verbose_reg_relu" in only:
+            make_verbose_prints(ref, "verbose_reg_relu", "reg", "relu", 0.0, 52, hs=(9,))
+        return
+    make_verbose_prints(ref, "verbose_clf_sigmoid", "clf", "sigmoid", 0.0, 51)
+    make_verbose_prints(ref, "verbose_reg_relu", "reg", "relu", 0.0, 52, hs=(9,))
     make_rbm_fit(ref, "rbm_fit_sigmoid_k1", "sigmoid", 1, 11)
     make_rbm_fit(ref, "rbm_fit_sigmoid_k3", "sigmoid", 3, 12)
     make_rbm_fit(ref, "rbm_fit_relu_k1", "relu", 1, 13)
