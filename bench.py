@@ -62,7 +62,8 @@ def peaks():
 
 # ---------------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled every 100 ms during the timed region."""
+    """SM clock and throttle reasons of this rank's GPU sampled every 5 ms through NVML (in-process, so that even a
+    30 ms timed region holds several samples); `nvidia-smi -lms 100` is the fallback when NVML cannot be loaded."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -71,8 +72,41 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.rows, self.proc = index, [], None
         self.t0 = self.t1 = None
+        self._stop_flag = False
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = index
+            if vis:
+                ids = [v.strip() for v in vis.split(",") if v.strip()]
+                if index < len(ids) and ids[index].isdigit():
+                    phys = int(ids[index])
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _nvml_row(self):
+        n = self.nvml
+        sm = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+        r = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+        act = lambda bit: "Active" if (r & bit) else "Not Active"
+        return [str(sm), str(self.max_sm), "0",
+                act(n.nvmlClocksThrottleReasonHwSlowdown), act(n.nvmlClocksThrottleReasonHwThermalSlowdown),
+                act(n.nvmlClocksThrottleReasonSwThermalSlowdown), act(n.nvmlClocksThrottleReasonSwPowerCap)]
 
     def run(self):
+        if self.nvml is not None:
+            while not self._stop_flag:
+                try:
+                    self.rows.append((time.perf_counter(), self._nvml_row()))
+                except Exception:
+                    break
+                time.sleep(0.005)
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -89,12 +123,13 @@ class ClockSampler(threading.Thread):
         self.t1 = time.perf_counter()
 
     def stop(self):
+        self._stop_flag = True
         if self.proc is not None:
             self.proc.terminate()
         self.join(timeout=2)
         # samples taken inside the timed region; if it was shorter than the sampling period, the samples
         # of the (identical-load) warm-up that immediately precedes it are used and the window says so
-        inside = [r for (t, r) in self.rows if self.t0 is not None and self.t0 - 0.05 <= t <= self.t1 + 0.05]
+        inside = [r for (t, r) in self.rows if self.t0 is not None and self.t0 <= t <= self.t1]
         window = "timed region"
         if len(inside) < 2:
             inside = [r for (_t, r) in self.rows][-10:]
@@ -104,7 +139,8 @@ class ClockSampler(threading.Thread):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({names[i] for r in inside if len(r) >= 7 for i in range(4) if r[3 + i] == "Active"})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm), "window": window}
+                "reasons": reasons, "samples": len(sm), "window": window,
+                "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 # ---------------------------------------------------------------------------------------------------

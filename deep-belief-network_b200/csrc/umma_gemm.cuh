@@ -53,6 +53,7 @@ struct UmmaGemmParams {
   int rowA[2], rowB[2];
   int M, N;  // accumulator extent (incl. the ones row / column)
   int tiles_m, tiles_n, group_m;
+  int mb_rot;          // row blocks are visited in the order (mb + mb_rot) % tiles_m (peer scatter: own rows last)
   int split, fs_per;   // split-K kernel: cluster size and fat stages per CTA
   long long* trace;  // debug: per-CTA phase timestamps (dbn_debug_set_trace), normally NULL
 };
@@ -185,7 +186,8 @@ __device__ __forceinline__ void tile_coords(const UmmaGemmParams& p, int tile, i
   const int first_m = g * p.group_m;
   const int gm = min(p.group_m, p.tiles_m - first_m);
   const int r = tile - g * per_group;
-  mb = first_m + r % gm;
+  mb = first_m + r % gm + p.mb_rot;
+  if (mb >= p.tiles_m) mb -= p.tiles_m;
   nb = r / gm;
 }
 
@@ -930,6 +932,7 @@ struct UmmaActEpi {
   static constexpr bool kIsUpdate = false;
   dbn_act_epilogue e;
   bool scatter_host() const { return false; }
+  void scatter_order(UmmaGemmParams&) const {}
   __device__ __forceinline__ void apply(uint32_t epoch, int m, int n0, const float acc[32], int M, int N, int, int) const {
     act_epilogue_row<32, true>(e, epoch, m, n0, acc, M, N);
   }
@@ -951,6 +954,18 @@ struct UmmaUpdEpi {
   static constexpr bool kIsUpdate = true;
   dbn_update_epilogue e;
   bool scatter_host() const { return e.raw_peers[0] != nullptr; }
+  // Tile order of a scattered dW (CTA-pair kernel, 256-row blocks).  The accumulator tiles leave over NVLink in
+  // bursts, one per wave of tiles, and the last burst is exposed after the last MMA.  Visiting the owners' row blocks
+  // in the order rank+1, rank+2, ..., rank makes (a) every rank send to a different owner at any time (no incast)
+  // and (b) the final wave consist of the rows this rank owns itself -- local stores, nothing left on the wire.
+  void scatter_order(UmmaGemmParams& p) const {
+    if (e.raw_peers[0] == nullptr || e.rows_per_peer <= 0 || (e.rows_per_peer % 256) != 0) return;
+    const int per_owner = e.rows_per_peer / 256;
+    if (p.tiles_m % per_owner != 0) return;
+    const int owners = p.tiles_m / per_owner;
+    p.group_m = per_owner;
+    p.mb_rot = ((e.raw_slot + 1) % owners) * per_owner;
+  }
   __device__ __forceinline__ void apply(uint32_t, int m, int n0, const float acc[32], int M, int N, int augM, int augN) const {
     upd_epilogue_row<32>(e, m, n0, acc, M, N, augM, augN);
   }
@@ -1202,12 +1217,25 @@ inline int umma_launch2(cudaStream_t st, UmmaGemmParams& p, const Epi& epi, int 
   p.tiles_m = ceil_div(p.M, 256);
   p.tiles_n = ceil_div(p.N, BN);
   p.group_m = std::max(1, std::min(p.tiles_m, 8));
+  p.mb_rot = 0;
+  epi.scatter_order(p);    // peer scatter: one super-tile per owner, visited in rotated order with the own rows last
   const int n_tiles = p.tiles_m * p.tiles_n;
   const int clusters = std::min(n_tiles, umma_num_sms() / 2);
   DBN_CUDA_OK(launch_pdl(umma_gemm2_kernel<BN, UG2_KS, Epi>, dim3(clusters * 2), dim3(UG_THREADS), SMEM, st, p, epi, coreM,
                          coreN, augM, augN));
   DBN_LAUNCH_CHECK();
   return DBN_OK;
+}
+
+// relative cost of a 256 x 128 CTA-pair tile against half a 256 x 256 one (more operand bytes per MAC out of L2)
+constexpr double UG2_BN128_COST = 1.50;   // measured on B200: 1040 vs 1600 TFLOP/s at 4096-wide layers (L2 operand traffic), so 256 x 128 never pays there
+inline int umma_2cta_bn_override() {   // DBN_B200_2CTA_BN=128|256 forces the CTA-pair tile width (experiments)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DBN_B200_2CTA_BN");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
 }
 
 inline bool umma_use_2cta() {
@@ -1270,8 +1298,19 @@ inline int umma_gemm_run(cudaStream_t st, int M, int N, int augM, int augN, cons
     }
   }
   if (sk_S) bn = sk_bn;
+  // CTA-pair tile width: 256 x 256 has the best operand reuse, but a grid of few tiles quantises badly over the
+  // 74 SM pairs (4096 x 4096: 256 tiles = 3.46 waves, the last one 46 % full); 256 x 128 tiles halve the tail.
+  int bn2 = 256;
+  if (two_cta) {
+    const int pairs = sms / 2;
+    const long t256 = (long)ceil_div(p.M, 256) * ceil_div(p.N, 256), t128 = (long)ceil_div(p.M, 256) * ceil_div(p.N, 128);
+    const double c256 = (double)((t256 + pairs - 1) / pairs), c128 = 0.5 * UG2_BN128_COST * (double)((t128 + pairs - 1) / pairs);
+    if (c128 < c256) bn2 = 128;
+    const int forced = umma_2cta_bn_override();
+    if (forced == 128 || forced == 256) bn2 = forced;
+  }
   const int ks = two_cta ? UG2_KS : sk_S ? SK_KS : umma_ks(bm, bn);
-  const int b_rows = two_cta ? 128 : bn;        // B rows (K-major) / columns (MN-major) staged per CTA
+  const int b_rows = two_cta ? bn2 / 2 : bn;    // B rows (K-major) / columns (MN-major) staged per CTA
   for (int i = 0; i < n_ops; ++i) {
     const dbn_operands& o = ops[i];
     p.K[i] = o.K;
@@ -1291,6 +1330,7 @@ inline int umma_gemm_run(cudaStream_t st, int M, int N, int augM, int augN, cons
     if (bn == 128) return umma_launch_sk<128, Epi>(st, p, epi, M, N, augM, augN);
     return umma_launch_sk<64, Epi>(st, p, epi, M, N, augM, augN);
   }
+  if (two_cta && bn2 == 128) return umma_launch2<128, Epi>(st, p, epi, M, N, augM, augN);
   if (two_cta) return umma_launch2<256, Epi>(st, p, epi, M, N, augM, augN);
   if (bn == 256) return umma_launch<256, Epi>(st, p, epi, M, N, augM, augN);
   if (bn == 128) return umma_launch<128, Epi>(st, p, epi, M, N, augM, augN);

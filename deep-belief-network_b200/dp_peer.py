@@ -296,6 +296,26 @@ class DpPeerRunner:
         self.step_compute(s)
         self.step_apply()
 
+    def step_traced(self, s, ev):
+        """One step with a CUDA event after every phase (debug: tools/dp_trace.py); ev = list of 7 timing events."""
+        lib, a = self.lib, self.args
+        st = torch.cuda.current_stream()
+        ev[0].record(st)
+        if self.value > 0:
+            L.check(lib.dbn_dp_wait(E.stream_ptr(), C.byref(self.x), 1, self.value))
+        ev[1].record(st)
+        self.value += 1
+        a.row0 = s * self.bl
+        a.rng.row0 = E.dp_global_row0(s, self.bs, self.rank, self.bl)
+        L.check(lib.dbn_rbm_cd_step(E.stream_ptr(), C.byref(a)))
+        ev[2].record(st)
+        L.check(lib.dbn_rbm_delta_scatter(E.stream_ptr(), C.byref(a), C.byref(self.x)))
+        ev[3].record(st)
+        L.check(lib.dbn_dp_signal(E.stream_ptr(), C.byref(self.x), self.stats, self.value))
+        ev[4].record(st)
+        self.step_apply()
+        ev[5].record(st)
+
     def drain(self):
         if self.value > 0:
             L.check(self.lib.dbn_dp_wait(E.stream_ptr(), C.byref(self.x), 1, self.value))
