@@ -563,6 +563,178 @@ class RbmEpochRunner:
         self.epochs_run += 1
 
 
+def resident_budget_bytes(device):
+    """How many bytes of dataset (fp32 rows + their staged 16-bit epoch copy) a fit may keep in HBM: the
+    DBN_B200_RESIDENT_BYTES override, else 60 % of the memory currently free on the device."""
+    env = os.environ.get("DBN_B200_RESIDENT_BYTES")
+    if env:
+        return int(float(env))
+    free, _total = torch.cuda.mem_get_info(device)
+    return int(0.6 * free)
+
+
+def parallel_take(X, rows, out):
+    """out[i] = X[rows[i]] on a few host threads (the reference's `data = _data[idx]`, dbn/models.py:106-107 and
+    dbn/utils.py:12-13, for one chunk of the epoch; NumPy releases the GIL inside take)."""
+    global _CAST_POOL
+    m = len(rows)
+    if m * X.shape[1] < (1 << 18):
+        np.take(X, rows, axis=0, out=out[:m], mode="clip")
+        return
+    if _CAST_POOL is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _CAST_POOL = ThreadPoolExecutor(max_workers=8)
+    parts = 8
+    step = (m + parts - 1) // parts
+
+    def job(i):
+        a, b = i * step, min(m, (i + 1) * step)
+        if a < b:
+            np.take(X, rows[a:b], axis=0, out=out[a:b], mode="clip")
+    list(_CAST_POOL.map(job, range(parts)))
+
+
+class HostRbmEpochRunner:
+    """Epoch-at-a-time training of one RBM layer on a dataset that STAYS ON THE HOST (it does not fit in HBM, or the
+    caller caps the resident bytes): the staging pipeline behind SURVEY 8f-4.  Per epoch the host permutation (the
+    reference's double shuffle, dbn/models.py:106-107 + dbn/utils.py:12-13) is applied chunk by chunk:
+
+        host threads   gather chunk c+1 of the shuffled epoch into a pinned buffer        (parallel_take)
+        upload stream  H2D of chunk c+1 into one of two device buffers
+        compute stream stage chunk c (cast + ones column), then its mini-batch CD steps   (dbn_rbm_fit_epoch)
+
+    so the kernels consume chunk c while chunk c+1 lands.  Chunks are whole numbers of mini-batches and the Philox
+    counters carry the GLOBAL epoch row, so the trained parameters are bit-identical to the resident path's."""
+
+    def __init__(self, layer, X_host, batch_size, k, lr, seed, chunk_rows=None):
+        self.layer = layer
+        self.X = X_host
+        self.n, self.V = int(X_host.shape[0]), int(X_host.shape[1])
+        self.bs, self.k = int(batch_size), int(k)
+        dev = layer.device
+        if chunk_rows is None:   # ~64 MB of fp32 rows per chunk, at least 4 mini-batches
+            chunk_rows = max(4 * self.bs, (64 << 20) // (4 * self.V))
+        env = os.environ.get("DBN_B200_CHUNK_ROWS")
+        if env:
+            chunk_rows = int(env)
+        self.R = max(self.bs, chunk_rows // self.bs * self.bs)
+        self.R = min(self.R, (self.n + self.bs - 1) // self.bs * self.bs)
+        self.pinned, self.ev_up, self.ev_done = [], [], []
+        for _ in range(2):
+            buf, _ev = _PinnedPool.take(self.R * self.V * 4)
+            self.pinned.append(buf)
+            self.ev_up.append(torch.cuda.Event())
+            self.ev_done.append(torch.cuda.Event())
+        self.host = [b[:self.R * self.V * 4].view(torch.float32).view(self.R, self.V) for b in self.pinned]
+        self.dev32 = [torch.empty(self.R, self.V, dtype=torch.float32, device=dev) for _ in range(2)]
+        self.Xp = [layer.alloc_staged(self.R, self.V) for _ in range(2)]
+        self.ws = layer.make_workspace(min(self.bs, self.n))
+        self.epoch_ctr = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.args = [layer._step_args(xp, k, lr / batch_size, self.ws, seed, self.epoch_ctr) for xp in self.Xp]
+        self.used = [False, False]
+        self.launches_per_epoch = 0
+
+    def __del__(self):
+        try:
+            for b in self.pinned:
+                _PinnedPool.give(b, None)
+        except Exception:
+            pass
+
+    def _chunks(self, order, visit):
+        """Software pipeline over the chunks of one pass: visit(slot, s0, m) is enqueued once chunk rows [s0, s0+m)
+        of `order` are on the device in dev32[slot]."""
+        up = _upload_stream(self.layer.device)
+        cur = torch.cuda.current_stream()
+        for c, s0 in enumerate(range(0, self.n, self.R)):
+            m = min(self.R, self.n - s0)
+            slot = c & 1
+            if self.used[slot]:
+                self.ev_up[slot].synchronize()       # the H2D that last read this pinned buffer
+            rows = order[s0:s0 + m] if order is not None else None
+            if rows is None:
+                self.host[slot].numpy()[:m] = self.X[s0:s0 + m]
+            else:
+                parallel_take(self.X, rows, self.host[slot].numpy())
+            with torch.cuda.stream(up):
+                if self.used[slot]:
+                    up.wait_event(self.ev_done[slot])   # the kernels that last read this device buffer
+                self.dev32[slot][:m].copy_(self.host[slot][:m], non_blocking=True)
+                self.ev_up[slot].record(up)
+            cur.wait_event(self.ev_up[slot])
+            visit(slot, s0, m)
+            self.ev_done[slot].record(cur)
+            self.used[slot] = True
+
+    def run(self, order=None):
+        """One epoch (dbn/models.py:105-119)."""
+        layer, lib = self.layer, self.layer.lib
+        if order is None:
+            order = epoch_order(self.n)
+        order = np.asarray(order)
+        before = lib.dbn_launch_count()
+
+        def visit(slot, s0, m):
+            layer.stage(self.dev32[slot][:m], out=self.Xp[slot][:m])
+            a = self.args[slot]
+            a.row0 = 0
+            a.rng.row0 = s0                           # global epoch row of the chunk's first row
+            L.check(lib.dbn_rbm_fit_epoch(stream_ptr(), C.byref(a), m, self.bs))
+        self._chunks(order, visit)
+        self.epoch_ctr.add_(1)
+        self.launches_per_epoch = int(lib.dbn_launch_count() - before)
+
+    def reconstruction_error(self):
+        """_compute_reconstruction_error (dbn/models.py:212-220) over the host dataset, chunk by chunk."""
+        layer = self.layer
+        acc = torch.zeros(1, dtype=torch.float32, device=layer.device)
+        tc = layer.prec in TC_PRECS
+        hdt, hld = OP_DTYPE[layer.prec], (bf16_pitch(layer.H) if tc else layer.H)
+
+        def visit(slot, s0, m):
+            xs = self.dev32[slot][:m]
+            xop = layer.stage(xs, out=self.Xp[slot][:m]) if tc else xs
+            hm = torch.zeros(m, hld, dtype=hdt, device=layer.device)
+            layer.hidden_means(xop, 0, m, hm)
+            rec = torch.empty(m, layer.V, dtype=torch.float32, device=layer.device)
+            layer.visible_means(hm, m, rec)
+            L.check(layer.lib.dbn_sum_sq_diff(stream_ptr(), mat(rec), mat(xs), 0, m, layer.V, 1.0 / self.n, ptr(acc)))
+        self._chunks(None, visit)
+        return float(acc.item())
+
+    def transform_to_host(self):
+        """transform (dbn/models.py:77-86) of the whole host dataset into a new host array [n, H] float32: the next
+        layer of a stack trains on it, again from the host."""
+        layer = self.layer
+        out = np.empty((self.n, layer.H), dtype=np.float32)
+        tc = layer.prec in TC_PRECS
+        pending = []
+
+        def visit(slot, s0, m):
+            xs = self.dev32[slot][:m]
+            xop = layer.stage(xs, out=self.Xp[slot][:m]) if tc else xs
+            hm = torch.empty(m, layer.H, dtype=torch.float32, device=layer.device)
+            layer.hidden_means(xop, 0, m, hm)
+            buf, ev = _PinnedPool.take(m * layer.H * 4)
+            stage = buf[:m * layer.H * 4].view(torch.float32).view(m, layer.H)
+            stage.copy_(hm, non_blocking=True)
+            ev.record()
+            pending.append((s0, m, stage, buf, ev))
+            while len(pending) > 2:
+                self._drain_one(pending, out)
+        self._chunks(None, visit)
+        while pending:
+            self._drain_one(pending, out)
+        return out
+
+    @staticmethod
+    def _drain_one(pending, out):
+        s0, m, stage, buf, ev = pending.pop(0)
+        ev.synchronize()
+        out[s0:s0 + m] = stage.numpy()
+        _PinnedPool.give(buf, ev)
+
+
 class DpRbmEpochRunner:
     """Data-parallel epoch of one RBM layer (BASELINE.json config 5).
 

@@ -47,6 +47,13 @@ def _to_device_f32(X):
     return t.to(_device())
 
 
+def _resident(n, v, h):
+    """Does a dataset of n rows fit the device for a layer v -> h: fp32 rows, their 16-bit epoch copy, and the fp32
+    features handed to the next layer (engine.resident_budget_bytes; DBN_B200_RESIDENT_BYTES overrides)."""
+    need = n * v * 4 + n * E.bf16_pitch(v) * 2 + n * h * 4
+    return need <= E.resident_budget_bytes(_device())
+
+
 def _draw_seed():
     """Philox key drawn from the global np.random stream, so `np.random.seed(...)` stays the
     user-facing reproducibility knob (reference: example_classification.py:3)."""
@@ -274,11 +281,37 @@ class BinaryRBM(BaseEstimator, TransformerMixin, BaseModel):
         self._adopt(layer)
         return layer
 
+    def _fit_host(self, X, draws=None):
+        """Train on a dataset that stays on the HOST (engine.HostRbmEpochRunner: permuted chunks are gathered into
+        pinned memory and uploaded while the previous chunk trains).  Same draws, same Philox counters as the resident
+        path, hence bit-identical parameters.  Returns (DeviceRbm, runner)."""
+        if self.rng != 'philox':
+            raise ValueError("rng='numpy' (replay of the reference's uniform stream) needs the dataset resident on the device.")
+        X = np.ascontiguousarray(np.asarray(X), dtype=np.float32)
+        self._init_params(int(X.shape[1]), draws.get() if draws is not None else None)
+        if self.optimization_algorithm != 'sgd':
+            raise ValueError("Invalid optimization algorithm.")
+        layer = self._device_layer()
+        seed = draws.get() if draws is not None else _draw_seed()
+        runner = E.HostRbmEpochRunner(layer, X, self.batch_size, self.contrastive_divergence_iter, self.learning_rate, seed)
+        import torch
+        for epoch in range(1, self.n_epochs + 1):
+            runner.run(draws.get() if draws is not None else None)
+            if self.verbose:
+                print(">> Epoch %d finished \tRBM Reconstruction error %f" % (epoch, runner.reconstruction_error()))
+        torch.cuda.current_stream().synchronize()
+        self._adopt(layer)
+        return layer, runner
+
     def fit(self, X):
         """Fit the RBM to X (n_samples, n_features).  Returns self (dbn/models.py:49-75)."""
         dp = E.dp_context()
         if dp is not None:
             self._fit_data_parallel(X, dp)
+            return self
+        shape = np.shape(X)
+        if len(shape) == 2 and shape[0] > 0 and self.rng == 'philox' and not _resident(shape[0], shape[1], self.n_hidden_units):
+            self._fit_host(X)       # out of core: the dataset is streamed from the host every epoch
             return self
         draws = None
         if self.rng == 'philox' and os.environ.get("DBN_B200_DRAW_AHEAD", "1") != "0":
@@ -377,8 +410,36 @@ class UnsupervisedDBN(BaseEstimator, TransformerMixin, BaseModel):
                 yield E.epoch_order(n)
             v = rbm.n_hidden_units
 
+    def _fit_host(self, X):
+        """Greedy pre-training with every layer's input on the host (out of core): layer l trains from host chunks,
+        its features are computed chunk-wise back into host memory and become layer l+1's dataset."""
+        self.rbm_layers = [
+            self.rbm_class(n_hidden_units=h, activation_function=self.activation_function,
+                           optimization_algorithm=self.optimization_algorithm, learning_rate=self.learning_rate_rbm,
+                           n_epochs=self.n_epochs_rbm, contrastive_divergence_iter=self.contrastive_divergence_iter,
+                           batch_size=self.batch_size, verbose=self.verbose, precision=self.precision, rng=self.rng)
+            for h in self.hidden_layers_structure]
+        if self.verbose:
+            print("[START] Pre-training step:")
+        data = np.ascontiguousarray(np.asarray(X), dtype=np.float32)
+        for i, rbm in enumerate(self.rbm_layers):
+            _layer, runner = rbm._fit_host(data)
+            if i + 1 < len(self.rbm_layers):
+                data = runner.transform_to_host()
+        if self.verbose:
+            print("[END] Pre-training step")
+        return self
+
+    def _out_of_core(self, shape):
+        if len(shape) != 2 or shape[0] == 0 or self.rng != 'philox' or self.rbm_class is not BinaryRBM:
+            return False
+        widths = [shape[1]] + list(self.hidden_layers_structure)
+        return not all(_resident(shape[0], v, h) for v, h in zip(widths[:-1], widths[1:]))
+
     def fit(self, X, y=None):
         """Pre-train every layer on the previous layer's features (dbn/models.py:248-276)."""
+        if self._out_of_core(np.shape(X)):
+            return self._fit_host(X)
         return self._fit_device(_to_device_f32(X))
 
     def _transform_device(self, Xd):
@@ -428,7 +489,10 @@ class AbstractSupervisedDBN(BaseEstimator, BaseModel):
 
     # ---- public API (dbn/models.py:327-362) ----
     def fit(self, X, y=None, pre_train=True):
-        Xd = _to_device_f32(X)
+        if pre_train and self.unsupervised_dbn._out_of_core(np.shape(X)):
+            self.unsupervised_dbn._fit_host(X)      # pre-training streams the dataset from the host
+            pre_train = False
+        Xd = _to_device_f32(X)                       # the fine-tune keeps its inputs resident
         if pre_train:
             self.unsupervised_dbn._fit_device(Xd)
         self._fine_tuning(Xd, y)   # labels as given: the label map's keys are the caller's elements (dbn/models.py:575-584)

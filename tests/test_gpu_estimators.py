@@ -345,3 +345,38 @@ def test_converted_reference_model_predicts_on_the_gpu(tmp_path):
         assert "_dev_cache" not in g2.__dict__ and np.array_equal(g2.predict_proba(X), g.predict_proba(X))
     finally:
         sys.path.remove(ref_root)
+
+
+@pytest.mark.parametrize("precision,V,hs,bs", [("fp16", 256, [128, 192], 64), ("fp32", 40, [24], 16)])
+def test_out_of_core_fit_equals_the_resident_fit(precision, V, hs, bs, monkeypatch):
+    """a dataset forced out of core (resident budget of one byte, chunks of 3 mini-batches, ragged last
+    chunk and last batch) is streamed from the host -- permuted chunks gathered into pinned memory, uploaded while the
+    previous chunk trains -- and must give BIT-IDENTICAL parameters to the resident path in Philox mode: same draws,
+    same global-row counters, same kernels.  Covers the stacked case (features of layer 1 go back to the host)."""
+    rng = np.random.default_rng(3)
+    N = 13 * bs + 5
+    X = (rng.random((N, V)) < 0.3).astype(np.float32)
+    monkeypatch.setenv("DBN_B200_PERSISTENT", "0")        # the on-chip fp32 kernel sums in another order
+    kw = dict(hidden_layers_structure=hs, learning_rate_rbm=0.05, n_epochs_rbm=3, batch_size=bs, verbose=False,
+              precision=precision)
+    monkeypatch.setenv("DBN_B200_DRAW_AHEAD", "0")
+    np.random.seed(9)
+    res = UnsupervisedDBN(**kw).fit(X)
+    monkeypatch.setenv("DBN_B200_RESIDENT_BYTES", "1")
+    monkeypatch.setenv("DBN_B200_CHUNK_ROWS", str(3 * bs))
+    np.random.seed(9)
+    ooc = UnsupervisedDBN(**kw).fit(X)
+    for a, b in zip(res.rbm_layers, ooc.rbm_layers):
+        assert np.array_equal(a.W, b.W) and np.array_equal(a.b, b.b) and np.array_equal(a.c, b.c)
+    # a single layer through BinaryRBM.fit, with the verbose metric computed chunk-wise
+    monkeypatch.delenv("DBN_B200_RESIDENT_BYTES")
+    np.random.seed(4)
+    r1 = BinaryRBM(n_hidden_units=hs[0], learning_rate=0.05, n_epochs=2, batch_size=bs, verbose=False, precision=precision).fit(X)
+    e1 = r1._compute_reconstruction_error(X)
+    monkeypatch.setenv("DBN_B200_RESIDENT_BYTES", "1")
+    np.random.seed(4)
+    m = BinaryRBM(n_hidden_units=hs[0], learning_rate=0.05, n_epochs=2, batch_size=bs, verbose=False, precision=precision)
+    _layer, runner = m._fit_host(X)
+    assert np.array_equal(m.W, r1.W) and np.array_equal(m.c, r1.c)
+    assert abs(runner.reconstruction_error() - e1) < 1e-4 * max(1.0, e1)
+    assert np.allclose(runner.transform_to_host(), r1.transform(X), atol=1e-6)
