@@ -88,7 +88,7 @@ class MlpStepArgs(C.Structure):
                 ("rng", Rng), ("masks", Mat * (MAX_LAYERS + 1)), ("workspace", C.c_void_p),
                 ("workspace_bytes", C.c_size_t), ("ws_rows", C.c_int32), ("_pad4", C.c_int32),
                 ("loss_rows", C.c_void_p), ("out", Mat),
-                ("raw_grads", Mat * (MAX_LAYERS + 1))]
+                ("raw_grads", Mat * (MAX_LAYERS + 1)), ("aux_stream", C.c_void_p)]
 
 
 # every symbol include/dbn_b200.h declares: name -> (restype, argtypes)

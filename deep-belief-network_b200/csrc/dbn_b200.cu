@@ -142,6 +142,27 @@ size_t mlp_ws_layout(int precision, int Bmax, int n_in, const int32_t* dims, int
   return off;
 }
 
+// Fork / join between the two streams of a fine-tune step.  Events are created once (per process, timing disabled)
+// and reused round-robin; a record followed by a wait is legal inside a stream capture, where it becomes a graph edge.
+cudaEvent_t next_event() {
+  static cudaEvent_t ring[64];
+  static std::atomic<unsigned> n{0};
+  static std::atomic<uint64_t> made{0};
+  const unsigned i = n.fetch_add(1) % 64;
+  if (!((made.load() >> i) & 1)) {
+    cudaEventCreateWithFlags(&ring[i], cudaEventDisableTiming);
+    made.fetch_or(uint64_t(1) << i);
+  }
+  return ring[i];
+}
+// `to` waits for everything issued so far on `from`
+int stream_edge(cudaStream_t from, cudaStream_t to) {
+  cudaEvent_t e = next_event();
+  DBN_CUDA_OK(cudaEventRecord(e, from));
+  DBN_CUDA_OK(cudaStreamWaitEvent(to, e, 0));
+  return DBN_OK;
+}
+
 int copy2d(cudaStream_t st, const dbn_mat& dst, const dbn_mat& src, int rows, int cols) {
   if (dst.dtype == src.dtype) {
     DBN_CUDA_OK(cudaMemcpy2DAsync(dst.ptr, (size_t)dst.ld * elt_size(dst.dtype), src.ptr,
@@ -639,12 +660,15 @@ int dbn_mlp_train_step(void* stream, const dbn_mlp_step_args* a) {
   }
   const int HL = a->dims[L - 1];
   const dbn_mat WoM = make_mat(a->Wo, a->ldwo, DBN_F32);
+  bool head_did_delta = false;
   if (a->n_out <= 32) {  // fused head: scores + softmax/identity + delta + loss in one launch
-    DBN_CUDA_OK(launch_pdl(head_fused_kernel, dim3(ceil_div(B * 32, 256)), dim3(256), 0, st, ws.act[L - 1], HL,
+    // ... and, in the same launch, the delta of the last hidden layer (dbn/models.py:495-499)
+    DBN_CUDA_OK(launch_pdl(head_fused_kernel, dim3(ceil_div(B, 2)), dim3(256), 0, st, ws.act[L - 1], HL,
                            (const float*)a->Wo, a->ldwo, (const float*)a->bo, B, a->n_out, a->head,
                            a->Y + (size_t)a->row0 * a->ldy, a->ldy, static_cast<float*>(ws.Z.ptr), ws.Z.ld,
-                           static_cast<float*>(ws.dO.ptr), ws.dO.ld, ws.dOb, a->loss_rows));
+                           static_cast<float*>(ws.dO.ptr), ws.dO.ld, ws.dOb, a->loss_rows, ws.delta[L - 1], prime));
     DBN_LAUNCH_CHECK();
+    head_did_delta = true;
   } else {
     // head scores (dbn/models.py:601 / :703), strict FP32
     dbn_operands o = make_ops(ws.act[L - 1], 0, 0, WoM, 0, 0, HL);
@@ -656,51 +680,66 @@ int dbn_mlp_train_step(void* stream, const dbn_mlp_step_args* a) {
   }
   if (a->out.ptr) DBN_TRY(copy2d(st, a->out, ws.Z, B, a->n_out));
 
-  // ---- backward deltas (dbn/models.py:489-501), all with the pre-update weights ----
-  {
-    dbn_operands o = make_ops(ws.dO, 0, 0, WoM, 1, 0, a->n_out);
-    dbn_act_epilogue e = blank_act();
-    e.act = DBN_ACT_IDENTITY; e.mul = prime; e.aux = ws.act[L - 1]; e.out = ws.delta[L - 1];
-    DBN_TRY(simt_gemm_act(st, B, HL, &o, 1, e));
-  }
-  for (int l = L - 2; l >= 0; --l) {
-    dbn_operands o = make_ops(ws.delta[l + 1], 0, 0, Wop(l + 1), 1, 0, a->dims[l + 1]);
-    dbn_act_epilogue e = blank_act();
-    e.act = DBN_ACT_IDENTITY; e.mul = prime; e.aux = ws.act[l]; e.out = ws.delta[l];
-    DBN_TRY(dbn_gemm_act(stream, a->precision, B, a->dims[l], &o, 1, &e));
-  }
-
-  // ---- gradients + decayed SGD update (dbn/models.py:508-513, :454-465) ----
-  if (tc && a->n_out <= 32) {
-    // narrow head in BF16 mode: the same tcgen05 contraction as the hidden layers (M = n_out rows of a
-    // 128-row tile), operands = bf16 copy of the head delta and the last activations with their ones column
-    dbn_operands o = make_ops(ws.dOb, 1, 0, ws.act[L - 1], 1, 0, B);
-    dbn_update_epilogue u = blank_upd();
-    u.W = a->Wo; u.ldw = a->ldwo; u.vecM = a->bo; u.decay = a->decay; u.scale = -a->lr_over_bs;
-    if (raw) u.raw = a->raw_grads[L];
-    DBN_TRY(dbn_gemm_update(stream, a->precision, a->n_out, HL, 0, 1, &o, 1, &u));
-  } else if (a->n_out <= 32 && (size_t)B * a->n_out * sizeof(float) <= 48 * 1024) {   // narrow head, FP32 mode
-    float* rawp = raw ? static_cast<float*>(a->raw_grads[L].ptr) : nullptr;
-    DBN_CUDA_OK(launch_pdl(head_grad_kernel, dim3(ceil_div(HL + 1, 128)), dim3(128), (size_t)B * a->n_out * sizeof(float), st,
-                           ws.act[L - 1], HL, (const float*)ws.dO.ptr, ws.dO.ld, B, a->n_out, a->Wo, a->ldwo, a->bo, a->decay,
-                           -a->lr_over_bs, rawp, raw ? a->raw_grads[L].ld : 0));
-    DBN_LAUNCH_CHECK();
-  } else {
+  // ---- backward deltas (dbn/models.py:489-501) and gradients + decayed SGD update (:508-513, :454-465) ----
+  // delta_l needs W_{l+1} as it was in the forward pass; the update of W_{l+1} needs delta_{l+1} and a_l.  So
+  //     delta_{L-1};  then for l = L-1 .. 1:   { delta_{l-1} (reads W_l) }  ||  { update of the layer above };  update W_0
+  // i.e. the update of layer l+1 may run NEXT TO the delta contraction of layer l-1... precisely: update(head) after
+  // delta_{L-1}; update(W_l) after delta_{l-1}.  With an auxiliary stream the updates go there (a second branch of the
+  // captured graph): the critical path is forward + deltas + the last update instead of forward + deltas + all updates.
+  cudaStream_t aux = a->aux_stream ? as_stream(a->aux_stream) : st;
+  void* auxp = a->aux_stream ? a->aux_stream : stream;
+  auto update_head = [&]() -> int {
+    if (tc && a->n_out <= 32) {
+      // narrow head in a tensor-core mode: the same tcgen05 contraction as the hidden layers (M = n_out rows of a
+      // 128-row tile), operands = 16-bit copy of the head delta and the last activations with their ones column
+      dbn_operands o = make_ops(ws.dOb, 1, 0, ws.act[L - 1], 1, 0, B);
+      dbn_update_epilogue u = blank_upd();
+      u.W = a->Wo; u.ldw = a->ldwo; u.vecM = a->bo; u.decay = a->decay; u.scale = -a->lr_over_bs;
+      if (raw) u.raw = a->raw_grads[L];
+      return dbn_gemm_update(auxp, a->precision, a->n_out, HL, 0, 1, &o, 1, &u);
+    }
+    if (a->n_out <= 32 && (size_t)B * a->n_out * sizeof(float) <= 48 * 1024) {   // narrow head, FP32 mode
+      float* rawp = raw ? static_cast<float*>(a->raw_grads[L].ptr) : nullptr;
+      DBN_CUDA_OK(launch_pdl(head_grad_kernel, dim3(ceil_div(HL + 1, 128)), dim3(128), (size_t)B * a->n_out * sizeof(float), aux,
+                             ws.act[L - 1], HL, (const float*)ws.dO.ptr, ws.dO.ld, B, a->n_out, a->Wo, a->ldwo, a->bo, a->decay,
+                             -a->lr_over_bs, rawp, raw ? a->raw_grads[L].ld : 0));
+      DBN_LAUNCH_CHECK();
+      return DBN_OK;
+    }
     dbn_operands o = make_ops(ws.dO, 1, 0, ws.act[L - 1], 1, 0, B);
     dbn_update_epilogue u = blank_upd();
     u.W = a->Wo; u.ldw = a->ldwo; u.vecM = a->bo; u.decay = a->decay; u.scale = -a->lr_over_bs;
     if (raw) u.raw = a->raw_grads[L];
-    DBN_TRY(simt_gemm_update(st, a->n_out, HL, 0, 1, &o, 1, u));
-  }
-  for (int l = L - 1; l >= 0; --l) {
+    return simt_gemm_update(aux, a->n_out, HL, 0, 1, &o, 1, u);
+  };
+  auto update_layer = [&](int l, void* on) -> int {
     const int K_in = l == 0 ? a->n_in : a->dims[l - 1];
     dbn_operands o = make_ops(ws.delta[l], 1, 0, l == 0 ? in0 : ws.act[l - 1], 1, l == 0 ? in0_row0 : 0, B);
     dbn_update_epilogue u = blank_upd();
     u.W = a->W[l]; u.ldw = a->ldw[l]; u.Wb = tc ? a->Wb[l] : null_mat();
     u.vecM = a->c[l]; u.decay = a->decay; u.scale = -a->lr_over_bs;
     if (raw) u.raw = a->raw_grads[l];
-    DBN_TRY(dbn_gemm_update(stream, a->precision, a->dims[l], K_in, 0, 1, &o, 1, &u));
+    return dbn_gemm_update(on, a->precision, a->dims[l], K_in, 0, 1, &o, 1, &u);
+  };
+  const bool forked = aux != st;
+  if (!head_did_delta) {  // delta_{L-1} = (delta_out W_o) * f'(a_{L-1})   (wide heads; narrow ones did it in the head kernel)
+    dbn_operands o = make_ops(ws.dO, 0, 0, WoM, 1, 0, a->n_out);
+    dbn_act_epilogue e = blank_act();
+    e.act = DBN_ACT_IDENTITY; e.mul = prime; e.aux = ws.act[L - 1]; e.out = ws.delta[L - 1];
+    DBN_TRY(simt_gemm_act(st, B, HL, &o, 1, e));
   }
+  if (forked) DBN_TRY(stream_edge(st, aux));   // the head update reads delta_out (done) and rewrites W_o (delta_{L-1} has read it)
+  DBN_TRY(update_head());
+  for (int l = L - 2; l >= 0; --l) {
+    dbn_operands o = make_ops(ws.delta[l + 1], 0, 0, Wop(l + 1), 1, 0, a->dims[l + 1]);
+    dbn_act_epilogue e = blank_act();
+    e.act = DBN_ACT_IDENTITY; e.mul = prime; e.aux = ws.act[l]; e.out = ws.delta[l];
+    DBN_TRY(dbn_gemm_act(stream, a->precision, B, a->dims[l], &o, 1, &e));
+    if (forked) DBN_TRY(stream_edge(st, aux));  // W_{l+1} has been read by delta_l: its update may start on the side
+    DBN_TRY(update_layer(l + 1, auxp));
+  }
+  DBN_TRY(update_layer(0, stream));             // the last update stays on the main stream (nothing left to overlap)
+  if (forked) DBN_TRY(stream_edge(aux, st));    // join: the next step's forward pass reads every updated layer
   return DBN_OK;
 }
 

@@ -153,21 +153,31 @@ __device__ __forceinline__ void head_load8(const dbn_mat& A, int row, int k, flo
   }
 }
 
+// Block = 8 warps = 2 sample rows x 4 quarters of K: a row's K = 2000 activations are four independent
+// 2-iteration loops instead of one 8-iteration chain, and a 256-row mini-batch fills 128 SMs instead of 32.
+// With `delta_last` set the kernel also back-propagates through the head,
+//     delta_{L-1}[row, h] = (sum_c delta_out[row, c] W_o[c, h]) * f'(a_{L-1}[row, h])      (dbn/models.py:495-499)
+// while W_o and the row's activations are still in L1: one launch less on the critical path of the fine-tune step.
 __global__ void __launch_bounds__(256) head_fused_kernel(dbn_mat A, int K, const float* __restrict__ Wo, int ldwo,
                                                          const float* __restrict__ bo, int B, int C, int head,
                                                          const float* __restrict__ Y, int ldy, float* out, int ldo,
-                                                         float* delta, int ldd, dbn_mat delta_b, float* loss_rows) {
+                                                         float* delta, int ldd, dbn_mat delta_b, float* loss_rows,
+                                                         dbn_mat delta_last, int prime) {
   if (threadIdx.x == 0) pdl_launch_dependents();
   pdl_wait();
-  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (row >= B) return;
+  __shared__ float partial[2][4][32];
+  __shared__ float dout[2][32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r_in = warp >> 2, part = warp & 3;
+  const int row = blockIdx.x * 2 + r_in;
+  const bool active = row < B;
   float acc[32];
 #pragma unroll
   for (int c = 0; c < 32; ++c) acc[c] = 0.0f;
   const bool vec = (K % 8 == 0) && (ldwo % 4 == 0) && (A.ld % 8 == 0) && ((reinterpret_cast<uintptr_t>(A.ptr) & 15) == 0) &&
                    ((reinterpret_cast<uintptr_t>(Wo) & 15) == 0);
-  if (vec) {
-    for (int k = lane * 8; k < K; k += 256) {
+  if (active && vec) {
+    for (int k = (part * 32 + lane) * 8; k < K; k += 1024) {
       float a[8];
       head_load8(A, row, k, a);
 #pragma unroll
@@ -182,52 +192,96 @@ __global__ void __launch_bounds__(256) head_fused_kernel(dbn_mat A, int K, const
         }
       }
     }
-  } else {
-    for (int k = lane; k < K; k += 32) {
+  } else if (active) {
+    for (int k = part * 32 + lane; k < K; k += 128) {
       const float a = mat_load(A, row, k);
 #pragma unroll
       for (int c = 0; c < 32; ++c)
         if (c < C) acc[c] = fmaf(a, __ldg(Wo + (size_t)c * ldwo + k), acc[c]);
     }
   }
-  float z = 0.0f;  // lane c ends up holding score c
+  float z = 0.0f;  // lane c ends up holding this quarter's share of score c
 #pragma unroll
   for (int c = 0; c < 32; ++c) {
     if (c < C) {   // warp-uniform
       float s = acc[c];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (lane == c) z = s + bo[c];
+      if (lane == c) z = s;
     }
   }
-  const bool valid = lane < C;
-  float o_val = z, loss = 0.0f;
-  const float y = (valid && Y != nullptr) ? Y[(size_t)row * ldy + lane] : 0.0f;
-  if (head == DBN_HEAD_SOFTMAX) {
-    float mx = valid ? z : -INFINITY;
+  partial[r_in][part][lane] = z;
+  __syncthreads();
+  if (part == 0) {
+    const bool valid = active && lane < C;
+    z = valid ? ((partial[r_in][0][lane] + partial[r_in][1][lane]) + (partial[r_in][2][lane] + partial[r_in][3][lane])) + bo[lane] : 0.0f;
+    float o_val = z, loss = 0.0f;
+    const float y = (valid && Y != nullptr) ? Y[(size_t)row * ldy + lane] : 0.0f;
+    if (head == DBN_HEAD_SOFTMAX) {
+      float mx = valid ? z : -INFINITY;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    const float e = valid ? expf(z - mx) : 0.0f;
-    float sum = e;
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      const float e = valid ? expf(z - mx) : 0.0f;
+      float sum = e;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    o_val = e / sum;
-    float py = o_val * y;
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      o_val = active ? e / sum : 0.0f;
+      float py = o_val * y;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) py += __shfl_xor_sync(0xffffffffu, py, o);
-    loss = -logf(py);
+      for (int o = 16; o > 0; o >>= 1) py += __shfl_xor_sync(0xffffffffu, py, o);
+      loss = active ? -logf(py) : 0.0f;
+    } else {
+      const float d = valid ? (z - y) : 0.0f;
+      loss = d * d;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) loss += __shfl_xor_sync(0xffffffffu, loss, o);
+    }
+    if (valid) {
+      out[(size_t)row * ldo + lane] = o_val;
+      if (delta != nullptr) delta[(size_t)row * ldd + lane] = o_val - y;
+      if (delta_b.ptr != nullptr) mat_store(delta_b, row, lane, o_val - y);   // tensor-core operand copy (bf16 / fp16)
+    }
+    dout[r_in][lane] = valid ? (o_val - y) : 0.0f;
+    if (active && loss_rows != nullptr && Y != nullptr && lane == 0) loss_rows[row] = loss;
+  }
+  __syncthreads();
+  if (delta_last.ptr == nullptr || !active) return;
+  // delta of the last hidden layer, this warp's quarter of the units
+  float d[32];
+#pragma unroll
+  for (int c = 0; c < 32; ++c) d[c] = (c < C) ? dout[r_in][c] : 0.0f;
+  if (vec && (delta_last.ld % 8) == 0 && (reinterpret_cast<uintptr_t>(delta_last.ptr) & 15) == 0) {
+    for (int k = (part * 32 + lane) * 8; k < K; k += 1024) {
+      float a[8], s[8];
+      head_load8(A, row, k, a);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s[j] = 0.0f;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        if (c < C) {
+          const float4* w = reinterpret_cast<const float4*>(Wo + (size_t)c * ldwo + k);
+          const float4 w0 = __ldg(w), w1 = __ldg(w + 1);
+          s[0] = fmaf(d[c], w0.x, s[0]); s[1] = fmaf(d[c], w0.y, s[1]); s[2] = fmaf(d[c], w0.z, s[2]); s[3] = fmaf(d[c], w0.w, s[3]);
+          s[4] = fmaf(d[c], w1.x, s[4]); s[5] = fmaf(d[c], w1.y, s[5]); s[6] = fmaf(d[c], w1.z, s[6]); s[7] = fmaf(d[c], w1.w, s[7]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        s[j] = (prime == DBN_MUL_PRIME_SIGMOID) ? s[j] * (a[j] * (1.0f - a[j])) : ((a[j] > 0.0f) ? s[j] : 0.0f);
+      mat_store4(delta_last, row, k, s, 4);
+      mat_store4(delta_last, row, k + 4, s + 4, 4);
+    }
   } else {
-    const float d = valid ? (z - y) : 0.0f;
-    loss = d * d;
+    for (int k = part * 32 + lane; k < K; k += 128) {
+      const float a = mat_load(A, row, k);
+      float s = 0.0f;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) loss += __shfl_xor_sync(0xffffffffu, loss, o);
+      for (int c = 0; c < 32; ++c)
+        if (c < C) s = fmaf(d[c], __ldg(Wo + (size_t)c * ldwo + k), s);
+      s = (prime == DBN_MUL_PRIME_SIGMOID) ? s * (a * (1.0f - a)) : ((a > 0.0f) ? s : 0.0f);
+      mat_store(delta_last, row, k, s);
+    }
   }
-  if (valid) {
-    out[(size_t)row * ldo + lane] = o_val;
-    if (delta != nullptr) delta[(size_t)row * ldd + lane] = o_val - y;
-    if (delta_b.ptr != nullptr) mat_store(delta_b, row, lane, o_val - y);   // tensor-core operand copy (bf16 / fp16)
-  }
-  if (loss_rows != nullptr && Y != nullptr && lane == 0) loss_rows[row] = loss;
 }
 
 // Gradient + decayed SGD update of a narrow head (C <= 32), dbn/models.py:508-513 with :462-465:

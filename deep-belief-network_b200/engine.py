@@ -1004,6 +1004,12 @@ class MlpIterRunner:
         decay = 1.0 - (lr * l2) / n
         self.args = mlp.step_args(self.Xp, self.Yp, lr / batch_size, decay, self.keep_p, self.ws, seed, self.iter_ctr,
                                   self.loss_rows, self.masks)
+        # second stream: the weight updates run next to the delta contractions below them (two branches of the
+        # captured graph) instead of after all of them
+        self.aux = None
+        if os.environ.get("DBN_B200_MLP_FORK", "1") != "0":
+            self.aux = torch.cuda.Stream(device=dev)
+            self.args.aux_stream = self.aux.cuda_stream
         self.graph = None
         self.launches_per_iter = 0
         self.iters_run = 0

@@ -396,6 +396,10 @@ typedef struct dbn_mlp_step_args {
   float* loss_rows;                 /* optional [B]: -log p[label] or sum_t (pred-y)^2 */
   dbn_mat out;                      /* optional fp32 [B, n_out] head outputs          */
   dbn_mat raw_grads[DBN_MAX_LAYERS + 1]; /* optional fp32 [(out_l), in_l + 1] raw gradient | bias column; if raw_grads[0].ptr set nothing is updated */
+  void* aux_stream;                 /* optional second cudaStream_t: the weight-gradient / update contraction of layer l+1
+                                       then runs NEXT TO the delta contraction of layer l instead of after it (they share
+                                       delta_{l+1} and nothing else; fork / join by events, also inside a stream capture, where
+                                       it becomes two branches of the graph).  NULL = one stream, strictly serial. */
 } dbn_mlp_step_args;
 
 size_t dbn_mlp_workspace_bytes(int precision, int Bmax, int n_in, const int32_t* dims, int n_layers,
