@@ -45,7 +45,8 @@ class Operands(C.Structure):
 
 
 class ColSum(C.Structure):
-    _fields_ = [("acc", C.c_void_p), ("sign", C.c_float), ("ref_row0", C.c_int32), ("ref", Mat)]
+    _fields_ = [("acc", C.c_void_p), ("sign", C.c_float), ("ref_row0", C.c_int32), ("ref", Mat), ("square", C.c_int32),
+                ("_pad", C.c_int32)]
 
 
 class ActEpilogue(C.Structure):
@@ -110,6 +111,8 @@ SYMBOLS = {
                                        C.c_void_p, C.c_int, _P(Mat)]),
     "dbn_rbm_visible_means": (C.c_int, [C.c_void_p, C.c_int, _P(Mat), C.c_int, C.c_int, C.c_int, _P(Mat),
                                         C.c_void_p, C.c_int, _P(Mat)]),
+    "dbn_rbm_reconstruction_sq": (C.c_int, [C.c_void_p, C.c_int, _P(Mat), C.c_int, C.c_int, C.c_int, _P(Mat), C.c_void_p,
+                                            C.c_int, _P(Mat), C.c_int, C.c_void_p]),
     "dbn_rbm_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "dbn_rbm_workspace_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "dbn_rbm_cd_step": (C.c_int, [C.c_void_p, _P(RbmStepArgs)]),

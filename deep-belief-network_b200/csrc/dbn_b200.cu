@@ -261,6 +261,17 @@ int dbn_rbm_visible_means(void* stream, int precision, const dbn_mat* Hm, int B,
   return dbn_gemm_act(stream, precision, B, V, &o, 1, &e);
 }
 
+int dbn_rbm_reconstruction_sq(void* stream, int precision, const dbn_mat* Hm, int B, int V, int H, const dbn_mat* W,
+                              const float* b, int act, const dbn_mat* X, int row0, unsigned long long* acc) {
+  DBN_REQUIRE(Hm && W && X && X->ptr && acc, "null argument");
+  dbn_operands o = make_ops(*Hm, 0, 0, *W, 1, 0, H);
+  dbn_act_epilogue e = blank_act();
+  e.bias = b; e.act = act;
+  e.colsum.acc = acc; e.colsum.sign = 1.0f; e.colsum.square = 1;
+  e.colsum.ref = *X; e.colsum.ref_row0 = row0;
+  return dbn_gemm_act(stream, precision, B, V, &o, 1, &e);
+}
+
 size_t dbn_rbm_workspace_bytes(int precision, int Bmax, int V, int H) {
   return rbm_ws_layout(precision, Bmax, V, H, nullptr, nullptr);
 }

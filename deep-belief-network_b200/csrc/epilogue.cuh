@@ -114,8 +114,10 @@ __device__ __forceinline__ void act_epilogue_quad(const dbn_act_epilogue& e, uin
     float r[4] = {0.f, 0.f, 0.f, 0.f};
     if (e.colsum.ref.ptr != nullptr) mat_load4(e.colsum.ref, e.colsum.ref_row0 + m, n4, r, nvalid);
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-      if (j < nvalid) stat_add(e.colsum.acc, n4 + j, e.colsum.sign * (e.colsum.ref.ptr != nullptr ? r[j] - a[j] : a[j]));
+    for (int j = 0; j < 4; ++j) {
+      const float x = e.colsum.ref.ptr != nullptr ? r[j] - a[j] : a[j];
+      if (j < nvalid) stat_add(e.colsum.acc, n4 + j, e.colsum.square ? x * x : e.colsum.sign * x);
+    }
   }
   if (e.rng.mode == DBN_RNG_SAMPLE && e.sample.ptr != nullptr) {
     float s[4];
@@ -355,7 +357,11 @@ __device__ __forceinline__ void act_epilogue_row(const dbn_act_epilogue& e, uint
         for (int j = 0; j < W; ++j) r[j] = mat_load(e.colsum.ref, e.colsum.ref_row0 + m, n0 + j);
       }
 #pragma unroll
-      for (int j = 0; j < W; ++j) a[j] = e.colsum.sign * (r[j] - a[j]);
+      for (int j = 0; j < W; ++j) a[j] = r[j] - a[j];
+    }
+    if (e.colsum.square) {
+#pragma unroll
+      for (int j = 0; j < W; ++j) a[j] *= a[j];
     } else {
 #pragma unroll
       for (int j = 0; j < W; ++j) a[j] *= e.colsum.sign;

@@ -379,10 +379,16 @@ class DeviceRbm:
             self.hidden_means(xop, 0, m, out[s:s + m])
         return out
 
+    def reconstruction_sq(self, Hop, n, Xd, row0, acc):
+        """acc[j] += sum_rows (x - v'(h))^2 in fixed point, taken in the epilogue that produces v' (no reconstruction
+        buffer, no reduction kernel)."""
+        L.check(self.lib.dbn_rbm_reconstruction_sq(stream_ptr(), self.prec, mat(Hop), n, self.V, self.H, self.w_operand(),
+                                                   ptr(self.b), self.act, mat(Xd), row0, ptr(acc)))
+
     def reconstruction_error(self, Xd):
         """mean_n sum_j (reconstruct(transform(x)) - x)^2 (dbn/models.py:212-220)."""
         n = int(Xd.shape[0])
-        acc = torch.zeros(1, dtype=torch.float32, device=self.device)
+        acc = torch.zeros(self.V, dtype=torch.int64, device=self.device)
         hdt = OP_DTYPE[self.prec]
         hld = bf16_pitch(self.H) if self.prec in TC_PRECS else self.H
         for s in range(0, n, _CHUNK):
@@ -391,10 +397,8 @@ class DeviceRbm:
             xop = self.stage(xs) if self.prec in TC_PRECS else xs
             hm = torch.zeros(m, hld, dtype=hdt, device=self.device)   # operand of the next contraction: finite padding
             self.hidden_means(xop, 0, m, hm)
-            rec = torch.empty(m, self.V, dtype=torch.float32, device=self.device)
-            self.visible_means(hm, m, rec)
-            L.check(self.lib.dbn_sum_sq_diff(stream_ptr(), mat(rec), mat(xs), 0, m, self.V, 1.0 / n, ptr(acc)))
-        return float(acc.item())
+            self.reconstruction_sq(hm, m, xs, 0, acc)
+        return float(acc.sum().item()) / 4294967296.0 / n
 
     # -- training -------------------------------------------------------------------------------------
     def _step_args(self, Xop, k, lr_over_bs, ws, seed, epoch_ctr, U=None):
@@ -594,6 +598,73 @@ def parallel_take(X, rows, out):
     list(_CAST_POOL.map(job, range(parts)))
 
 
+class HostChunkFeeder:
+    """Software pipeline that brings a HOST dataset (and optional row-aligned companions, e.g. the targets) to the
+    device chunk by chunk: host threads gather chunk c+1 of the given row order into pinned buffers, the upload stream
+    copies it into one of two device buffers, and the compute stream works on chunk c meanwhile."""
+
+    def __init__(self, arrays, chunk_rows, device):
+        self.arrays = [np.ascontiguousarray(a, dtype=np.float32) for a in arrays]
+        self.n = int(self.arrays[0].shape[0])
+        self.R = int(chunk_rows)
+        self.device = device
+        self.pinned, self.host, self.dev = [], [], []
+        for a in self.arrays:
+            w = int(a.shape[1])
+            bufs = [_PinnedPool.take(self.R * w * 4)[0] for _ in range(2)]
+            self.pinned.append(bufs)
+            self.host.append([b[:self.R * w * 4].view(torch.float32).view(self.R, w) for b in bufs])
+            self.dev.append([torch.empty(self.R, w, dtype=torch.float32, device=device) for _ in range(2)])
+        self.ev_up = [torch.cuda.Event() for _ in range(2)]
+        self.ev_done = [torch.cuda.Event() for _ in range(2)]
+        self.used = [False, False]
+
+    def __del__(self):
+        try:
+            for bufs in self.pinned:
+                for b in bufs:
+                    _PinnedPool.give(b, None)
+        except Exception:
+            pass
+
+    def iterate(self, order, visit):
+        """visit(slot, s0, m) is enqueued once rows order[s0:s0+m] (or s0..s0+m if order is None) of every array are
+        in dev[i][slot][:m]."""
+        up = _upload_stream(self.device)
+        cur = torch.cuda.current_stream()
+        for c, s0 in enumerate(range(0, self.n, self.R)):
+            m = min(self.R, self.n - s0)
+            slot = c & 1
+            if self.used[slot]:
+                self.ev_up[slot].synchronize()       # the H2D that last read these pinned buffers
+            for a, host in zip(self.arrays, self.host):
+                if order is None:
+                    host[slot].numpy()[:m] = a[s0:s0 + m]
+                else:
+                    parallel_take(a, order[s0:s0 + m], host[slot].numpy())
+            with torch.cuda.stream(up):
+                if self.used[slot]:
+                    up.wait_event(self.ev_done[slot])   # the kernels that last read these device buffers
+                for host, dev in zip(self.host, self.dev):
+                    dev[slot][:m].copy_(host[slot][:m], non_blocking=True)
+                self.ev_up[slot].record(up)
+            cur.wait_event(self.ev_up[slot])
+            visit(slot, s0, m)
+            self.ev_done[slot].record(cur)
+            self.used[slot] = True
+
+
+def host_chunk_rows(batch_size, n, row_bytes, chunk_rows=None):
+    """Rows per chunk of a host-streamed epoch: ~64 MB of fp32 rows, a whole number of mini-batches (at least 4)."""
+    if chunk_rows is None:
+        chunk_rows = max(4 * batch_size, (64 << 20) // max(1, row_bytes))
+    env = os.environ.get("DBN_B200_CHUNK_ROWS")
+    if env:
+        chunk_rows = int(env)
+    R = max(batch_size, chunk_rows // batch_size * batch_size)
+    return min(R, (n + batch_size - 1) // batch_size * batch_size)
+
+
 class HostRbmEpochRunner:
     """Epoch-at-a-time training of one RBM layer on a dataset that STAYS ON THE HOST (it does not fit in HBM, or the
     caller caps the resident bytes): the staging pipeline behind SURVEY 8f-4.  Per epoch the host permutation (the
@@ -608,63 +679,17 @@ class HostRbmEpochRunner:
 
     def __init__(self, layer, X_host, batch_size, k, lr, seed, chunk_rows=None):
         self.layer = layer
-        self.X = X_host
         self.n, self.V = int(X_host.shape[0]), int(X_host.shape[1])
         self.bs, self.k = int(batch_size), int(k)
         dev = layer.device
-        if chunk_rows is None:   # ~64 MB of fp32 rows per chunk, at least 4 mini-batches
-            chunk_rows = max(4 * self.bs, (64 << 20) // (4 * self.V))
-        env = os.environ.get("DBN_B200_CHUNK_ROWS")
-        if env:
-            chunk_rows = int(env)
-        self.R = max(self.bs, chunk_rows // self.bs * self.bs)
-        self.R = min(self.R, (self.n + self.bs - 1) // self.bs * self.bs)
-        self.pinned, self.ev_up, self.ev_done = [], [], []
-        for _ in range(2):
-            buf, _ev = _PinnedPool.take(self.R * self.V * 4)
-            self.pinned.append(buf)
-            self.ev_up.append(torch.cuda.Event())
-            self.ev_done.append(torch.cuda.Event())
-        self.host = [b[:self.R * self.V * 4].view(torch.float32).view(self.R, self.V) for b in self.pinned]
-        self.dev32 = [torch.empty(self.R, self.V, dtype=torch.float32, device=dev) for _ in range(2)]
+        self.R = host_chunk_rows(self.bs, self.n, 4 * self.V, chunk_rows)
+        self.feed = HostChunkFeeder([X_host], self.R, dev)
+        self.dev32 = self.feed.dev[0]
         self.Xp = [layer.alloc_staged(self.R, self.V) for _ in range(2)]
         self.ws = layer.make_workspace(min(self.bs, self.n))
         self.epoch_ctr = torch.zeros(1, dtype=torch.int32, device=dev)
         self.args = [layer._step_args(xp, k, lr / batch_size, self.ws, seed, self.epoch_ctr) for xp in self.Xp]
-        self.used = [False, False]
         self.launches_per_epoch = 0
-
-    def __del__(self):
-        try:
-            for b in self.pinned:
-                _PinnedPool.give(b, None)
-        except Exception:
-            pass
-
-    def _chunks(self, order, visit):
-        """Software pipeline over the chunks of one pass: visit(slot, s0, m) is enqueued once chunk rows [s0, s0+m)
-        of `order` are on the device in dev32[slot]."""
-        up = _upload_stream(self.layer.device)
-        cur = torch.cuda.current_stream()
-        for c, s0 in enumerate(range(0, self.n, self.R)):
-            m = min(self.R, self.n - s0)
-            slot = c & 1
-            if self.used[slot]:
-                self.ev_up[slot].synchronize()       # the H2D that last read this pinned buffer
-            rows = order[s0:s0 + m] if order is not None else None
-            if rows is None:
-                self.host[slot].numpy()[:m] = self.X[s0:s0 + m]
-            else:
-                parallel_take(self.X, rows, self.host[slot].numpy())
-            with torch.cuda.stream(up):
-                if self.used[slot]:
-                    up.wait_event(self.ev_done[slot])   # the kernels that last read this device buffer
-                self.dev32[slot][:m].copy_(self.host[slot][:m], non_blocking=True)
-                self.ev_up[slot].record(up)
-            cur.wait_event(self.ev_up[slot])
-            visit(slot, s0, m)
-            self.ev_done[slot].record(cur)
-            self.used[slot] = True
 
     def run(self, order=None):
         """One epoch (dbn/models.py:105-119)."""
@@ -680,14 +705,14 @@ class HostRbmEpochRunner:
             a.row0 = 0
             a.rng.row0 = s0                           # global epoch row of the chunk's first row
             L.check(lib.dbn_rbm_fit_epoch(stream_ptr(), C.byref(a), m, self.bs))
-        self._chunks(order, visit)
+        self.feed.iterate(order, visit)
         self.epoch_ctr.add_(1)
         self.launches_per_epoch = int(lib.dbn_launch_count() - before)
 
     def reconstruction_error(self):
         """_compute_reconstruction_error (dbn/models.py:212-220) over the host dataset, chunk by chunk."""
         layer = self.layer
-        acc = torch.zeros(1, dtype=torch.float32, device=layer.device)
+        acc = torch.zeros(layer.V, dtype=torch.int64, device=layer.device)
         tc = layer.prec in TC_PRECS
         hdt, hld = OP_DTYPE[layer.prec], (bf16_pitch(layer.H) if tc else layer.H)
 
@@ -696,11 +721,9 @@ class HostRbmEpochRunner:
             xop = layer.stage(xs, out=self.Xp[slot][:m]) if tc else xs
             hm = torch.zeros(m, hld, dtype=hdt, device=layer.device)
             layer.hidden_means(xop, 0, m, hm)
-            rec = torch.empty(m, layer.V, dtype=torch.float32, device=layer.device)
-            layer.visible_means(hm, m, rec)
-            L.check(layer.lib.dbn_sum_sq_diff(stream_ptr(), mat(rec), mat(xs), 0, m, layer.V, 1.0 / self.n, ptr(acc)))
-        self._chunks(None, visit)
-        return float(acc.item())
+            layer.reconstruction_sq(hm, m, xs, 0, acc)
+        self.feed.iterate(None, visit)
+        return float(acc.sum().item()) / 4294967296.0 / self.n
 
     def transform_to_host(self):
         """transform (dbn/models.py:77-86) of the whole host dataset into a new host array [n, H] float32: the next
@@ -722,7 +745,7 @@ class HostRbmEpochRunner:
             pending.append((s0, m, stage, buf, ev))
             while len(pending) > 2:
                 self._drain_one(pending, out)
-        self._chunks(None, visit)
+        self.feed.iterate(None, visit)
         while pending:
             self._drain_one(pending, out)
         return out
@@ -733,6 +756,47 @@ class HostRbmEpochRunner:
         ev.synchronize()
         out[s0:s0 + m] = stage.numpy()
         _PinnedPool.give(buf, ev)
+
+
+class HostMlpIterRunner:
+    """The supervised fine-tune (dbn/models.py:434-465) on inputs and targets that stay on the HOST: the same chunk
+    pipeline as HostRbmEpochRunner, with the targets gathered alongside the rows.  Philox dropout masks are keyed by
+    the global row of the iteration and the L2 decay uses the full dataset size, so the trained parameters are
+    bit-identical to the resident MlpIterRunner's."""
+
+    def __init__(self, mlp, X_host, Y_host, batch_size, lr, l2, dropout_p, seed, chunk_rows=None):
+        self.mlp = mlp
+        self.n, self.bs = int(X_host.shape[0]), int(batch_size)
+        dev = mlp.device
+        self.first = mlp.layers[0]
+        self.R = host_chunk_rows(self.bs, self.n, 4 * int(X_host.shape[1]), chunk_rows)
+        self.feed = HostChunkFeeder([X_host, Y_host], self.R, dev)
+        self.Xp = [self.first.alloc_staged(self.R, mlp.n_in) for _ in range(2)]
+        self.ws = mlp.make_workspace(min(self.bs, self.n))
+        self.iter_ctr = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.loss_rows = torch.zeros(self.n, dtype=torch.float32, device=dev)
+        decay = 1.0 - (lr * l2) / self.n
+        self.args = [mlp.step_args(xp, yd, lr / batch_size, decay, 1.0 - dropout_p, self.ws, seed, self.iter_ctr,
+                                   self.loss_rows, None) for xp, yd in zip(self.Xp, self.feed.dev[1])]
+        self.launches_per_iter = 0
+
+    def run(self, order=None):
+        lib = self.mlp.lib
+        if order is None:
+            order = epoch_order(self.n)
+        order = np.asarray(order)
+        before = lib.dbn_launch_count()
+
+        def visit(slot, s0, m):
+            self.first.stage(self.feed.dev[0][slot][:m], out=self.Xp[slot][:m])
+            a = self.args[slot]
+            a.row0 = 0
+            a.rng.row0 = s0
+            a.loss_rows = self.loss_rows.data_ptr() + 4 * s0
+            L.check(lib.dbn_mlp_fit_epoch(stream_ptr(), C.byref(a), m, self.bs))
+        self.feed.iterate(order, visit)
+        self.iter_ctr.add_(1)
+        self.launches_per_iter = int(lib.dbn_launch_count() - before)
 
 
 class DpRbmEpochRunner:
@@ -944,11 +1008,17 @@ class DeviceMlp:
 
     def fit(self, Xd, Yd, n_iter, batch_size, lr, l2, dropout_p, seed, rng_mode="philox", verbose=None):
         """NumPyAbstractSupervisedDBN._stochastic_gradient_descent (dbn/models.py:419-469).  The
-        1/p pre-scale and p post-scale of _fine_tuning (:533-548) are done by the caller."""
+        1/p pre-scale and p post-scale of _fine_tuning (:533-548) are done by the caller.  Xd / Yd are device tensors
+        (resident fine-tune) or host ndarrays (streamed from the host chunk by chunk: HostMlpIterRunner)."""
         n = int(Xd.shape[0])
         if n == 0 or n_iter <= 0:
             return
-        runner = MlpIterRunner(self, Xd, Yd, batch_size, lr, l2, dropout_p, seed, rng_mode)
+        if isinstance(Xd, np.ndarray):
+            if rng_mode != "philox":
+                raise ValueError("rng='numpy' (replay of the reference's dropout stream) needs the dataset resident on the device.")
+            runner = HostMlpIterRunner(self, Xd, Yd, batch_size, lr, l2, dropout_p, seed)
+        else:
+            runner = MlpIterRunner(self, Xd, Yd, batch_size, lr, l2, dropout_p, seed, rng_mode)
         for it in range(1, n_iter + 1):
             runner.run()
             if verbose is not None:

@@ -489,10 +489,14 @@ class AbstractSupervisedDBN(BaseEstimator, BaseModel):
 
     # ---- public API (dbn/models.py:327-362) ----
     def fit(self, X, y=None, pre_train=True):
-        if pre_train and self.unsupervised_dbn._out_of_core(np.shape(X)):
-            self.unsupervised_dbn._fit_host(X)      # pre-training streams the dataset from the host
-            pre_train = False
-        Xd = _to_device_f32(X)                       # the fine-tune keeps its inputs resident
+        if self.unsupervised_dbn._out_of_core(np.shape(X)):
+            # out of core: both phases stream the dataset from the host, chunk by chunk
+            Xh = np.ascontiguousarray(np.asarray(X), dtype=np.float32)
+            if pre_train:
+                self.unsupervised_dbn._fit_host(Xh)
+            self._fine_tuning(Xh, y)
+            return self
+        Xd = _to_device_f32(X)
         if pre_train:
             self.unsupervised_dbn._fit_device(Xd)
         self._fine_tuning(Xd, y)   # labels as given: the label map's keys are the caller's elements (dbn/models.py:575-584)
@@ -568,7 +572,8 @@ class AbstractSupervisedDBN(BaseEstimator, BaseModel):
         cb = None
         if self.verbose:
             cb = lambda it, err: print(">> Epoch %d finished \tANN training loss %f" % (it, err))
-        mlp.fit(Xd, _to_device_f32(labels), self.n_iter_backprop, self.batch_size, self.learning_rate,
+        targets = np.ascontiguousarray(labels, dtype=np.float32) if isinstance(Xd, np.ndarray) else _to_device_f32(labels)
+        mlp.fit(Xd, targets, self.n_iter_backprop, self.batch_size, self.learning_rate,
                 self.l2_regularization, self.dropout_p, _draw_seed() if self.rng == 'philox' else 0,
                 rng_mode=self.rng, verbose=cb)
         for layer in mlp.layers:

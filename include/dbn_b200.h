@@ -128,7 +128,10 @@ typedef struct dbn_colsum {
   unsigned long long* acc; /* [N] fixed-point accumulators, or NULL = off */
   float sign;              /* +1 / -1                                     */
   int32_t ref_row0;
-  dbn_mat ref;             /* optional [rows, ld] matrix (bf16 / fp32)    */
+  dbn_mat ref;             /* optional [rows, ld] matrix (16-bit / fp32)  */
+  int32_t square;          /* != 0: accumulate x^2 instead of sign * x -- with `ref` the squared reconstruction distance
+                              sum_rows (v - v')^2 of dbn/models.py:212-220, taken in the epilogue that produces v' */
+  int32_t _pad;
 } dbn_colsum;
 
 /* Activation-type epilogue:
@@ -225,6 +228,12 @@ int dbn_gemm_update(void* stream, int precision, int M, int N, int augM, int aug
                     const dbn_operands* ops, int n_ops, const dbn_update_epilogue* epi);
 
 /* ---- RBM: BinaryRBM hot path ---------------------------------------------------------------- */
+/* _compute_reconstruction_error (dbn/models.py:212-220) for a block of rows without materialising the reconstruction:
+ * v' = act(Hm W + b) and acc[j] += sum_rows (X[row0 + m, j] - v'[m, j])^2 (fixed point, see dbn_colsum) in the epilogue of
+ * the contraction.  Hm: hidden means of the same rows.  The caller sums acc[0..V) and divides by 2^32 and by the number of rows. */
+int dbn_rbm_reconstruction_sq(void* stream, int precision, const dbn_mat* Hm, int B, int V, int H, const dbn_mat* W,
+                              const float* b, int act, const dbn_mat* X, int row0, unsigned long long* acc);
+
 /* _compute_hidden_units_matrix (dbn/models.py:176-183): out[B,H] = act(X W^T + c). */
 int dbn_rbm_hidden_means(void* stream, int precision, const dbn_mat* X, int row0, int B, int V, int H,
                          const dbn_mat* W, const float* c, int act, const dbn_mat* out);

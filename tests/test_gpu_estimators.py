@@ -380,3 +380,31 @@ def test_out_of_core_fit_equals_the_resident_fit(precision, V, hs, bs, monkeypat
     assert np.array_equal(m.W, r1.W) and np.array_equal(m.c, r1.c)
     assert abs(runner.reconstruction_error() - e1) < 1e-4 * max(1.0, e1)
     assert np.allclose(runner.transform_to_host(), r1.transform(X), atol=1e-6)
+
+
+@pytest.mark.parametrize("kind,precision,dropout", [("clf", "bf16", 0.2), ("reg", "fp32", 0.0)])
+def test_out_of_core_supervised_fit_equals_the_resident_fit(kind, precision, dropout, monkeypatch):
+    """Pre-training AND fine-tuning streamed from the host (inputs and targets gathered chunk by chunk) against the
+    resident fit: bit-identical layers and head in Philox mode (global-row dropout masks, decay over the full N)."""
+    rng = np.random.default_rng(5)
+    bs, V, hs = 64, 192, [128, 160]
+    N = 7 * bs + 9
+    X = rng.random((N, V)).astype(np.float32)
+    y = rng.integers(0, 5, N) if kind == "clf" else (X @ rng.standard_normal((V, 2))).astype(np.float64)
+    cls = SupervisedDBNClassification if kind == "clf" else SupervisedDBNRegression
+    kw = dict(hidden_layers_structure=hs, learning_rate_rbm=0.05, learning_rate=0.05, n_epochs_rbm=2, n_iter_backprop=3,
+              batch_size=bs, dropout_p=dropout, verbose=False, precision=precision)
+    monkeypatch.setenv("DBN_B200_PERSISTENT", "0")
+    monkeypatch.setenv("DBN_B200_DRAW_AHEAD", "0")
+    monkeypatch.setenv("DBN_B200_MLP_FORK", "0")
+    np.random.seed(2)
+    res = cls(**kw).fit(X, y)
+    monkeypatch.setenv("DBN_B200_RESIDENT_BYTES", "1")
+    monkeypatch.setenv("DBN_B200_CHUNK_ROWS", str(2 * bs))
+    np.random.seed(2)
+    ooc = cls(**kw).fit(X, y)
+    for a, b in zip(res.unsupervised_dbn.rbm_layers, ooc.unsupervised_dbn.rbm_layers):
+        assert np.array_equal(a.W, b.W) and np.array_equal(a.c, b.c) and np.array_equal(a.b, b.b)
+    assert np.array_equal(res.W, ooc.W) and np.array_equal(res.b, ooc.b)
+    monkeypatch.delenv("DBN_B200_RESIDENT_BYTES")
+    assert np.array_equal(np.asarray(res.predict(X[:20])), np.asarray(ooc.predict(X[:20])))
