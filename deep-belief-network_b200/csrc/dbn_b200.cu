@@ -572,8 +572,16 @@ int dbn_dp_apply(void* stream, const dbn_dp_exchange* x, float scale, float* W, 
   DBN_NEED_DEVICE();
   DBN_TRY(dp_check(x));
   DBN_REQUIRE(W && b && c && local_stats && counter && ldw >= x->V, "bad argument");
+  // A small persistent grid on purpose: with every warp of a huge grid resident at once the kernel runs as two bulk
+  // phases (all loads of the slots, then all peer stores); a few iterations per thread let the peer stores of
+  // iteration i ride under the slot reads of iteration i+1 (dp_apply_blocks() = DBN_B200_DP_APPLY_BLOCKS or 2 per SM).
   const long total = (long)x->rows_per_peer * ((x->V + 7) / 8);
-  const int blocks = (int)std::max<long>(1, std::min<long>((total + 255) / 256, 148L * 4));
+  static int per_sm = -1;
+  if (per_sm < 0) {
+    const char* e = getenv("DBN_B200_DP_APPLY_BLOCKS");
+    per_sm = e ? std::max(1, atoi(e)) : 2;
+  }
+  const int blocks = (int)std::max<long>(1, std::min<long>((total + 255) / 256, 148L * per_sm));
   dp_apply_kernel<<<blocks, 256, 0, as_stream(stream)>>>(*x, scale, W, ldw, b, c, local_stats, counter, value);
   DBN_LAUNCH_CHECK();
   return DBN_OK;

@@ -53,7 +53,7 @@ struct UmmaGemmParams {
   int rowA[2], rowB[2];
   int M, N;  // accumulator extent (incl. the ones row / column)
   int tiles_m, tiles_n, group_m;
-  int mb_rot;          // row blocks are visited in the order (mb + mb_rot) % tiles_m (peer scatter: own rows last)
+  int own_start, own_rows;   // peer scatter: row blocks [own_start, own_start + own_rows) belong to this rank and are visited last
   int split, fs_per;   // split-K kernel: cluster size and fat stages per CTA
   long long* trace;  // debug: per-CTA phase timestamps (dbn_debug_set_trace), normally NULL
 };
@@ -180,14 +180,29 @@ __device__ __forceinline__ uint32_t make_idesc(int bm, int bn, int transA, int t
 }
 
 __device__ __forceinline__ void tile_coords(const UmmaGemmParams& p, int tile, int& mb, int& nb) {
+  if (p.own_rows > 0) {
+    // peer scatter (see UmmaUpdEpi::scatter_order): the other owners' row blocks first, walked block by block for one
+    // column block at a time, starting behind this rank's own rows; the own row blocks (local stores) last
+    const int remote_m = p.tiles_m - p.own_rows;
+    const int n_remote = remote_m * p.tiles_n;
+    if (tile < n_remote) {
+      mb = p.own_start + p.own_rows + tile % remote_m;
+      if (mb >= p.tiles_m) mb -= p.tiles_m;
+      nb = tile / remote_m;
+    } else {
+      const int t = tile - n_remote;
+      mb = p.own_start + t % p.own_rows;
+      nb = t / p.own_rows;
+    }
+    return;
+  }
   // grouped raster: `group_m` row-blocks x all column-blocks form an L2-resident super-tile
   const int per_group = p.group_m * p.tiles_n;
   const int g = tile / per_group;
   const int first_m = g * p.group_m;
   const int gm = min(p.group_m, p.tiles_m - first_m);
   const int r = tile - g * per_group;
-  mb = first_m + r % gm + p.mb_rot;
-  if (mb >= p.tiles_m) mb -= p.tiles_m;
+  mb = first_m + r % gm;
   nb = r / gm;
 }
 
@@ -954,17 +969,21 @@ struct UmmaUpdEpi {
   static constexpr bool kIsUpdate = true;
   dbn_update_epilogue e;
   bool scatter_host() const { return e.raw_peers[0] != nullptr; }
-  // Tile order of a scattered dW (CTA-pair kernel, 256-row blocks).  The accumulator tiles leave over NVLink in
-  // bursts, one per wave of tiles, and the last burst is exposed after the last MMA.  Visiting the owners' row blocks
-  // in the order rank+1, rank+2, ..., rank makes (a) every rank send to a different owner at any time (no incast)
-  // and (b) the final wave consist of the rows this rank owns itself -- local stores, nothing left on the wire.
+  // Tile order of a scattered dW (CTA-pair kernel, 256-row blocks).  The accumulator tiles leave over NVLink as
+  // they are finished, so the ORDER of the tiles is the traffic pattern:
+  //   * the other owners' row blocks are walked block by block for one column block at a time, so consecutive tiles
+  //     go to consecutive owners -- every owner receives all the time, none is the target of a whole wave -- and rank
+  //     r starts behind its own rows, so the ranks target different owners at the same moment;
+  //   * the rows this rank owns itself come last: the final wave of tiles stores locally and nothing is left on the
+  //     wire when the kernel ends.
+  // (Measured on 8 x B200, profiles/r02_notes.md: the default raster -- 8 row blocks = 4 owners per super-tile -- hands
+  //  the owners of the second half their rows late; one super-tile per owner is slower still.)
   void scatter_order(UmmaGemmParams& p) const {
     if (e.raw_peers[0] == nullptr || e.rows_per_peer <= 0 || (e.rows_per_peer % 256) != 0) return;
     const int per_owner = e.rows_per_peer / 256;
-    if (p.tiles_m % per_owner != 0) return;
-    const int owners = p.tiles_m / per_owner;
-    p.group_m = per_owner;
-    p.mb_rot = ((e.raw_slot + 1) % owners) * per_owner;
+    if (p.tiles_m % per_owner != 0 || p.tiles_m == per_owner) return;
+    p.own_start = e.raw_slot * per_owner;
+    p.own_rows = per_owner;
   }
   __device__ __forceinline__ void apply(uint32_t, int m, int n0, const float acc[32], int M, int N, int augM, int augN) const {
     upd_epilogue_row<32>(e, m, n0, acc, M, N, augM, augN);
@@ -1217,8 +1236,7 @@ inline int umma_launch2(cudaStream_t st, UmmaGemmParams& p, const Epi& epi, int 
   p.tiles_m = ceil_div(p.M, 256);
   p.tiles_n = ceil_div(p.N, BN);
   p.group_m = std::max(1, std::min(p.tiles_m, 8));
-  p.mb_rot = 0;
-  epi.scatter_order(p);    // peer scatter: one super-tile per owner, visited in rotated order with the own rows last
+  epi.scatter_order(p);    // peer scatter: the tile order is the traffic pattern
   const int n_tiles = p.tiles_m * p.tiles_n;
   const int clusters = std::min(n_tiles, umma_num_sms() / 2);
   DBN_CUDA_OK(launch_pdl(umma_gemm2_kernel<BN, UG2_KS, Epi>, dim3(clusters * 2), dim3(UG_THREADS), SMEM, st, p, epi, coreM,
