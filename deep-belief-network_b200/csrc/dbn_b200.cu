@@ -7,6 +7,7 @@
 #include "umma_gemm.cuh"
 #include "misc_kernels.cuh"
 #include "rbm_persistent.cuh"
+#include "rbm_tc_epoch.cuh"
 #include "dp_kernels.cuh"
 
 using namespace dbn;
@@ -75,6 +76,8 @@ inline int bf16_pitch(int cols) { return (int)align_up((size_t)cols + 1, 64); }
 struct RbmWorkspace {
   dbn_mat P0, Hs, Vt, Pk;
   unsigned long long* stats;   // [H + V] fixed-point bias statistics dc | db (dbn_colsum)
+  TeCtl* ctl;                  // tensor-core modes: control block + split-K scratch of the persistent epoch kernel
+  float* scratch;
 };
 size_t rbm_ws_layout(int precision, int Bmax, int V, int H, char* base, RbmWorkspace* ws) {
   const int dt = is_tc(precision) ? tc_dtype(precision) : DBN_F32;
@@ -90,6 +93,17 @@ size_t rbm_ws_layout(int precision, int Bmax, int V, int H, char* base, RbmWorks
   w.P0 = carve(ldH); w.Hs = carve(ldH); w.Vt = carve(ldV); w.Pk = carve(ldH);
   w.stats = reinterpret_cast<unsigned long long*>(base ? base + off : nullptr);
   off = align_up(off + (size_t)(H + V) * sizeof(unsigned long long), 1024);
+  w.ctl = nullptr;
+  w.scratch = nullptr;
+  if (is_tc(precision)) {
+    w.ctl = reinterpret_cast<TeCtl*>(base ? base + off : nullptr);
+    off = align_up(off + sizeof(TeCtl), 1024);
+    TePlan pl;
+    if (te_plan(V, H, Bmax, &pl) && pl.scratch_bytes > 0) {
+      w.scratch = reinterpret_cast<float*>(base ? base + off : nullptr);
+      off = align_up(off + pl.scratch_bytes, 1024);
+    }
+  }
   if (ws) *ws = w;
   return off;
 }
@@ -432,8 +446,102 @@ int dbn_rbm_fit_epoch_persistent(void* stream, const dbn_rbm_step_args* t, const
   return rbm_persistent_launch(as_stream(stream), a, t->V, t->H, batch_size);
 }
 
+// Whole epoch in ONE cooperative launch of rbm_tc_epoch_kernel when the layer fits its tile plan (tensor-core modes,
+// mini-batches of 16..256 rows, plain in-place training); *done = 0: not applicable, the caller runs the tiled path.
+static int rbm_fit_epoch_tc(cudaStream_t st, const dbn_rbm_step_args* t, int n_rows, int batch_size, int* done) {
+  *done = 0;
+  const int B = t->ws_rows > 0 ? t->ws_rows : std::min(batch_size, n_rows);
+  if (!te_enabled() || !is_tc(t->precision) || t->k < 1 || n_rows <= 0) return DBN_OK;
+  if (B < std::min(batch_size, n_rows) || (n_rows > B && B != batch_size)) return DBN_OK;   // the step stride is the tile height
+  if (t->flags & (DBN_STEP_SKIP_UPDATE | DBN_STEP_SKIP_FIRST_HIDDEN)) return DBN_OK;
+  if (t->P0.ptr || t->Vk.ptr || t->Pk.ptr || t->H0s.ptr || t->raw_delta.ptr) return DBN_OK;
+  if (t->act != DBN_ACT_SIGMOID && t->act != DBN_ACT_RELU) return DBN_OK;
+  if (t->rng.injected.ptr && t->rng.injected.dtype != DBN_F32) return DBN_OK;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) {
+    (void)cudaGetLastError();
+    return DBN_OK;   // a cooperative launch is not captured: graphs keep the tiled path
+  }
+  TeArgs a;
+  memset(&a, 0, sizeof(a));
+  if (!te_plan(t->V, t->H, B, &a.pl)) return DBN_OK;
+  if (a.pl.grid > te_max_coresident()) return DBN_OK;
+  if (t->workspace_bytes < dbn_rbm_workspace_bytes(t->precision, B, t->V, t->H)) return DBN_OK;
+  if (!umma_operand_ok(t->X, t->V) || !umma_operand_ok(t->Wb, t->V) || t->X.dtype != t->Wb.dtype) return DBN_OK;
+  RbmWorkspace ws;
+  rbm_ws_layout(t->precision, B, t->V, t->H, static_cast<char*>(t->workspace), &ws);
+  if (a.pl.scratch_bytes > 0 && ws.scratch == nullptr) return DBN_OK;
+  a.V = t->V; a.H = t->H; a.B = B; a.k = t->k; a.act = t->act; a.dtype = t->X.dtype;
+  a.n_rows = n_rows; a.row0 = t->row0; a.scale = t->lr_over_bs;
+  a.X = t->X; a.P0 = ws.P0; a.Hs = ws.Hs; a.Vt = ws.Vt; a.Pk = ws.Pk; a.Wb = t->Wb;
+  a.W = t->W; a.ldw = t->ldw; a.b = t->b; a.c = t->c; a.stats = ws.stats;
+  a.rng = t->rng;
+  a.ctl = ws.ctl; a.scratch = ws.scratch;
+  a.trace = umma_trace_ptr();
+  const TePlan& pl = a.pl;
+  const uint64_t xrows = (uint64_t)t->row0 + (uint64_t)n_rows;
+  // K-major operands: one copy brings every 64-wide k-slab of a tile's rows
+  DBN_TRY(make_operand_map(&a.tm_x3, t->X, xrows, pl.kv_slabs, pl.rb_h, pl.kv_slabs));
+  DBN_TRY(make_operand_map(&a.tm_vt3, ws.Vt, B, pl.kv_slabs, pl.rb_h, pl.kv_slabs));
+  DBN_TRY(make_operand_map(&a.tm_hs3, ws.Hs, B, ceil_div(t->H, 64), pl.rb_v, pl.kc_slabs));
+  DBN_TRY(make_operand_map(&a.tm_wb3, t->Wb, t->H, pl.kv_slabs, pl.hs, pl.kv_slabs));
+  // MN-major operands: 64 columns x up to 256 k rows per copy
+  DBN_TRY(te_make_map2(&a.tm_wb2, t->Wb, t->Wb.ld, t->H, std::min(pl.kc_slabs * 64, 256)));
+  DBN_TRY(te_make_map2(&a.tm_p02, ws.P0, ws.P0.ld, B, 256));
+  DBN_TRY(te_make_map2(&a.tm_pk2, ws.Pk, ws.Pk.ld, B, 256));
+  DBN_TRY(te_make_map2(&a.tm_x2, t->X, t->X.ld, xrows, 256));
+  DBN_TRY(te_make_map2(&a.tm_vt2, ws.Vt, ws.Vt.ld, B, 256));
+  static std::atomic<uint64_t> attr_set{0};
+  if (first_use_on_device(attr_set))
+    DBN_CUDA_OK(cudaFuncSetAttribute(rbm_tc_epoch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TE_SMEM_MAX));
+  DBN_CUDA_OK(cudaMemsetAsync(ws.ctl, 0, sizeof(TeCtl), st));
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(pl.grid);
+  cfg.blockDim = dim3(TE_THREADS);
+  cfg.dynamicSmemBytes = pl.smem_bytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;     // all CTAs co-resident or the launch fails: the grid barrier cannot deadlock
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  DBN_CUDA_OK(cudaLaunchKernelEx(&cfg, rbm_tc_epoch_kernel, a));
+  DBN_LAUNCH_CHECK();
+  *done = 1;
+  return DBN_OK;
+}
+
+int dbn_rbm_tc_epoch_plan(int precision, int V, int H, int batch_size) {
+  TePlan pl;
+  if (!is_tc(precision) || !te_enabled() || !te_plan(V, H, batch_size, &pl)) return 0;
+  return pl.grid;
+}
+int dbn_set_tc_epoch(int enabled) {
+  const int prev = te_enabled_flag();
+  te_enabled_flag() = enabled ? 1 : 0;
+  return prev;
+}
+int dbn_rbm_tc_epoch_plan_info(int V, int H, int batch_size, int32_t* out, int n) {
+  DBN_REQUIRE(out && n >= 0, "bad argument");
+  TePlan pl;
+  if (!te_plan(V, H, batch_size, &pl)) return 0;
+  const int32_t v[] = {pl.grid, pl.rb_h, pl.hs, pl.nt_h_rows * pl.nt_h_cols, pl.rb_v, pl.vs, pl.ksplit, pl.kc_slabs,
+                       pl.nt_v_rows * pl.nt_v_cols * pl.ksplit, pl.n4, pl.nt_u_rows * pl.nt_u_cols, (int32_t)pl.smem_bytes,
+                       pl.v1c_early, pl.p1_in_act, (int32_t)pl.scratch_bytes, pl.kv_slabs};
+  const int m = (int)(sizeof(v) / sizeof(v[0]));
+  for (int i = 0; i < n && i < m; ++i) out[i] = v[i];
+  return m;
+}
+
 int dbn_rbm_fit_epoch(void* stream, const dbn_rbm_step_args* tmpl, int n_rows, int batch_size) {
   DBN_REQUIRE(tmpl && n_rows >= 0 && batch_size > 0, "bad argument");
+  {
+    DBN_NEED_DEVICE();
+    int done = 0;
+    DBN_TRY(rbm_fit_epoch_tc(as_stream(stream), tmpl, n_rows, batch_size, &done));
+    if (done) return DBN_OK;
+  }
   for (int s = 0; s < n_rows; s += batch_size) {  // batch_generator: dbn/utils.py:14-22 (short last batch)
     dbn_rbm_step_args a = *tmpl;
     a.B = std::min(batch_size, n_rows - s);

@@ -524,6 +524,10 @@ class RbmEpochRunner:
         self.persistent = (os.environ.get("DBN_B200_PERSISTENT", "1") != "0" and Xd.dtype == torch.float32 and
                            Xd.is_contiguous() and
                            lib.dbn_rbm_persistent_plan(layer.prec, layer.V, layer.H, min(self.bs, n)) > 0)
+        # tensor-core modes at batch <= 256: dbn_rbm_fit_epoch is ONE cooperative launch of the persistent tcgen05 kernel
+        # (csrc/rbm_tc_epoch.cuh) -- nothing to capture, and a cooperative launch is not captured anyway
+        self.tc_epoch = (not self.persistent and layer.prec in TC_PRECS and
+                         lib.dbn_rbm_tc_epoch_plan(layer.prec, layer.V, layer.H, min(self.bs, n)) > 0)
         if self.persistent:   # reads the un-permuted dataset through the index array: no epoch array, no workspace
             self.Xp = Xd
             self.ws = torch.empty(16, dtype=torch.uint8, device=layer.device)
@@ -553,7 +557,7 @@ class RbmEpochRunner:
             self.U.copy_(torch.from_numpy(np.random.random_sample((self.n, self.k * layer.H)).astype(np.float32)))
         # Epoch 1 runs eagerly (it doubles as the warm-up that loads every kernel before capture, and a
         # one-epoch fit never pays for capture + instantiation); epoch 2 is captured; later epochs replay.
-        if _use_graphs() and self.epochs_run >= 1 and not self.persistent:
+        if _use_graphs() and self.epochs_run >= 1 and not self.persistent and not self.tc_epoch:
             if self.graph is None:
                 torch.cuda.current_stream().synchronize()
                 self.graph = torch.cuda.CUDAGraph()

@@ -290,6 +290,23 @@ int dbn_rbm_cd_step(void* stream, const dbn_rbm_step_args* args);
  * template's optional outputs must be NULL.  Pure launches: capture it in a CUDA graph. */
 int dbn_rbm_fit_epoch(void* stream, const dbn_rbm_step_args* tmpl, int n_rows, int batch_size);
 
+/* Tensor-core modes: dbn_rbm_fit_epoch runs the whole epoch as ONE cooperative launch of the persistent tcgen05
+ * kernel (csrc/rbm_tc_epoch.cuh: <= 148 co-resident CTAs, a grid barrier between the phases of a mini-batch instead
+ * of a launch boundary, the CTA's weight slices resident in shared memory for the step, P0 / samples / V1 / Pk kept
+ * in L2) when the layer fits its tile plan -- mini-batches of 16..256 rows, plain in-place training (no optional
+ * outputs, no DBN_STEP_SKIP_* flags), stream not being captured -- and as the loop of dbn_rbm_cd_step otherwise.
+ * Replaces the whole mini-batch loop of dbn/models.py:105-119.  Returns the number of CTAs the plan uses, 0 when the
+ * shape does not fit (or DBN_B200_TC_EPOCH=0): callers skip CUDA-graph capture of the epoch when it is non-zero. */
+int dbn_rbm_tc_epoch_plan(int precision, int V, int H, int batch_size);
+/* Switch the persistent epoch kernel on / off at run time (default: on unless DBN_B200_TC_EPOCH=0); returns the
+ * previous setting.  Parity tests run the same epoch through both paths. */
+int dbn_set_tc_epoch(int enabled);
+/* The tile plan as numbers (tests, profiles/ notes): out[0..] = CTAs, hidden tile rows, hidden tile units, hidden tiles,
+ * visible tile rows, visible tile units, K split, k-slabs per chunk, visible tiles, dW tile width, dW tiles,
+ * shared-memory bytes, Vk-columns-fetched-early, P1-in-activation-buffer, split-K scratch bytes, k-slabs of V.
+ * Returns the number of values the plan has (0: the shape does not fit). */
+int dbn_rbm_tc_epoch_plan_info(int V, int H, int batch_size, int32_t* out, int n);
+
 /* On-chip persistent variant of dbn_rbm_fit_epoch for layers whose weights fit in the shared memory of
  * one thread-block cluster (strict FP32 only): ONE launch trains the whole epoch with W resident in
  * distributed shared memory; hidden units are sharded over the cluster's CTAs.  tmpl->X is the

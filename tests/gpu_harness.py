@@ -182,3 +182,42 @@ def relF(a, b):
     """Norm-wise relative error ||a-b||_F / ||b||_F."""
     nb = np.linalg.norm(b)
     return float(np.linalg.norm(np.asarray(a) - np.asarray(b)) / (nb if nb > 0 else 1.0))
+
+
+def run_rbm_epoch(W, b, c, X, batch_size, k, act, precision, seed=0, lr=0.1, U=None, tc_epoch=True, epochs=1):
+    """`epochs` passes of dbn_rbm_fit_epoch over the rows of X in their stored order (no shuffle), either as ONE
+    persistent launch per epoch (tc_epoch=True, csrc/rbm_tc_epoch.cuh) or as the tiled four-launch steps.  Returns the
+    trained parameters, the 16-bit shadow and the number of kernels the library launched."""
+    import torch
+    l = lib()
+    H, V = W.shape
+    n = X.shape[0]
+    layer = E.DeviceRbm(W, b, c, act, precision, torch.device("cuda"))
+    Xop = stage_operand(X, precision)
+    ws = layer.make_workspace(min(batch_size, n))
+    ctr = torch.zeros(1, dtype=torch.int32, device="cuda")
+    Ud = None
+    if U is not None:
+        Ud = _t(np.asarray(U, dtype=np.float32).reshape(n, k * H), torch.float32)
+    a = layer._step_args(Xop, k, lr / batch_size, ws, seed, ctr, Ud)
+    prev = l.dbn_set_tc_epoch(1 if tc_epoch else 0)
+    try:
+        before = l.dbn_launch_count()
+        for _ in range(epochs):
+            L.check(l.dbn_rbm_fit_epoch(E.stream_ptr(), C.byref(a), n, batch_size))
+            ctr.add_(1)
+        torch.cuda.synchronize()
+        launches = int(l.dbn_launch_count() - before)
+    finally:
+        l.dbn_set_tc_epoch(prev)
+    Wn, bn, cn = layer.export()
+    return {"W": Wn, "b": bn, "c": cn, "Wb": layer.Wb[:, :V].float().double().cpu().numpy(), "launches": launches}
+
+
+def tc_epoch_plan(V, H, B):
+    """Tile plan of the persistent epoch kernel as a dict (empty: the shape does not fit)."""
+    out = (C.c_int32 * 16)()
+    m = lib().dbn_rbm_tc_epoch_plan_info(V, H, B, out, 16)
+    names = ["ctas", "hid_rows", "hid_units", "hid_tiles", "vis_rows", "vis_units", "ksplit", "kc_slabs", "vis_tiles",
+             "dw_width", "dw_tiles", "smem", "vk_early", "p1_in_act", "scratch", "kv_slabs"]
+    return {names[i]: int(out[i]) for i in range(min(m, 16))}
