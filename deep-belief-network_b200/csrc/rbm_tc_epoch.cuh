@@ -18,8 +18,9 @@
 //     tile's owner, which also refreshes the 16-bit shadow; db / dc are fixed-point column sums taken in the
 //     phase epilogues (dbn_colsum) and folded into b / c by their owner threads.
 //
-// Warp roles (18 warps): warp 0 = TMA producer (one lane), warp 1 = TMEM allocator + MMA issuer (one lane),
-// warps 2-17 = epilogue (four warps per TMEM lane quarter, 8-column chunks dealt round robin) + grid barrier.
+// Warp roles (20 warps): warp 0 = TMA producer (one lane), warps 1-3 = MMA issuers (one lane each; warp 1 also owns
+// the TMEM allocation), warps 4-19 = epilogue (four warps per TMEM lane quarter, 8-column chunks dealt round robin)
+// + grid barrier.
 // Results match the tiled path to fp32 round-off (other summation order inside a dot product), samples are
 // drawn from the same Philox counters.  Every wait is bounded: a protocol bug traps instead of hanging.
 #pragma once
@@ -29,17 +30,20 @@ namespace dbn {
 
 constexpr int TE_EPI_WARPS = 16;
 constexpr int TE_EPI_THREADS = 32 * TE_EPI_WARPS;
-constexpr int TE_THREADS = 64 + TE_EPI_THREADS;
+constexpr int TE_NISS = 3;                 // MMA issuer warps
+constexpr int TE_WARP_EPI = 1 + TE_NISS;   // first epilogue warp (a multiple of 4: warp % 4 = TMEM lane quarter)
+constexpr int TE_THREADS = 32 * TE_WARP_EPI + TE_EPI_THREADS;   // 20 warps (registers are allotted per 4 warps: same budget as 18)
 constexpr int TE_MAX_TILE_CTRS = 480;
 constexpr int TE_PLAN_CTAS = 148;          // SMs of a B200: the plan never asks for more CTAs than can be co-resident
 constexpr int TE_SMEM_MAX = 232448;        // 227 KB opt-in limit per CTA
 constexpr int TE_BOX_BYTES = 256 * 128;    // one MN-major operand chunk: 256 k rows x 64 elements
-// A chain of small MMAs into ONE accumulator is latency-bound (~70 cycles per dependent 64 x 32 x 16 MMA against 16 of
-// tensor-pipe work): consecutive k-steps therefore go to TE_NACC interleaved accumulators (TMEM columns i * width),
-// which the epilogue adds up.  Every phase starts at column 0: a phase's MMAs cannot start before this CTA's epilogue
+// One thread issues a 64 x N x 16 MMA every ~70 cycles (descriptor arithmetic + the election wrapper, one warp's
+// dependent-issue latency) while the tensor pipe needs N/2 cycles for it: at N = 32..56 the ISSUE is the bound of a
+// phase.  The k-steps of a tile are therefore dealt to TE_NISS issuer warps in contiguous blocks of 4 (one 64-wide
+// slab); issuer w accumulates into its own TMEM columns [w * width, (w + 1) * width) and the epilogue adds the
+// partial accumulators up.  Every phase starts at column 0: a phase's MMAs cannot start before this CTA's epilogue
 // of the previous phase has drained TMEM (its operands arrive behind the barrier that epilogue arrives at).
-constexpr int TE_NACC = 4;
-constexpr int TE_TRACE_STEPS = 8, TE_TRACE_SLOTS = 8 * 4;         // debug trace: steps x (phases x 4 stamps)
+constexpr int TE_TRACE_STEPS = 8, TE_TRACE_SLOTS = 8 * 16;        // debug trace: steps x (phases x 16 stamps)
 
 struct TeCtl {                 // device control block, zeroed before every launch
   unsigned int arrived;        // grid barrier: arrivals so far (monotonic)
@@ -75,17 +79,20 @@ struct TeArgs {
   dbn_rng rng;
   TeCtl* ctl;
   float* scratch;
-  long long* trace;            // debug (dbn_debug_set_trace): [cta][step < 8][phase < 8][4] clock64 stamps
+  long long* trace;            // debug (dbn_debug_set_trace): [cta][step < 8][phase < 8][16] clock64 stamps: 0 operands landed
+                               // (issuer 0), 1 accumulator ready (epilogue thread 0), 2 its epilogue done, 3 CTA done, 4 arrived
+                               // at the grid barrier, 5 barrier passed, 6 MMAs complete (issuer 0), 7 prefetch done, 8 first
+                               // accumulator chunk in registers, 9 first chunk stored, 10 MMAs issued (issuer 0), 11 loads issued
 };
 
 enum { TE_B_WR = 0, TE_B_WC, TE_B_ACT, TE_B_G4P, TE_B_V0C, TE_B_P1, TE_B_ACC, TE_NBARS };
 enum { TE_HID0 = 0, TE_VIS = 1, TE_HID = 2, TE_HIDK = 3, TE_UPD = 4 };
 
-// accumulators a phase interleaves: a power of two <= TE_NACC, <= the number of k-steps, and 512 TMEM columns in all
-__device__ __forceinline__ int te_nacc(int nk, int width) {
-  int n = TE_NACC;
-  while (n > 1 && (n > nk || n * width > 512)) n >>= 1;
-  return n;
+// blocks of 4 k-steps per issuer, and the number of issuers that get any (= partial accumulators to add up)
+__device__ __forceinline__ int te_units_per_issuer(int nunits) { return (nunits + TE_NISS - 1) / TE_NISS; }
+__device__ __forceinline__ int te_nacc(int nunits) {
+  const int per = te_units_per_issuer(nunits);
+  return (nunits + per - 1) / per;
 }
 
 __device__ __forceinline__ int te_phase_kind(int p, int np) {
@@ -102,10 +109,20 @@ __device__ __forceinline__ void tc_ld8(uint32_t taddr, uint32_t v[8]) {
                : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// one lane of a converged warp (the compiler then keeps warp-uniform values -- descriptors, coordinates -- in
+// uniform registers: no per-instruction R2UR shuffle in front of every UTCHMMA / UTMALDG)
+__device__ __forceinline__ bool te_elect() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 
-// 8 columns of a tile row: the sum of the phase's interleaved accumulators (fixed order)
-__device__ __forceinline__ void te_ld_acc(uint32_t taddr, int nacc, int width, float acc[8]) {
+// A tile row's 8-column chunk sits in lanes 0-15 of a TMEM quarter (UMMA M = 64).  The sum of the phase's partial
+// accumulators is split over the whole warp: lane l < 16 keeps columns 0-3 of row l, lane l + 16 takes columns 4-7,
+// so all 32 lanes run the element-wise tail on 4 columns each.
+__device__ __forceinline__ void te_ld_acc4(uint32_t taddr, int nacc, int width, int lane, float x[4]) {   // nacc <= TE_NISS
   uint32_t v[8];
+  float acc[8];
   tc_ld8(taddr, v);
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = __uint_as_float(v[j]);
@@ -113,6 +130,11 @@ __device__ __forceinline__ void te_ld_acc(uint32_t taddr, int nacc, int width, f
     tc_ld8(taddr + (uint32_t)(i * width), v);
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] += __uint_as_float(v[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float hi = __shfl_sync(0xffffffffu, acc[4 + j], lane & 15);
+    x[j] = lane < 16 ? acc[j] : hi;
   }
 }
 
@@ -124,8 +146,8 @@ __device__ __forceinline__ void te_fail(TeCtl* ctl, int code) {
 
 // ---- grid barrier: one monotonic arrival counter in L2 ---------------------------------------------------
 // Writers: every epilogue thread has stored its outputs and met the others at a CTA barrier; one thread then
-// publishes them (fence) and arrives.  The activations are read back by OTHER CTAs through TMA, i.e. through the
-// async proxy: a proxy fence on both sides orders the generic-proxy stores against those reads.
+// publishes them (release) and arrives.  The activations are read back by OTHER CTAs through TMA, i.e. through the
+// async proxy: a proxy fence orders the generic-proxy stores against those reads.
 __device__ __forceinline__ void te_grid_arrive(TeCtl* ctl) {
   asm volatile("fence.proxy.async.global;" ::: "memory");
   asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(&ctl->arrived) : "memory");   // the release publishes the CTA's stores (bar.sync made them this thread's)
@@ -139,7 +161,6 @@ __device__ __forceinline__ void te_grid_wait(TeCtl* ctl, unsigned target) {
     if (v >= target) break;
     if (spin > (1u << 22)) te_fail(ctl, 1);
   }
-  asm volatile("fence.proxy.async.global;" ::: "memory");
 }
 // progress counter in shared memory (epilogue thread -> producer): grid barriers passed so far
 __device__ __forceinline__ void te_publish(volatile unsigned* slot, unsigned v) {
@@ -152,79 +173,68 @@ __device__ __forceinline__ void te_await(TeCtl* ctl, volatile unsigned* slot, un
   __threadfence_block();
 }
 
-// ---- small vector helpers ---------------------------------------------------------------------------------
-// 8 floats of a vector that is rewritten inside the kernel (b, c, master W): L2 only, never a stale L1 line
-__device__ __forceinline__ void te_load8_cg(const float* p, int n0, int N, float v[8]) {
-  if (n0 + 8 <= N && (reinterpret_cast<uintptr_t>(p + n0) & 15) == 0) {
+// ---- small vector helpers (4 consecutive columns, n0 % 4 == 0) --------------------------------------------
+// 4 floats of a vector that is rewritten inside the kernel (b, c, master W): L2 only, never a stale L1 line
+__device__ __forceinline__ void te_load4_cg(const float* p, int n0, int N, float v[4]) {
+  if (n0 + 4 <= N && (reinterpret_cast<uintptr_t>(p + n0) & 15) == 0) {
     const float4 x = __ldcg(reinterpret_cast<const float4*>(p + n0));
-    const float4 y = __ldcg(reinterpret_cast<const float4*>(p + n0) + 1);
-    v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w; v[4] = y.x; v[5] = y.y; v[6] = y.z; v[7] = y.w;
+    v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
   } else {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = (n0 + j < N) ? __ldcg(p + n0 + j) : 0.0f;
+    for (int j = 0; j < 4; ++j) v[j] = (n0 + j < N) ? __ldcg(p + n0 + j) : 0.0f;
   }
 }
-__device__ __forceinline__ void te_store8_f32(float* p, int n0, int N, const float v[8]) {
-  if (n0 + 8 <= N && (reinterpret_cast<uintptr_t>(p + n0) & 15) == 0) {
-    reinterpret_cast<float4*>(p + n0)[0] = make_float4(v[0], v[1], v[2], v[3]);
-    reinterpret_cast<float4*>(p + n0)[1] = make_float4(v[4], v[5], v[6], v[7]);
+__device__ __forceinline__ void te_store4_f32(float* p, int n0, int N, const float v[4]) {
+  if (n0 + 4 <= N && (reinterpret_cast<uintptr_t>(p + n0) & 15) == 0) {
+    *reinterpret_cast<float4*>(p + n0) = make_float4(v[0], v[1], v[2], v[3]);
   } else {
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
+    for (int j = 0; j < 4; ++j)
       if (n0 + j < N) p[n0 + j] = v[j];
   }
 }
-// 8 consecutive 16-bit elements of row r (n0 % 8 == 0, pitch a multiple of 64: 16-byte aligned)
-__device__ __forceinline__ void te_store8_h(const dbn_mat& m, int r, int n0, int N, const float v[8]) {
-  if (n0 + 8 <= N) {
-    uint4 pk;
+// 16-bit rows: pitch a multiple of 64 elements, so 4 elements at a multiple of 4 are 8-byte aligned
+__device__ __forceinline__ void te_store4_h(const dbn_mat& m, int r, int n0, int N, const float v[4]) {
+  if (n0 + 4 <= N) {
+    uint2 pk;
     pk.x = pack16x2(m.dtype, v[0], v[1]); pk.y = pack16x2(m.dtype, v[2], v[3]);
-    pk.z = pack16x2(m.dtype, v[4], v[5]); pk.w = pack16x2(m.dtype, v[6], v[7]);
-    *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(m.ptr) + (size_t)r * (size_t)m.ld + (size_t)n0) = pk;
+    *reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(m.ptr) + (size_t)r * (size_t)m.ld + (size_t)n0) = pk;
   } else {
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
+    for (int j = 0; j < 4; ++j)
       if (n0 + j < N) mat_store(m, r, n0 + j, v[j]);
   }
 }
-__device__ __forceinline__ void te_load8_h(const dbn_mat& m, int r, int n0, int N, float v[8]) {
-  if (n0 + 8 <= N) {
-    const uint4 pk = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(m.ptr) + (size_t)r * (size_t)m.ld + (size_t)n0));
+__device__ __forceinline__ void te_load4_h(const dbn_mat& m, int r, int n0, int N, float v[4]) {
+  if (n0 + 4 <= N) {
+    const uint2 pk = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(m.ptr) + (size_t)r * (size_t)m.ld + (size_t)n0));
     unpack16x2(m.dtype, pk.x, v[0], v[1]); unpack16x2(m.dtype, pk.y, v[2], v[3]);
-    unpack16x2(m.dtype, pk.z, v[4], v[5]); unpack16x2(m.dtype, pk.w, v[6], v[7]);
   } else {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = (n0 + j < N) ? mat_load(m, r, n0 + j) : 0.0f;
+    for (int j = 0; j < 4; ++j) v[j] = (n0 + j < N) ? mat_load(m, r, n0 + j) : 0.0f;
   }
 }
-// Column sums of 8 columns held one row per lane by lanes 0-15 (the other lanes carry zeros): a butterfly that
-// halves the columns a lane carries per step.  Afterwards the even lanes < 16 hold the sum of column
-// 4*bit3 + 2*bit2 + bit1 of their lane index.
-__device__ __forceinline__ float te_colsum8(const float x[8], int lane) {
-  float y[4], z[2];
+// Column sums over the 16 rows of a half-warp (one row per lane, 4 columns per lane): a butterfly that halves the
+// columns a lane carries per step.  Afterwards the lanes with (lane & 3) == 0 hold the sum of column 2*bit3 + bit2.
+__device__ __forceinline__ float te_colsum4(const float x[4], int lane) {
+  float y[2];
   bool up = (lane & 8) != 0;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const float send = up ? x[j] : x[j + 4], keep = up ? x[j + 4] : x[j];
+  for (int j = 0; j < 2; ++j) {
+    const float send = up ? x[j] : x[j + 2], keep = up ? x[j + 2] : x[j];
     y[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
   }
   up = (lane & 4) != 0;
-#pragma unroll
-  for (int j = 0; j < 2; ++j) {
-    const float send = up ? y[j] : y[j + 2], keep = up ? y[j + 2] : y[j];
-    z[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-  }
-  up = (lane & 2) != 0;
-  const float send = up ? z[0] : z[1], keep = up ? z[1] : z[0];
-  float w = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  const float send = up ? y[0] : y[1], keep = up ? y[1] : y[0];
+  float w = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  w += __shfl_xor_sync(0xffffffffu, w, 2);
   w += __shfl_xor_sync(0xffffffffu, w, 1);
   return w;
 }
 __device__ __forceinline__ void te_stat_commit(unsigned long long* acc, int n0, int N, float w, int lane) {
-  const int n = n0 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-  if (lane < 16 && (lane & 1) == 0 && n < N) stat_add(acc, n, w);
+  const int n = n0 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+  if ((lane & 3) == 0 && n < N) stat_add(acc, n, w);
 }
-
 // consume a statistic (its one owner thread): straight from L2 -- the atomics of the other CTAs landed there
 __device__ __forceinline__ float te_stat_take(unsigned long long* acc, int i) {
   const unsigned long long v = __ldcg(acc + i);
@@ -234,69 +244,68 @@ __device__ __forceinline__ float te_stat_take(unsigned long long* acc, int i) {
 
 __device__ __forceinline__ void te_trace(const TeArgs& a, int step, int p, int slot) {
   if (a.trace != nullptr && step < TE_TRACE_STEPS && p < 8)
-    a.trace[((size_t)blockIdx.x * TE_TRACE_STEPS + step) * TE_TRACE_SLOTS + p * 4 + slot] = clock64();
+    a.trace[((size_t)blockIdx.x * TE_TRACE_STEPS + step) * TE_TRACE_SLOTS + p * 16 + slot] = clock64();
 }
 
-// ---- the activation tail of a hidden / visible phase on one 8-column chunk of one row ------------------
+// ---- the activation tail of a hidden / visible phase on 4 columns of one row ---------------------------
 // hid: x = act(acc + c) -> means (P0 / Pk), sample = (u < x) -> Hs (dbn/models.py:148-155, :176-183)
 // vis: x = act(acc + b) -> Vt                                  (dbn/models.py:195-201)
 // rows at or beyond the valid ones (short last mini-batch) store zeros, so the dW contraction over the whole
-// batch tile adds nothing for them.  Column statistics of the chunk: dc / db (dbn/models.py:143-144).
+// batch tile adds nothing for them.  Column statistics: dc / db (dbn/models.py:143-144).
 //
 // te_act_prefetch runs BEFORE the accumulator is ready and fetches / computes everything that does not depend on
-// it: the bias segment (L2), the uniforms (Philox is ~200 instructions per chunk; or the injected values) and, for
-// the last visible phase, the v_0 segment of the db statistic.  te_act_finish is what is left behind the MMAs.
+// it: the bias segment (L2), the uniforms (one Philox call; or the injected values) and, for the last visible
+// phase, the v_0 segment of the db statistic.  te_act_finish is what is left behind the MMAs.
 __device__ __forceinline__ void te_act_prefetch(const TeArgs& a, bool hid, int kind, int t, uint32_t epoch, int step, int grow,
-                                                bool row_ok, int n0, float bias[8], float aux[8]) {
+                                                bool row_ok, int n0, float bias[4], float aux[4]) {
   const int N = hid ? a.H : a.V;
-  te_load8_cg(hid ? a.c : a.b, n0, N, bias);
+  te_load4_cg(hid ? a.c : a.b, n0, N, bias);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) aux[j] = 0.0f;
+  for (int j = 0; j < 4; ++j) aux[j] = 0.0f;
   if (hid) {
     if (kind != TE_HIDK) {
       const int erow = step * a.B + grow;           // row inside the epoch slice: the Philox counter (GPU-count invariant)
       if (a.rng.injected.ptr != nullptr) {
         const float* up = reinterpret_cast<const float*>(a.rng.injected.ptr) + (size_t)erow * (size_t)a.rng.injected.ld + (size_t)t * a.H;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) aux[j] = (row_ok && n0 + j < N) ? __ldg(up + n0 + j) : 1.0f;
+        for (int j = 0; j < 4; ++j) aux[j] = (row_ok && n0 + j < N) ? __ldg(up + n0 + j) : 1.0f;
       } else {
         dbn_rng g = a.rng;
         g.stream = a.rng.stream + (uint32_t)t;
         rng_uniform4(g, epoch, erow, n0, aux);
-        rng_uniform4(g, epoch, erow, n0 + 4, aux + 4);
       }
     }
   } else if (t == a.k - 1 && row_ok) {
-    te_load8_h(a.X, a.row0 + step * a.B + grow, n0, N, aux);                // v_0 for db = sum_rows (v_0 - v_k)
+    te_load4_h(a.X, a.row0 + step * a.B + grow, n0, N, aux);                // v_0 for db = sum_rows (v_0 - v_k)
   }
 }
 __device__ __forceinline__ void te_act_finish(const TeArgs& a, bool hid, int kind, int t, int grow, bool in_tile, bool row_ok,
-                                              int n0, const float acc[8], const float bias[8], const float aux[8], int lane) {
+                                              int n0, const float acc[4], const float bias[4], const float aux[4], int lane) {
   const int N = hid ? a.H : a.V;
-  float x[8];
+  float x[4];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) x[j] = row_ok ? apply_act<true>(a.act, acc[j] + bias[j]) : 0.0f;
+  for (int j = 0; j < 4; ++j) x[j] = row_ok ? apply_act<true>(a.act, acc[j] + bias[j]) : 0.0f;
   if (hid) {
-    if (in_tile) te_store8_h((kind == TE_HID0) ? a.P0 : a.Pk, grow, n0, N, x);
+    if (in_tile) te_store4_h((kind == TE_HID0) ? a.P0 : a.Pk, grow, n0, N, x);
     if (kind != TE_HIDK) {
-      float s[8];
+      float s[4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) s[j] = (aux[j] < x[j]) ? 1.0f : 0.0f;   // strict '<': dbn/models.py:155
-      if (in_tile) te_store8_h(a.Hs, grow, n0, N, s);
+      for (int j = 0; j < 4; ++j) s[j] = (aux[j] < x[j]) ? 1.0f : 0.0f;   // strict '<': dbn/models.py:155
+      if (in_tile) te_store4_h(a.Hs, grow, n0, N, s);
     }
     if (kind == TE_HID0 || kind == TE_HIDK) {
       if (kind == TE_HIDK) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) x[j] = -x[j];
+        for (int j = 0; j < 4; ++j) x[j] = -x[j];
       }
-      te_stat_commit(a.stats, n0, N, te_colsum8(x, lane), lane);          // dc = sum_rows (h_0 - h_k)
+      te_stat_commit(a.stats, n0, N, te_colsum4(x, lane), lane);          // dc = sum_rows (h_0 - h_k)
     }
   } else {
-    if (in_tile) te_store8_h(a.Vt, grow, n0, N, x);
+    if (in_tile) te_store4_h(a.Vt, grow, n0, N, x);
     if (t == a.k - 1) {                                                     // db = sum_rows (v_0 - v_k)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) x[j] = row_ok ? aux[j] - x[j] : 0.0f;
-      te_stat_commit(a.stats + a.H, n0, N, te_colsum8(x, lane), lane);
+      for (int j = 0; j < 4; ++j) x[j] = row_ok ? aux[j] - x[j] : 0.0f;
+      te_stat_commit(a.stats + a.H, n0, N, te_colsum4(x, lane), lane);
     }
   }
 }
@@ -313,7 +322,8 @@ __global__ void __launch_bounds__(TE_THREADS, 1) rbm_tc_epoch_kernel(const __gri
   const uint32_t bar_base = smem_u32(bars);
   auto bar = [&](int i) { return bar_base + 8u * (uint32_t)i; };
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform for the compiler, too
+  const int lane = threadIdx.x & 31;
   const int bid = (int)blockIdx.x;
   const int np = 2 * a.k + 2;                         // phases per mini-batch
   const int steps = (a.n_rows + a.B - 1) / a.B;
@@ -336,7 +346,7 @@ __global__ void __launch_bounds__(TE_THREADS, 1) rbm_tc_epoch_kernel(const __gri
   if (warp == 0 && lane == 0) {
     const CUtensorMap* maps[9] = {&a.tm_x3, &a.tm_vt3, &a.tm_hs3, &a.tm_wb3, &a.tm_wb2, &a.tm_p02, &a.tm_pk2, &a.tm_x2, &a.tm_vt2};
     for (int i = 0; i < 9; ++i) asm volatile("prefetch.tensormap [%0];" ::"l"(maps[i]) : "memory");
-    for (int i = 0; i < TE_NBARS; ++i) mbar_init(bar(i), 1);
+    for (int i = 0; i < TE_NBARS; ++i) mbar_init(bar(i), i == TE_B_ACC ? TE_NISS : 1);
     *gb_passed = 0u;
     *fin_flag = 0u;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -353,7 +363,7 @@ __global__ void __launch_bounds__(TE_THREADS, 1) rbm_tc_epoch_kernel(const __gri
 
   if (warp == 0) {
     // ======================================= TMA producer =======================================
-    if (lane == 0) {
+    if (te_elect()) {
       unsigned n_gb = 0, n_acc = 0;
       auto load_v0 = [&](int s) {   // input rows of mini-batch s for this CTA's hidden tile
         mbar_expect_tx(bar(TE_B_ACT), acth_bytes);
@@ -373,6 +383,7 @@ __global__ void __launch_bounds__(TE_THREADS, 1) rbm_tc_epoch_kernel(const __gri
             tma_load_2d(sbase + pl.off_wc + (uint32_t)(i * TE_BOX_BYTES), &a.tm_wb2, bar(TE_B_WC), v_cb * pl.vs,
                         v_kc * wc_rows + i * 256);
         }
+        te_trace(a, s, 0, 11);
         for (int p = 0; p < np; ++p) {
           const int kind = te_phase_kind(p, np);
           const bool mine = kind == TE_UPD ? has_u : (kind == TE_VIS ? has_v : has_h);
@@ -396,6 +407,14 @@ __global__ void __launch_bounds__(TE_THREADS, 1) rbm_tc_epoch_kernel(const __gri
             mbar_expect_tx(bar(TE_B_ACT), acth_bytes);
             tma_load_3d(sbase + pl.off_act, &a.tm_vt3, bar(TE_B_ACT), 0, h_rb * pl.rb_h, 0);
           }
+          if (next == TE_UPD && has_u) {             // the update's critical operand first
+            mbar_expect_tx(bar(TE_B_P1), (uint32_t)((1 + (pl.v1c_early ? 0 : pl.n4_chunks)) * TE_BOX_BYTES));
+            tma_load_2d(sbase + pl.off_p1, &a.tm_pk2, bar(TE_B_P1), u_mb * 64, 0);
+            if (!pl.v1c_early)
+              for (int ch = 0; ch < pl.n4_chunks; ++ch)
+                tma_load_2d(sbase + pl.off_v1c + (uint32_t)(ch * TE_BOX_BYTES), &a.tm_vt2, bar(TE_B_P1), u_nb * pl.n4 + ch * 64, 0);
+          }
+          te_trace(a, s, p + 1, 11);
           if (p == 0 && has_u) {                     // P0 is final: its tile of the dW contraction may come now
             mbar_expect_tx(bar(TE_B_G4P), (uint32_t)TE_BOX_BYTES);
             tma_load_2d(sbase + pl.off_g4p, &a.tm_p02, bar(TE_B_G4P), u_mb * 64, 0);
@@ -408,111 +427,102 @@ __global__ void __launch_bounds__(TE_THREADS, 1) rbm_tc_epoch_kernel(const __gri
               for (int ch = 0; ch < pl.n4_chunks; ++ch)
                 tma_load_2d(sbase + pl.off_v1c + (uint32_t)(ch * TE_BOX_BYTES), &a.tm_vt2, bar(TE_B_V0C), u_nb * pl.n4 + ch * 64, 0);
           }
-          if (next == TE_UPD) {
-            if (has_u) {
-              mbar_expect_tx(bar(TE_B_P1), (uint32_t)((1 + (pl.v1c_early ? 0 : pl.n4_chunks)) * TE_BOX_BYTES));
-              tma_load_2d(sbase + pl.off_p1, &a.tm_pk2, bar(TE_B_P1), u_mb * 64, 0);
-              if (!pl.v1c_early)
-                for (int ch = 0; ch < pl.n4_chunks; ++ch)
-                  tma_load_2d(sbase + pl.off_v1c + (uint32_t)(ch * TE_BOX_BYTES), &a.tm_vt2, bar(TE_B_P1), u_nb * pl.n4 + ch * 64, 0);
-            }
-            if ((!pl.p1_in_act || !has_u) && has_h && s + 1 < steps) load_v0(s + 1);
-          }
+          if (next == TE_UPD && (!pl.p1_in_act || !has_u) && has_h && s + 1 < steps) load_v0(s + 1);
         }
       }
     }
-  } else if (warp == 1) {
-    // ======================================= MMA issuer =======================================
-    if (lane == 0) {
-      unsigned n_act = 0;
+  } else if (warp < TE_WARP_EPI) {
+    // ======================================= MMA issuers =======================================
+    if (te_elect()) {
+      const int w = warp - 1;
+      unsigned n_act = 0, n_accw = 0;
       for (int s = 0; s < steps; ++s) {
         for (int p = 0; p < np; ++p) {
           const int kind = te_phase_kind(p, np);
+          const bool mine = kind == TE_UPD ? has_u : (kind == TE_VIS ? has_v : has_h);
+          if (!mine) continue;
+          int nk, width;
           if (kind == TE_UPD) {
-            if (!has_u) continue;
             mbar_wait(bar(TE_B_G4P), (unsigned)s & 1u);
             mbar_wait(bar(TE_B_V0C), (unsigned)s & 1u);
             mbar_wait(bar(TE_B_P1), (unsigned)s & 1u);
-            tc_fence_after();
-            te_trace(a, s, p, 0);
-            const int nk = (a.B + 15) / 16;          // K = batch rows (zero rows beyond the valid ones)
-            const uint32_t nacc = (uint32_t)te_nacc(nk, pl.n4);
-            uint32_t mc = 0;                         // MMAs issued: accumulator mc % nacc, first visit overwrites
-#pragma unroll 1
-            for (int pass = 0; pass < 2; ++pass) {
-              const uint32_t idesc = make_idesc(64, pl.n4, 1, 1, pass, fmt, fmt);
-              // MN-major operands: 16 k rows = 2048 bytes per MMA; the descriptors advance by 2048 >> 4 in their address field
-              uint64_t da = make_smem_desc(sbase + (pass == 0 ? pl.off_g4p : pl.off_p1), TE_BOX_BYTES, 1024);
-              uint64_t db = make_smem_desc(sbase + (pass == 0 ? pl.off_v0c : pl.off_v1c), TE_BOX_BYTES, 1024);
-#pragma unroll 4
-              for (int kk = 0; kk < nk; ++kk, ++mc) {
-                tc_mma_bf16(tmem_base + (mc & (nacc - 1)) * (uint32_t)pl.n4, da, db, idesc, mc >= nacc);
-                da += 128; db += 128;
-              }
-            }
-            tc_commit(bar(TE_B_ACC));
+            nk = (a.B + 15) / 16;                    // K = batch rows (zero rows beyond the valid ones)
+            width = pl.n4;
           } else if (kind == TE_VIS) {
-            if (!has_v) continue;
             if (p == 1) mbar_wait(bar(TE_B_WC), (unsigned)s & 1u);
             mbar_wait(bar(TE_B_ACT), n_act & 1u);
             ++n_act;
-            tc_fence_after();
-            te_trace(a, s, p, 0);
-            const int krows = min(wc_rows, a.H - v_kc * wc_rows);   // hidden units of this chunk (rows beyond H are zero-filled)
-            const int nk = (krows + 15) / 16;
-            const uint32_t idesc = make_idesc(64, pl.vs, 0, 1, 0, fmt, fmt);
-            // A (K-major): 4 MMAs of 32 bytes inside a 64-wide slab, slabs rb_v*128 bytes apart; B (MN-major): 2048 bytes per MMA
-            uint64_t da = make_smem_desc(sbase + pl.off_act, 16, 1024), db = make_smem_desc(sbase + pl.off_wc, TE_BOX_BYTES, 1024);
-            const uint64_t a_slab = (uint64_t)((pl.rb_v * 128) >> 4);
-            const uint32_t nacc = (uint32_t)te_nacc(nk, pl.vs);
-            int kk = 0;
-#pragma unroll 1
-            for (; kk + 4 <= nk; kk += 4) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                tc_mma_bf16(tmem_base + ((uint32_t)j & (nacc - 1)) * (uint32_t)pl.vs, da + (uint64_t)(2 * j), db + (uint64_t)(128 * j), idesc,
-                            (uint32_t)(kk + j) >= nacc);
-              da += a_slab; db += 512;
-            }
-            for (int j = 0; kk < nk; ++kk, ++j)
-              tc_mma_bf16(tmem_base + ((uint32_t)j & (nacc - 1)) * (uint32_t)pl.vs, da + (uint64_t)(2 * j), db + (uint64_t)(128 * j), idesc,
-                          (uint32_t)kk >= nacc);
-            tc_commit(bar(TE_B_ACC));
+            nk = (min(wc_rows, a.H - v_kc * wc_rows) + 15) / 16;   // hidden units of this chunk (rows beyond H are zero-filled)
+            width = pl.vs;
           } else {
-            if (!has_h) continue;
             if (p == 0) mbar_wait(bar(TE_B_WR), (unsigned)s & 1u);
             mbar_wait(bar(TE_B_ACT), n_act & 1u);
             ++n_act;
-            tc_fence_after();
-            te_trace(a, s, p, 0);
-            const int nk = (a.V + 15) / 16;
-            const uint32_t idesc = make_idesc(64, pl.hs, 0, 0, 0, fmt, fmt);
-            uint64_t da = make_smem_desc(sbase + pl.off_act, 16, 1024), db = make_smem_desc(sbase + pl.off_wr, 16, 1024);
-            const uint64_t a_slab = (uint64_t)((pl.rb_h * 128) >> 4), b_slab = (uint64_t)((pl.hs * 128) >> 4);
-            const uint32_t nacc = (uint32_t)te_nacc(nk, pl.hs);
-            int kk = 0;
-#pragma unroll 1
-            for (; kk + 4 <= nk; kk += 4) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                tc_mma_bf16(tmem_base + ((uint32_t)j & (nacc - 1)) * (uint32_t)pl.hs, da + (uint64_t)(2 * j), db + (uint64_t)(2 * j), idesc,
-                            (uint32_t)(kk + j) >= nacc);
-              da += a_slab; db += b_slab;
-            }
-            for (int j = 0; kk < nk; ++kk, ++j)
-              tc_mma_bf16(tmem_base + ((uint32_t)j & (nacc - 1)) * (uint32_t)pl.hs, da + (uint64_t)(2 * j), db + (uint64_t)(2 * j), idesc,
-                          (uint32_t)kk >= nacc);
-            tc_commit(bar(TE_B_ACC));
+            nk = (a.V + 15) / 16;
+            width = pl.hs;
           }
+          tc_fence_after();
+          if (w == 0) te_trace(a, s, p, 0);
+          const int upp = (nk + 3) >> 2;                               // blocks of 4 k-steps per pass
+          const int nunits = kind == TE_UPD ? 2 * upp : upp;
+          const int per = te_units_per_issuer(nunits);
+          const int u0 = w * per, u1 = min(nunits, u0 + per);
+          const uint32_t tmem_d = tmem_base + (uint32_t)(w * width);
+          // descriptor bases and their increments (address field: bytes >> 4) per block of 4 k-steps / per k-step
+          uint64_t dA, dB, dA1 = 0, dB1 = 0;
+          uint32_t ua, ub, ia, ib, idesc, idesc1 = 0;
+          if (kind == TE_UPD) {                      // both operands MN-major: 16 k rows = 2048 bytes per k-step
+            idesc = make_idesc(64, width, 1, 1, 0, fmt, fmt);
+            idesc1 = make_idesc(64, width, 1, 1, 1, fmt, fmt);
+            dA = make_smem_desc(sbase + pl.off_g4p, TE_BOX_BYTES, 1024); dB = make_smem_desc(sbase + pl.off_v0c, TE_BOX_BYTES, 1024);
+            dA1 = make_smem_desc(sbase + pl.off_p1, TE_BOX_BYTES, 1024); dB1 = make_smem_desc(sbase + pl.off_v1c, TE_BOX_BYTES, 1024);
+            ua = 512; ub = 512; ia = 128; ib = 128;
+          } else if (kind == TE_VIS) {               // A K-major (32 bytes per k-step inside a slab), B MN-major
+            idesc = make_idesc(64, width, 0, 1, 0, fmt, fmt);
+            dA = make_smem_desc(sbase + pl.off_act, 16, 1024); dB = make_smem_desc(sbase + pl.off_wc, TE_BOX_BYTES, 1024);
+            ua = (uint32_t)(pl.rb_v * 128) >> 4; ub = 512; ia = 2; ib = 128;
+          } else {                                   // both K-major
+            idesc = make_idesc(64, width, 0, 0, 0, fmt, fmt);
+            dA = make_smem_desc(sbase + pl.off_act, 16, 1024); dB = make_smem_desc(sbase + pl.off_wr, 16, 1024);
+            ua = (uint32_t)(pl.rb_h * 128) >> 4; ub = (uint32_t)(pl.hs * 128) >> 4; ia = 2; ib = 2;
+          }
+          uint32_t accumulate = 0;
+#pragma unroll 1
+          for (int u = u0; u < u1; ++u) {
+            const int pass = u >= upp ? 1 : 0, us = u - pass * upp;
+            const int ks = min(4, nk - 4 * us);
+            const uint64_t da = (pass ? dA1 : dA) + (uint64_t)(ua * (uint32_t)us), db = (pass ? dB1 : dB) + (uint64_t)(ub * (uint32_t)us);
+            const uint32_t id = pass ? idesc1 : idesc;
+            if (ks == 4) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                tc_mma_bf16(tmem_d, da + (uint64_t)(ia * j), db + (uint64_t)(ib * j), id, accumulate);
+                accumulate = 1;
+              }
+            } else {
+              for (int j = 0; j < ks; ++j) {
+                tc_mma_bf16(tmem_d, da + (uint64_t)(ia * j), db + (uint64_t)(ib * j), id, accumulate);
+                accumulate = 1;
+              }
+            }
+          }
+          if (w == 0) te_trace(a, s, p, 10);
+          tc_commit(bar(TE_B_ACC));   // one arrival per issuer, when its MMAs (if any) have completed
+          if (w == 0 && a.trace != nullptr) {
+            mbar_wait(bar(TE_B_ACC), n_accw & 1u);
+            te_trace(a, s, p, 6);
+          }
+          ++n_accw;
         }
       }
     }
   } else {
     // ============================ epilogue warps (+ grid barrier) ============================
     const int q = warp & 3;                      // TMEM lane quarter this warp may read
-    const int g = (warp - 2) >> 2;               // column group: chunks g, g + 4, ...
-    const int tid_e = (int)threadIdx.x - 64;
-    const int rloc = q * 16 + lane;              // UMMA M = 64: tile row r lives in lane 32*(r/16) + r%16
+    const int g = (warp - TE_WARP_EPI) >> 2;     // column group: chunks g, g + 4, ...
+    const int tid_e = (int)threadIdx.x - 32 * TE_WARP_EPI;
+    const int rloc = q * 16 + (lane & 15);       // UMMA M = 64: tile row r lives in lane 32*(r/16) + r%16 ...
+    const int coff = (lane >> 4) * 4;            // ... and its 8-column chunk is split over lanes l (0-3) and l + 16 (4-7)
     const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16);
     uint32_t epoch = a.rng.epoch + (a.rng.epoch_ptr ? *a.rng.epoch_ptr : 0u);
     unsigned n_acc = 0, n_bar = 0;
@@ -526,21 +536,22 @@ __global__ void __launch_bounds__(TE_THREADS, 1) rbm_tc_epoch_kernel(const __gri
           // The master segments, the biases and their statistics are requested BEFORE the accumulator is ready
           // (the statistics are final since the last barrier), so their L2 latency hides behind the MMAs.
           const int m = u_mb * 64 + rloc;
-          const int chunks = pl.n4 >> 3;           // <= 16: at most 4 chunks per thread
-          const int nacc = te_nacc((a.B + 15) / 16, pl.n4);
-          const bool row_ok = lane < 16 && m < a.H;
+          const int chunks = pl.n4 >> 3;           // <= 16: at most 4 chunks per warp
+          const int nacc = te_nacc(2 * (((a.B + 15) / 16 + 3) >> 2));
+          const bool row_ok = m < a.H;
           float* wrow = a.W + (size_t)m * (size_t)a.ldw;
-          float wpre[4][8];
+          float wpre[4][4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const int n0 = u_nb * pl.n4 + (g + 4 * i) * 8;
-            if (g + 4 * i < chunks && n0 < a.V && row_ok) te_load8_cg(wrow, n0, a.V, wpre[i]);
+            const int n0 = u_nb * pl.n4 + (g + 4 * i) * 8 + coff;
+            if (g + 4 * i < chunks && n0 < a.V && row_ok) te_load4_cg(wrow, n0, a.V, wpre[i]);
           }
           const int hc = u_mb * 64 + tid_e, vb = u_nb * pl.n4 + tid_e;
           const bool own_c = u_nb == 0 && tid_e < 64 && hc < a.H, own_b = u_mb == 0 && tid_e < pl.n4 && vb < a.V;
           float cval = 0.f, cst = 0.f, bval = 0.f, bst = 0.f;
           if (own_c) { cval = __ldcg(a.c + hc); cst = te_stat_take(a.stats, hc); }
           if (own_b) { bval = __ldcg(a.b + vb); bst = te_stat_take(a.stats + a.H, vb); }
+          if (tid_e == 0) te_trace(a, s, p, 7);
           mbar_wait(bar(TE_B_ACC), n_acc & 1u);
           ++n_acc;
           tc_fence_after();
@@ -548,17 +559,19 @@ __global__ void __launch_bounds__(TE_THREADS, 1) rbm_tc_epoch_kernel(const __gri
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int ch = g + 4 * i;
-            const int n0 = u_nb * pl.n4 + ch * 8;
-            if (ch < chunks && n0 < a.V) {         // warp-uniform
-              float acc[8];
-              te_ld_acc(tq + (uint32_t)(ch * 8), nacc, pl.n4, acc);
-              if (row_ok) {
-                float w[8];
+            if (ch < chunks && u_nb * pl.n4 + ch * 8 < a.V) {         // warp-uniform
+              const int n0 = u_nb * pl.n4 + ch * 8 + coff;
+              float acc[4];
+              te_ld_acc4(tq + (uint32_t)(ch * 8), nacc, pl.n4, lane, acc);
+              if (tid_e == 0 && i == 0) te_trace(a, s, p, 8);
+              if (row_ok && n0 < a.V) {
+                float w[4];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) w[j] = fmaf(a.scale, acc[j], wpre[i][j]);
-                te_store8_f32(wrow, n0, a.V, w);
-                te_store8_h(a.Wb, m, n0, a.V, w);
+                for (int j = 0; j < 4; ++j) w[j] = fmaf(a.scale, acc[j], wpre[i][j]);
+                te_store4_f32(wrow, n0, a.V, w);
+                te_store4_h(a.Wb, m, n0, a.V, w);
               }
+              if (tid_e == 0 && i == 0) te_trace(a, s, p, 9);
             }
           }
           // ---- b, c += scale * statistics, by the one owner thread of every unit (:118-119) ----
@@ -573,17 +586,17 @@ __global__ void __launch_bounds__(TE_THREADS, 1) rbm_tc_epoch_kernel(const __gri
           const int N = hid ? a.H : a.V;
           const int col0 = hid ? h_cb * pl.hs : v_cb * pl.vs;
           const int grow = (hid ? h_rb * pl.rb_h : v_rb * pl.rb_v) + rloc;      // row inside the mini-batch
-          const bool lane_ok = lane < 16 && rloc < rb && grow < a.B;
+          const bool lane_ok = rloc < rb && grow < a.B;
           const bool row_ok = lane_ok && grow < valid;
-          const int nacc = hid ? te_nacc((a.V + 15) / 16, width)
-                               : te_nacc((min(wc_rows, a.H - v_kc * wc_rows) + 15) / 16, width);
-          const int chunks = width >> 3;             // <= 8: at most 2 chunks per thread
-          float bias[2][8], aux[2][8];
+          const int nacc = te_nacc((((hid ? a.V : min(wc_rows, a.H - v_kc * wc_rows)) + 15) / 16 + 3) >> 2);
+          const int chunks = width >> 3;             // <= 8: at most 2 chunks per warp
+          float bias[2][4], aux[2][4];
 #pragma unroll
           for (int i = 0; i < 2; ++i) {
-            const int n0 = col0 + (g + 4 * i) * 8;
+            const int n0 = col0 + (g + 4 * i) * 8 + coff;
             if (g + 4 * i < chunks && n0 < N) te_act_prefetch(a, hid, kind, t, epoch, s, grow, row_ok, n0, bias[i], aux[i]);
           }
+          if (tid_e == 0) te_trace(a, s, p, 7);
           mbar_wait(bar(TE_B_ACC), n_acc & 1u);
           ++n_acc;
           tc_fence_after();
@@ -596,12 +609,9 @@ __global__ void __launch_bounds__(TE_THREADS, 1) rbm_tc_epoch_kernel(const __gri
             for (int i = 0; i < 2; ++i) {
               const int ch = g + 4 * i;
               if (ch < chunks) {
-                float v[8];
-                te_ld_acc(tq + (uint32_t)(ch * 8), nacc, width, v);
-                if (lane < 16) {
-                  __stcg(reinterpret_cast<float4*>(part + ch * 8), make_float4(v[0], v[1], v[2], v[3]));
-                  __stcg(reinterpret_cast<float4*>(part + ch * 8) + 1, make_float4(v[4], v[5], v[6], v[7]));
-                }
+                float v[4];
+                te_ld_acc4(tq + (uint32_t)(ch * 8), nacc, width, lane, v);
+                __stcg(reinterpret_cast<float4*>(part + ch * 8 + coff), make_float4(v[0], v[1], v[2], v[3]));
               }
             }
             asm volatile("bar.sync 1, %0;" ::"n"(TE_EPI_THREADS) : "memory");
@@ -617,18 +627,14 @@ __global__ void __launch_bounds__(TE_THREADS, 1) rbm_tc_epoch_kernel(const __gri
 #pragma unroll
               for (int i = 0; i < 2; ++i) {
                 const int ch = g + 4 * i;
-                const int n0 = col0 + ch * 8;
-                if (ch < chunks && n0 < N) {
-                  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                  if (lane < 16) {
-                    for (int kc = 0; kc < pl.ksplit; ++kc) {          // fixed order: deterministic sums
-                      const float4 x = __ldcg(reinterpret_cast<const float4*>(base + (size_t)kc * 4096 + ch * 8));
-                      const float4 y = __ldcg(reinterpret_cast<const float4*>(base + (size_t)kc * 4096 + ch * 8) + 1);
-                      acc[0] += x.x; acc[1] += x.y; acc[2] += x.z; acc[3] += x.w;
-                      acc[4] += y.x; acc[5] += y.y; acc[6] += y.z; acc[7] += y.w;
-                    }
+                const int n0 = col0 + ch * 8 + coff;
+                if (ch < chunks && col0 + ch * 8 < N) {     // warp-uniform
+                  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                  for (int kc = 0; kc < pl.ksplit; ++kc) {            // fixed order: deterministic sums
+                    const float4 x = __ldcg(reinterpret_cast<const float4*>(base + (size_t)kc * 4096 + ch * 8 + coff));
+                    acc[0] += x.x; acc[1] += x.y; acc[2] += x.z; acc[3] += x.w;
                   }
-                  te_act_finish(a, hid, kind, t, grow, lane_ok, row_ok, n0, acc, bias[i], aux[i], lane);
+                  te_act_finish(a, hid, kind, t, grow, lane_ok && n0 < N, row_ok && n0 < N, n0, acc, bias[i], aux[i], lane);
                 }
               }
             }
@@ -636,11 +642,13 @@ __global__ void __launch_bounds__(TE_THREADS, 1) rbm_tc_epoch_kernel(const __gri
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
               const int ch = g + 4 * i;
-              const int n0 = col0 + ch * 8;
-              if (ch < chunks && n0 < N) {         // warp-uniform
-                float acc[8];
-                te_ld_acc(tq + (uint32_t)(ch * 8), nacc, width, acc);
-                te_act_finish(a, hid, kind, t, grow, lane_ok, row_ok, n0, acc, bias[i], aux[i], lane);
+              const int n0 = col0 + ch * 8 + coff;
+              if (ch < chunks && col0 + ch * 8 < N) {       // warp-uniform
+                float acc[4];
+                te_ld_acc4(tq + (uint32_t)(ch * 8), nacc, width, lane, acc);
+                if (tid_e == 0 && i == 0) te_trace(a, s, p, 8);
+                te_act_finish(a, hid, kind, t, grow, lane_ok && n0 < N, row_ok && n0 < N, n0, acc, bias[i], aux[i], lane);
+                if (tid_e == 0 && i == 0) te_trace(a, s, p, 9);
               }
             }
           }
@@ -651,11 +659,13 @@ __global__ void __launch_bounds__(TE_THREADS, 1) rbm_tc_epoch_kernel(const __gri
         // ---- end of the phase: this CTA's outputs are complete -> grid barrier ----
         asm volatile("bar.sync 1, %0;" ::"n"(TE_EPI_THREADS) : "memory");
         if (tid_e == 0) {
+          te_trace(a, s, p, 3);
           te_grid_arrive(a.ctl);
+          te_trace(a, s, p, 4);
           ++n_bar;
           te_grid_wait(a.ctl, n_bar * gridDim.x);
           te_publish(gb_passed, n_bar);
-          te_trace(a, s, p, 3);
+          te_trace(a, s, p, 5);
         }
         // every epilogue thread passes the barrier: what the next phase prefetches (biases, statistics) is other CTAs' output
         asm volatile("bar.sync 1, %0;" ::"n"(TE_EPI_THREADS) : "memory");

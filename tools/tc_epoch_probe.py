@@ -60,25 +60,29 @@ def main():
         if not plan:
             continue
         ctas = plan["ctas"]
-        tr = torch.zeros(ctas * 8 * 32, dtype=torch.int64, device="cuda")
+        tr = torch.zeros(ctas * 8 * 128, dtype=torch.int64, device="cuda")
         lib.dbn_debug_set_trace(C.c_void_p(tr.data_ptr()))
         L.check(lib.dbn_rbm_fit_epoch(E.stream_ptr(), C.byref(a), n, bs))
         torch.cuda.synchronize()
         lib.dbn_debug_set_trace(None)
-        t = tr.cpu().numpy().reshape(ctas, 8, 8, 4).astype(np.float64)
+        t = tr.cpu().numpy().reshape(ctas, 8, 8, 16).astype(np.float64)
         names = ["v->h + sample", "h->v", "v->h (k)", "dW + update"]
         tiles = [plan["hid_tiles"], plan["vis_tiles"], plan["hid_tiles"], plan["dw_tiles"]]
-        print("   phase              tiles   operands   mma+commit   epilogue   barrier   (cycles, mean over CTAs, steps 2..7)")
+        print("   cycles, mean over the CTAs with a tile, steps 2..7; columns: loads issued after the barrier | operands landed | MMAs issued |"
+              " MMAs complete | (prefetch done) | accumulator seen by the epilogue | first chunk in registers | first chunk stored |"
+              " epilogue done | CTA joined | release + arrive | barrier passed (mean / min over CTAs)")
         tot = 0.0
         for p in range(4):
-            sel = t[:tiles[p], 2:8]
-            prev_bar = t[:tiles[p], 2:8, (p - 1) % 4, 3] if p > 0 else t[:tiles[p], 1:7, 3, 3]
-            ops = (sel[:, :, p, 0] - prev_bar).mean()
-            mma = (sel[:, :, p, 1] - sel[:, :, p, 0]).mean()
-            epi = (sel[:, :, p, 2] - sel[:, :, p, 1]).mean()
-            bar = (sel[:, :, p, 3] - sel[:, :, p, 2]).mean()
-            tot += ops + mma + epi + bar
-            print("   %-18s %5d %10.0f %12.0f %10.0f %9.0f" % (names[p], tiles[p], ops, mma, epi, bar))
+            sel = t[:tiles[p], 2:8, p]
+            prev_bar = t[:tiles[p], 2:8, p - 1, 5] if p > 0 else t[:tiles[p], 1:7, 3, 5]
+            d = lambda x, y: float((x - y).mean())
+            cols = [d(sel[..., 11], prev_bar) if p > 0 else float("nan"), d(sel[..., 0], prev_bar), d(sel[..., 10], sel[..., 0]), d(sel[..., 6], sel[..., 10]),
+                    d(sel[..., 7], prev_bar), d(sel[..., 1], sel[..., 6]), d(sel[..., 8], sel[..., 1]), d(sel[..., 9], sel[..., 8]),
+                    d(sel[..., 2], sel[..., 9]), d(sel[..., 3], sel[..., 2]), d(sel[..., 4], sel[..., 3])]
+            bar = sel[..., 5] - sel[..., 4]
+            tot += float((sel[..., 5] - prev_bar).mean())
+            print("   %-14s %4d | %5.0f | %5.0f | %5.0f | %5.0f | (%5.0f) | %5.0f | %5.0f | %5.0f | %5.0f | %5.0f | %5.0f | %5.0f / %.0f" %
+                  tuple([names[p], tiles[p]] + cols + [float(bar.mean()), float(bar.min(axis=0).mean())]))
         print("   sum %.0f cycles = %.2f us at 1.965 GHz" % (tot, tot / 1965.0))
 
 
