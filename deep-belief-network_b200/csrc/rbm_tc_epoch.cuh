@@ -138,10 +138,25 @@ __device__ __forceinline__ void te_ld_acc4(uint32_t taddr, int nacc, int width, 
   }
 }
 
-__device__ __forceinline__ void te_fail(TeCtl* ctl, int code) {
+__device__ __noinline__ void te_fail(TeCtl* ctl, int code) {
   atomicExch(&ctl->error, (unsigned)code);
   printf("dbn_b200: persistent epoch kernel gave up (code %d, block %d thread %d)\n", code, blockIdx.x, threadIdx.x);
   __trap();
+}
+
+// bounded wait (a protocol bug traps instead of hanging the GPU); the failure path is out of line
+__device__ __forceinline__ void te_mbar_wait(TeCtl* ctl, uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!done && spin > (1u << 24)) te_fail(ctl, 3);
+  }
 }
 
 // ---- grid barrier: one monotonic arrival counter in L2 ---------------------------------------------------
@@ -168,8 +183,10 @@ __device__ __forceinline__ void te_publish(volatile unsigned* slot, unsigned v) 
   *slot = v;
 }
 __device__ __forceinline__ void te_await(TeCtl* ctl, volatile unsigned* slot, unsigned v) {
-  for (unsigned spin = 0; *slot < v; ++spin)
-    if (spin > (1u << 26)) te_fail(ctl, 2);
+  for (unsigned spin = 0; *slot < v; ++spin) {
+    __nanosleep(20);      // a tight shared-memory spin would take issue slots from the epilogue warps on this scheduler
+    if (spin > (1u << 24)) te_fail(ctl, 2);
+  }
   __threadfence_block();
 }
 
@@ -371,11 +388,13 @@ __global__ void __launch_bounds__(TE_THREADS, 1) rbm_tc_epoch_kernel(const __gri
       };
       for (int s = 0; s < steps; ++s) {
         const int r0 = a.row0 + s * a.B;
-        // the weights of the step (the barrier that ended the previous step has been passed)
-        if (has_h) {
+        // (the operands on the critical path -- what the phase behind a barrier waits for: activation rows, P1, the
+        //  W row slice of the next step -- are requested by the epilogue thread that watches the barrier open; this
+        //  warp fetches everything that can come early)
+        if (has_h && s == 0) {
           mbar_expect_tx(bar(TE_B_WR), wr_bytes);
           tma_load_3d(sbase + pl.off_wr, &a.tm_wb3, bar(TE_B_WR), 0, h_cb * pl.hs, 0);
-          if (s == 0) load_v0(0);
+          load_v0(0);
         }
         if (has_v) {
           mbar_expect_tx(bar(TE_B_WC), (uint32_t)(wc_boxes * wc_box_rows * 128));
@@ -383,7 +402,6 @@ __global__ void __launch_bounds__(TE_THREADS, 1) rbm_tc_epoch_kernel(const __gri
             tma_load_2d(sbase + pl.off_wc + (uint32_t)(i * TE_BOX_BYTES), &a.tm_wb2, bar(TE_B_WC), v_cb * pl.vs,
                         v_kc * wc_rows + i * 256);
         }
-        te_trace(a, s, 0, 11);
         for (int p = 0; p < np; ++p) {
           const int kind = te_phase_kind(p, np);
           const bool mine = kind == TE_UPD ? has_u : (kind == TE_VIS ? has_v : has_h);
@@ -391,7 +409,7 @@ __global__ void __launch_bounds__(TE_THREADS, 1) rbm_tc_epoch_kernel(const __gri
           if (p == np - 1) {
             // P1 sits in the activation buffer: the next input tile follows once the update's MMAs have read it
             if (pl.p1_in_act && has_u && has_h && s + 1 < steps) {
-              mbar_wait(bar(TE_B_ACC), (n_acc - 1) & 1u);
+              te_mbar_wait(a.ctl, bar(TE_B_ACC), (n_acc - 1) & 1u);
               load_v0(s + 1);
             }
             if (s + 1 == steps) break;
@@ -399,22 +417,6 @@ __global__ void __launch_bounds__(TE_THREADS, 1) rbm_tc_epoch_kernel(const __gri
           te_await(a.ctl, gb_passed, ++n_gb);        // every CTA has finished phase p: its outputs are visible
           if (p == np - 1) break;
           const int next = te_phase_kind(p + 1, np);
-          if (next == TE_VIS && has_v) {
-            mbar_expect_tx(bar(TE_B_ACT), actv_bytes);
-            tma_load_3d(sbase + pl.off_act, &a.tm_hs3, bar(TE_B_ACT), 0, v_rb * pl.rb_v, v_kc * pl.kc_slabs);
-          }
-          if ((next == TE_HID || next == TE_HIDK) && has_h) {
-            mbar_expect_tx(bar(TE_B_ACT), acth_bytes);
-            tma_load_3d(sbase + pl.off_act, &a.tm_vt3, bar(TE_B_ACT), 0, h_rb * pl.rb_h, 0);
-          }
-          if (next == TE_UPD && has_u) {             // the update's critical operand first
-            mbar_expect_tx(bar(TE_B_P1), (uint32_t)((1 + (pl.v1c_early ? 0 : pl.n4_chunks)) * TE_BOX_BYTES));
-            tma_load_2d(sbase + pl.off_p1, &a.tm_pk2, bar(TE_B_P1), u_mb * 64, 0);
-            if (!pl.v1c_early)
-              for (int ch = 0; ch < pl.n4_chunks; ++ch)
-                tma_load_2d(sbase + pl.off_v1c + (uint32_t)(ch * TE_BOX_BYTES), &a.tm_vt2, bar(TE_B_P1), u_nb * pl.n4 + ch * 64, 0);
-          }
-          te_trace(a, s, p + 1, 11);
           if (p == 0 && has_u) {                     // P0 is final: its tile of the dW contraction may come now
             mbar_expect_tx(bar(TE_B_G4P), (uint32_t)TE_BOX_BYTES);
             tma_load_2d(sbase + pl.off_g4p, &a.tm_p02, bar(TE_B_G4P), u_mb * 64, 0);
@@ -443,20 +445,20 @@ __global__ void __launch_bounds__(TE_THREADS, 1) rbm_tc_epoch_kernel(const __gri
           if (!mine) continue;
           int nk, width;
           if (kind == TE_UPD) {
-            mbar_wait(bar(TE_B_G4P), (unsigned)s & 1u);
-            mbar_wait(bar(TE_B_V0C), (unsigned)s & 1u);
-            mbar_wait(bar(TE_B_P1), (unsigned)s & 1u);
+            te_mbar_wait(a.ctl, bar(TE_B_G4P), (unsigned)s & 1u);
+            te_mbar_wait(a.ctl, bar(TE_B_V0C), (unsigned)s & 1u);
+            te_mbar_wait(a.ctl, bar(TE_B_P1), (unsigned)s & 1u);
             nk = (a.B + 15) / 16;                    // K = batch rows (zero rows beyond the valid ones)
             width = pl.n4;
           } else if (kind == TE_VIS) {
-            if (p == 1) mbar_wait(bar(TE_B_WC), (unsigned)s & 1u);
-            mbar_wait(bar(TE_B_ACT), n_act & 1u);
+            if (p == 1) te_mbar_wait(a.ctl, bar(TE_B_WC), (unsigned)s & 1u);
+            te_mbar_wait(a.ctl, bar(TE_B_ACT), n_act & 1u);
             ++n_act;
             nk = (min(wc_rows, a.H - v_kc * wc_rows) + 15) / 16;   // hidden units of this chunk (rows beyond H are zero-filled)
             width = pl.vs;
           } else {
-            if (p == 0) mbar_wait(bar(TE_B_WR), (unsigned)s & 1u);
-            mbar_wait(bar(TE_B_ACT), n_act & 1u);
+            if (p == 0) te_mbar_wait(a.ctl, bar(TE_B_WR), (unsigned)s & 1u);
+            te_mbar_wait(a.ctl, bar(TE_B_ACT), n_act & 1u);
             ++n_act;
             nk = (a.V + 15) / 16;
             width = pl.hs;
@@ -509,7 +511,7 @@ __global__ void __launch_bounds__(TE_THREADS, 1) rbm_tc_epoch_kernel(const __gri
           if (w == 0) te_trace(a, s, p, 10);
           tc_commit(bar(TE_B_ACC));   // one arrival per issuer, when its MMAs (if any) have completed
           if (w == 0 && a.trace != nullptr) {
-            mbar_wait(bar(TE_B_ACC), n_accw & 1u);
+            te_mbar_wait(a.ctl, bar(TE_B_ACC), n_accw & 1u);
             te_trace(a, s, p, 6);
           }
           ++n_accw;
@@ -552,7 +554,7 @@ __global__ void __launch_bounds__(TE_THREADS, 1) rbm_tc_epoch_kernel(const __gri
           if (own_c) { cval = __ldcg(a.c + hc); cst = te_stat_take(a.stats, hc); }
           if (own_b) { bval = __ldcg(a.b + vb); bst = te_stat_take(a.stats + a.H, vb); }
           if (tid_e == 0) te_trace(a, s, p, 7);
-          mbar_wait(bar(TE_B_ACC), n_acc & 1u);
+          te_mbar_wait(a.ctl, bar(TE_B_ACC), n_acc & 1u);
           ++n_acc;
           tc_fence_after();
           if (tid_e == 0) te_trace(a, s, p, 1);
@@ -597,7 +599,7 @@ __global__ void __launch_bounds__(TE_THREADS, 1) rbm_tc_epoch_kernel(const __gri
             if (g + 4 * i < chunks && n0 < N) te_act_prefetch(a, hid, kind, t, epoch, s, grow, row_ok, n0, bias[i], aux[i]);
           }
           if (tid_e == 0) te_trace(a, s, p, 7);
-          mbar_wait(bar(TE_B_ACC), n_acc & 1u);
+          te_mbar_wait(a.ctl, bar(TE_B_ACC), n_acc & 1u);
           ++n_acc;
           tc_fence_after();
           if (tid_e == 0) te_trace(a, s, p, 1);
@@ -664,8 +666,32 @@ __global__ void __launch_bounds__(TE_THREADS, 1) rbm_tc_epoch_kernel(const __gri
           te_trace(a, s, p, 4);
           ++n_bar;
           te_grid_wait(a.ctl, n_bar * gridDim.x);
-          te_publish(gb_passed, n_bar);
           te_trace(a, s, p, 5);
+          // the barrier is open: request what the next phase waits for, right here (its buffer is free -- this CTA's
+          // MMAs of the phase that used it completed before its epilogue ran)
+          if (p < np - 1) {
+            const int next = te_phase_kind(p + 1, np);
+            if (next == TE_VIS && has_v) {
+              mbar_expect_tx(bar(TE_B_ACT), actv_bytes);
+              tma_load_3d(sbase + pl.off_act, &a.tm_hs3, bar(TE_B_ACT), 0, v_rb * pl.rb_v, v_kc * pl.kc_slabs);
+            }
+            if ((next == TE_HID || next == TE_HIDK) && has_h) {
+              mbar_expect_tx(bar(TE_B_ACT), acth_bytes);
+              tma_load_3d(sbase + pl.off_act, &a.tm_vt3, bar(TE_B_ACT), 0, h_rb * pl.rb_h, 0);
+            }
+            if (next == TE_UPD && has_u) {
+              mbar_expect_tx(bar(TE_B_P1), (uint32_t)((1 + (pl.v1c_early ? 0 : pl.n4_chunks)) * TE_BOX_BYTES));
+              tma_load_2d(sbase + pl.off_p1, &a.tm_pk2, bar(TE_B_P1), u_mb * 64, 0);
+              if (!pl.v1c_early)
+                for (int ch = 0; ch < pl.n4_chunks; ++ch)
+                  tma_load_2d(sbase + pl.off_v1c + (uint32_t)(ch * TE_BOX_BYTES), &a.tm_vt2, bar(TE_B_P1), u_nb * pl.n4 + ch * 64, 0);
+            }
+          } else if (has_h) {                        // end of the step: the updated W row slice of the next one
+            mbar_expect_tx(bar(TE_B_WR), wr_bytes);
+            tma_load_3d(sbase + pl.off_wr, &a.tm_wb3, bar(TE_B_WR), 0, h_cb * pl.hs, 0);
+          }
+          te_trace(a, s, p + 1 < np ? p + 1 : 0, 11);   // (slot 11 of the end-of-step barrier lands in the same step's phase 0: ignored)
+          te_publish(gb_passed, n_bar);
         }
         // every epilogue thread passes the barrier: what the next phase prefetches (biases, statistics) is other CTAs' output
         asm volatile("bar.sync 1, %0;" ::"n"(TE_EPI_THREADS) : "memory");

@@ -77,11 +77,15 @@ def main():
                 group.close()
             results[mode] = (Wd, bd, cd, replicas_identical((Wd, bd, cd, shadow), dev))
         if rank == 0:
+            # the tiled kernels on both sides: this check is about the exchange (the persistent epoch kernel of small
+            # layers sums in another order -- its parity tests are tests/test_gpu_tc_epoch.py, tolerance 2e-3)
             single = E.DeviceRbm(W0, b0, c0, "sigmoid", prec, dev)
+            prev = layer.lib.dbn_set_tc_epoch(0)
             r1 = E.RbmEpochRunner(single, Xd, bs, 1, 0.05, 4242)
             for o in orders:
                 r1.run(order=o)
             torch.cuda.synchronize()
+            layer.lib.dbn_set_tc_epoch(prev)
             Ws, bs_, cs = single.export()
             upd = np.linalg.norm(Ws - W0)
             tol = 1e-5 if prec == "fp32" else 1e-4   # identical samples; fp32 partial sums in a different order
