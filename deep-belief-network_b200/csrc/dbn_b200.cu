@@ -478,6 +478,7 @@ static int rbm_fit_epoch_tc(cudaStream_t st, const dbn_rbm_step_args* t, int n_r
   a.rng = t->rng;
   a.ctl = ws.ctl; a.scratch = ws.scratch;
   a.trace = umma_trace_ptr();
+  { const char* e = getenv("DBN_B200_TE_EXP"); a.exp = e ? atoi(e) : 0; }
   const TePlan& pl = a.pl;
   const uint64_t xrows = (uint64_t)t->row0 + (uint64_t)n_rows;
   // K-major operands: one copy brings every 64-wide k-slab of a tile's rows

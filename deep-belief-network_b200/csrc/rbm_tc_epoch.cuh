@@ -79,6 +79,7 @@ struct TeArgs {
   dbn_rng rng;
   TeCtl* ctl;
   float* scratch;
+  int exp;                     // debug (DBN_B200_TE_EXP): experiment switches, 0 in production
   long long* trace;            // debug (dbn_debug_set_trace): [cta][step < 8][phase < 8][16] clock64 stamps: 0 operands landed
                                // (issuer 0), 1 accumulator ready (epilogue thread 0), 2 its epilogue done, 3 CTA done, 4 arrived
                                // at the grid barrier, 5 barrier passed, 6 MMAs complete (issuer 0), 7 prefetch done, 8 first
@@ -163,8 +164,8 @@ __device__ __forceinline__ void te_mbar_wait(TeCtl* ctl, uint32_t bar, uint32_t 
 // Writers: every epilogue thread has stored its outputs and met the others at a CTA barrier; one thread then
 // publishes them (release) and arrives.  The activations are read back by OTHER CTAs through TMA, i.e. through the
 // async proxy: a proxy fence orders the generic-proxy stores against those reads.
-__device__ __forceinline__ void te_grid_arrive(TeCtl* ctl) {
-  asm volatile("fence.proxy.async.global;" ::: "memory");
+__device__ __forceinline__ void te_grid_arrive(TeCtl* ctl, int exp) {
+  if (!(exp & 2)) asm volatile("fence.proxy.async.global;" ::: "memory");
   asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(&ctl->arrived) : "memory");   // the release publishes the CTA's stores (bar.sync made them this thread's)
 }
 // Everything a CTA reads of another CTA's output after the barrier comes straight from L2 (TMA, ld.global.cg), so the
@@ -252,6 +253,9 @@ __device__ __forceinline__ void te_stat_commit(unsigned long long* acc, int n0, 
   const int n = n0 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
   if ((lane & 3) == 0 && n < N) stat_add(acc, n, w);
 }
+__device__ __forceinline__ void te_stat_commit_x(int exp, unsigned long long* acc, int n0, int N, float w, int lane) {
+  if (!(exp & 1)) te_stat_commit(acc, n0, N, w, lane);
+}
 // consume a statistic (its one owner thread): straight from L2 -- the atomics of the other CTAs landed there
 __device__ __forceinline__ float te_stat_take(unsigned long long* acc, int i) {
   const unsigned long long v = __ldcg(acc + i);
@@ -315,14 +319,14 @@ __device__ __forceinline__ void te_act_finish(const TeArgs& a, bool hid, int kin
 #pragma unroll
         for (int j = 0; j < 4; ++j) x[j] = -x[j];
       }
-      te_stat_commit(a.stats, n0, N, te_colsum4(x, lane), lane);          // dc = sum_rows (h_0 - h_k)
+      te_stat_commit_x(a.exp, a.stats, n0, N, te_colsum4(x, lane), lane);          // dc = sum_rows (h_0 - h_k)
     }
   } else {
     if (in_tile) te_store4_h(a.Vt, grow, n0, N, x);
     if (t == a.k - 1) {                                                     // db = sum_rows (v_0 - v_k)
 #pragma unroll
       for (int j = 0; j < 4; ++j) x[j] = row_ok ? aux[j] - x[j] : 0.0f;
-      te_stat_commit(a.stats + a.H, n0, N, te_colsum4(x, lane), lane);
+      te_stat_commit_x(a.exp, a.stats + a.H, n0, N, te_colsum4(x, lane), lane);
     }
   }
 }
@@ -334,7 +338,6 @@ __global__ void __launch_bounds__(TE_THREADS, 1) rbm_tc_epoch_kernel(const __gri
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + pl.off_bars);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + TE_NBARS);
   volatile unsigned* gb_passed = reinterpret_cast<volatile unsigned*>(tmem_slot + 1);   // grid barriers this CTA has passed
-  volatile unsigned* fin_flag = gb_passed + 1;                                          // split-K: this CTA finalises the tile
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bar_base = smem_u32(bars);
   auto bar = [&](int i) { return bar_base + 8u * (uint32_t)i; };
@@ -365,7 +368,6 @@ __global__ void __launch_bounds__(TE_THREADS, 1) rbm_tc_epoch_kernel(const __gri
     for (int i = 0; i < 9; ++i) asm volatile("prefetch.tensormap [%0];" ::"l"(maps[i]) : "memory");
     for (int i = 0; i < TE_NBARS; ++i) mbar_init(bar(i), i == TE_B_ACC ? TE_NISS : 1);
     *gb_passed = 0u;
-    *fin_flag = 0u;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -527,7 +529,7 @@ __global__ void __launch_bounds__(TE_THREADS, 1) rbm_tc_epoch_kernel(const __gri
     const int coff = (lane >> 4) * 4;            // ... and its 8-column chunk is split over lanes l (0-3) and l + 16 (4-7)
     const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16);
     uint32_t epoch = a.rng.epoch + (a.rng.epoch_ptr ? *a.rng.epoch_ptr : 0u);
-    unsigned n_acc = 0, n_bar = 0;
+    unsigned n_acc = 0, n_bar = 0, n_vis = 0;
     for (int s = 0; s < steps; ++s) {
       const int valid = min(a.B, a.n_rows - s * a.B);     // rows of this mini-batch (dbn/utils.py:14-22: short last batch)
       for (int p = 0; p < np; ++p) {
@@ -604,7 +606,9 @@ __global__ void __launch_bounds__(TE_THREADS, 1) rbm_tc_epoch_kernel(const __gri
           tc_fence_after();
           if (tid_e == 0) te_trace(a, s, p, 1);
           if (!hid && pl.ksplit > 1) {
-            // split K: partial tile -> L2 scratch; the last of the ksplit CTAs sums them in a fixed order
+            // split K: partial tile -> L2 scratch; once all ksplit partials of the tile are there, EVERY one of the
+            // ksplit CTAs finishes its own rb_v / ksplit rows (sum in a fixed order: deterministic).  A half-warp
+            // takes 16 rows x 4 columns, so the column statistics keep their 16-lane butterfly.
             const int tile = v_rb * pl.nt_v_cols + v_cb;
             float* part = a.scratch + ((size_t)(tile * pl.ksplit + v_kc) * 64 + rloc) * 64;
 #pragma unroll
@@ -616,29 +620,38 @@ __global__ void __launch_bounds__(TE_THREADS, 1) rbm_tc_epoch_kernel(const __gri
                 __stcg(reinterpret_cast<float4*>(part + ch * 8 + coff), make_float4(v[0], v[1], v[2], v[3]));
               }
             }
+            const int R = pl.rb_v / pl.ksplit;                         // rows this CTA finishes (a multiple of 16)
+            const int quads = width >> 2;
+            const int item = (warp - TE_WARP_EPI) * 2 + (lane >> 4);   // half-warp index: at most one item each
+            const bool has_item = item < (R >> 4) * quads;
+            const int rt = v_kc * R + (item / quads) * 16 + (lane & 15);
+            const int fn0 = col0 + (item % quads) * 4;
+            const int fgrow = v_rb * pl.rb_v + rt;
+            const bool f_in = has_item && fgrow < a.B && fn0 < N, f_ok = f_in && fgrow < valid;
+            float fb[4] = {0.f, 0.f, 0.f, 0.f}, fa[4] = {0.f, 0.f, 0.f, 0.f};
+            if (has_item && fn0 < N) te_act_prefetch(a, hid, kind, t, epoch, s, fgrow, f_ok, fn0, fb, fa);
+            ++n_vis;
             asm volatile("bar.sync 1, %0;" ::"n"(TE_EPI_THREADS) : "memory");
             if (tid_e == 0) {
-              __threadfence();
-              const unsigned old = atomicAdd(&a.ctl->tile_done[tile], 1u);
-              *fin_flag = ((old + 1u) % (unsigned)pl.ksplit == 0u) ? 1u : 0u;
-              __threadfence();
+              asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(&a.ctl->tile_done[tile]) : "memory");
+              unsigned v = 0;
+              for (unsigned spin = 0;; ++spin) {
+                asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(&a.ctl->tile_done[tile]) : "memory");
+                if (v >= (unsigned)pl.ksplit * n_vis) break;
+                if (spin > (1u << 22)) te_fail(a.ctl, 4);
+              }
             }
             asm volatile("bar.sync 1, %0;" ::"n"(TE_EPI_THREADS) : "memory");
-            if (*fin_flag != 0u) {
-              const float* base = a.scratch + ((size_t)(tile * pl.ksplit) * 64 + rloc) * 64;
-#pragma unroll
-              for (int i = 0; i < 2; ++i) {
-                const int ch = g + 4 * i;
-                const int n0 = col0 + ch * 8 + coff;
-                if (ch < chunks && col0 + ch * 8 < N) {     // warp-uniform
-                  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-                  for (int kc = 0; kc < pl.ksplit; ++kc) {            // fixed order: deterministic sums
-                    const float4 x = __ldcg(reinterpret_cast<const float4*>(base + (size_t)kc * 4096 + ch * 8 + coff));
-                    acc[0] += x.x; acc[1] += x.y; acc[2] += x.z; acc[3] += x.w;
-                  }
-                  te_act_finish(a, hid, kind, t, grow, lane_ok && n0 < N, row_ok && n0 < N, n0, acc, bias[i], aux[i], lane);
+            if (__any_sync(0xffffffffu, has_item)) {                    // whole warp: the statistics butterfly shuffles with a full mask
+              float acc[4] = {0.f, 0.f, 0.f, 0.f};
+              if (has_item) {
+                const float* base = a.scratch + ((size_t)(tile * pl.ksplit) * 64 + rt) * 64 + (fn0 - col0);
+                for (int kc = 0; kc < pl.ksplit; ++kc) {                // fixed order: deterministic sums
+                  const float4 x = __ldcg(reinterpret_cast<const float4*>(base + (size_t)kc * 4096));
+                  acc[0] += x.x; acc[1] += x.y; acc[2] += x.z; acc[3] += x.w;
                 }
               }
+              te_act_finish(a, hid, kind, t, fgrow, f_in, f_ok, fn0, acc, fb, fa, lane);
             }
           } else {
 #pragma unroll
@@ -662,7 +675,7 @@ __global__ void __launch_bounds__(TE_THREADS, 1) rbm_tc_epoch_kernel(const __gri
         asm volatile("bar.sync 1, %0;" ::"n"(TE_EPI_THREADS) : "memory");
         if (tid_e == 0) {
           te_trace(a, s, p, 3);
-          te_grid_arrive(a.ctl);
+          te_grid_arrive(a.ctl, a.exp);
           te_trace(a, s, p, 4);
           ++n_bar;
           te_grid_wait(a.ctl, n_bar * gridDim.x);
@@ -761,6 +774,7 @@ inline bool te_plan(int V, int H, int B, TePlan* out) {
       for (int S : {1, 2, 4}) {
         const int kc = ceil_div(kh, S);
         if (ceil_div(kh, kc) != S) continue;           // some CTA would have nothing to contract
+        if (S > 1 && (rb_v % (16 * S)) != 0) continue; // every CTA of a split finishes whole 16-row groups of the tile
         int vs = 0;
         for (int c = 8; c <= 64; c += 8)
           if (ntr_v * ceil_div(V, c) * S <= G) { vs = c; break; }
