@@ -428,6 +428,10 @@ def pick_precision(args, wl):
     return "bf16" if wl == "c3" else "fp16"
 
 
+# ncu dram__bytes_read.sum + dram__bytes_write.sum of one rbm_tc_epoch_kernel launch per layer (profiles/r02_c2_tc_epoch_full.txt)
+C2_TC_TRAFFIC = {0: 108.5e6, 1: 69.1e6, 2: 75.1e6}   # algorithmic: 99.8 / 61.4 / 61.4 MB of input rows + 2.4 / 1.5 / 6.0 MB of W in and out
+
+
 def bench_c2(c, steps, warmup, with_e2e=True):
     import ctypes as C
     import torch
@@ -456,27 +460,51 @@ def bench_c2(c, steps, warmup, with_e2e=True):
                 layers[i].transform(feats[i], out=feats[i + 1])
 
     ms, clocks, eager = timed(c, step, steps, warmup)
-    launches = eager + steps * sum(r.launches_per_epoch for r in runners) * (1 if E._use_graphs() else 0)
+    launches = eager + steps * sum(r.launches_per_epoch for r in runners if not (r.tc_epoch or r.persistent)) * (1 if E._use_graphs() else 0)
     flops_per_step = sum(10.0 * v * h for v, h in zip(C2_DIMS[:-1], C2_DIMS[1:])) * C2_ROWS
-    # dominant kernel alone: the v->h contraction + Bernoulli sampling of layer 1 (256 x 500, K = 784), the
-    # largest share of the step in the ncu launch list (profiles/)
-    l1 = layers[0]
-    ws = l1.make_workspace(C2_BS)
-    a = l1._step_args(runners[0].Xp, 1, 0.0, ws, 1, None)
-    a.B, a.row0 = C2_BS, 0
+    if all(r.tc_epoch for r in runners):
+        # dominant kernel: rbm_tc_epoch_kernel, ONE cooperative launch per layer-epoch (csrc/rbm_tc_epoch.cuh).  Each layer's
+        # launch is timed alone with CUDA events on the launching stream; the longest one is reported.
+        per_layer = []
+        for i, r in enumerate(runners):
+            def one(r=r):
+                L.check(lib.dbn_rbm_fit_epoch(E.stream_ptr(), C.byref(r.args), r.n, r.bs))
+            per_layer.append(time_alone(one, 5))
+        i_dom = int(np.argmax(per_layer))
+        dom_ms = per_layer[i_dom]
+        v_d, h_d = C2_DIMS[i_dom], C2_DIMS[i_dom + 1]
+        dom_tf = 10.0 * v_d * h_d * C2_ROWS / (dom_ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "rbm_tc_epoch_kernel: persistent tcgen05 CD-1 epoch of layer %d (%d -> %d, %d mini-batches of "
+                                             "%d rows in one cooperative launch, grid barrier between phases)"
+                                             % (i_dom + 1, v_d, h_d, -(-C2_ROWS // C2_BS), C2_BS),
+                "achieved": dom_tf, "peak": c.pk["bf16_burst"], "unit": "TFLOP/s", "frac": dom_tf / c.pk["bf16_burst"],
+                "kernel_ms": dom_ms, "kernel_ms_per_layer": per_layer, "us_per_minibatch": [1e3 * t / -(-C2_ROWS // C2_BS) for t in per_layer],
+                "peak_source": c.pk["source"] + " bf16 burst (kernel timed alone)",
+                "algorithmic_flops_per_launch": 10.0 * v_d * h_d * C2_ROWS,
+                "traffic": C2_TC_TRAFFIC.get(i_dom), "traffic_source": "ncu dram__bytes_read+write of this launch, profiles/r02_c2_tc_epoch_full.txt "
+                                                                     "(algorithmic: the epoch's input rows once + W in and out; P0 / samples / V1 / Pk stay in L2)",
+                "note": "latency-bound by construction at batch 256: per mini-batch four dependent phases of < 0.3 us tensor time each, "
+                        "separated by grid barriers (~1.3 us) and operand refills out of L2 (~0.8 us); phase trace in profiles/r02_notes.md"}
+    else:
+        # dominant kernel alone: the v->h contraction + Bernoulli sampling of layer 1 (256 x 500, K = 784), the
+        # largest share of the step in the ncu launch list (profiles/)
+        l1 = layers[0]
+        ws = l1.make_workspace(C2_BS)
+        a = l1._step_args(runners[0].Xp, 1, 0.0, ws, 1, None)
+        a.B, a.row0 = C2_BS, 0
 
-    def dom():
-        L.check(lib.dbn_rbm_first_hidden(E.stream_ptr(), C.byref(a), 0, l1.H))
-    dom_ms = time_alone(dom, 200, graph_batch=50 if E._use_graphs() else 0)
-    dom_tf = 2.0 * C2_BS * l1.H * l1.V / (dom_ms * 1e-3) / 1e12
-    roof = {"bound": "tensor", "kernel": "umma_gemm_sk_kernel<64, act> (split-K, clusters of 4, 64 CTAs): v->h + sample "
-                                         "of layer 1 (256x500, K=784)",
-            "achieved": dom_tf, "peak": c.pk["bf16_burst"], "unit": "TFLOP/s", "frac": dom_tf / c.pk["bf16_burst"],
-            "kernel_ms": dom_ms, "peak_source": c.pk["source"] + " bf16 burst",
-            "traffic": 1.3e6, "traffic_source": "ncu dram__bytes_read+write per launch, profiles/r01_c2_splitk_full.txt "
-                                                "(algorithmic: 1.2 MB of operands; the outputs stay in L2)",
-            "note": "latency-bound at batch 256: 0.2 GFLOP per launch and a chain of four dependent launches per "
-                    "mini-batch; see step_roofline and profiles/ for the phase breakdown"}
+        def dom():
+            L.check(lib.dbn_rbm_first_hidden(E.stream_ptr(), C.byref(a), 0, l1.H))
+        dom_ms = time_alone(dom, 200, graph_batch=50 if E._use_graphs() else 0)
+        dom_tf = 2.0 * C2_BS * l1.H * l1.V / (dom_ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "umma_gemm_sk_kernel<64, act> (split-K, clusters of 4, 64 CTAs): v->h + sample "
+                                             "of layer 1 (256x500, K=784)",
+                "achieved": dom_tf, "peak": c.pk["bf16_burst"], "unit": "TFLOP/s", "frac": dom_tf / c.pk["bf16_burst"],
+                "kernel_ms": dom_ms, "peak_source": c.pk["source"] + " bf16 burst",
+                "traffic": 1.3e6, "traffic_source": "ncu dram__bytes_read+write per launch, profiles/r01_c2_splitk_full.txt "
+                                                    "(algorithmic: 1.2 MB of operands; the outputs stay in L2)",
+                "note": "latency-bound at batch 256: 0.2 GFLOP per launch and a chain of four dependent launches per "
+                        "mini-batch; see step_roofline and profiles/ for the phase breakdown"}
     rec = {"metric": METRIC, "value": C2_ROWS * steps / (ms * 1e-3), "unit": "samples/s", "steps": steps, "warmup": warmup,
            "ms_per_step": ms / steps, "config": workload_config("c2", c.world), "clocks": clocks,
            "gpu_launches": int(launches), "roofline": roof, "step_roofline": step_roofline(c, flops_per_step, steps, ms)}

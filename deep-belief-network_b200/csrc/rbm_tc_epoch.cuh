@@ -118,24 +118,31 @@ __device__ __forceinline__ bool te_elect() {
   return pred != 0;
 }
 
-// A tile row's 8-column chunk sits in lanes 0-15 of a TMEM quarter (UMMA M = 64).  The sum of the phase's partial
-// accumulators is split over the whole warp: lane l < 16 keeps columns 0-3 of row l, lane l + 16 takes columns 4-7,
-// so all 32 lanes run the element-wise tail on 4 columns each.
-__device__ __forceinline__ void te_ld_acc4(uint32_t taddr, int nacc, int width, int lane, float x[4]) {   // nacc <= TE_NISS
-  uint32_t v[8];
-  float acc[8];
-  tc_ld8(taddr, v);
-#pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = __uint_as_float(v[j]);
-  for (int i = 1; i < nacc; ++i) {
-    tc_ld8(taddr + (uint32_t)(i * width), v);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] += __uint_as_float(v[j]);
-  }
+__device__ __forceinline__ void tc_ld8_nowait(uint32_t taddr, uint32_t v[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
+// A tile row's 8-column chunk sits in lanes 0-15 of a TMEM quarter (UMMA M = 64).  All TE_NISS partial accumulators
+// are requested in one go (one wait; those of issuers without k-steps hold stale but allocated columns and are
+// dropped) and their sum is split over the whole warp: lane l < 16 keeps columns 0-3 of row l, lane l + 16 takes
+// columns 4-7, so all 32 lanes run the element-wise tail on 4 columns each.
+__device__ __forceinline__ void te_ld_acc4(uint32_t taddr, int nacc, int width, int lane, float x[4]) {
+  static_assert(TE_NISS == 3, "three partial accumulators");
+  uint32_t v0[8], v1[8], v2[8];
+  tc_ld8_nowait(taddr, v0);
+  tc_ld8_nowait(taddr + (uint32_t)width, v1);
+  tc_ld8_nowait(taddr + (uint32_t)(2 * width), v2);
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  const bool hi = lane >= 16;
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    const float hi = __shfl_sync(0xffffffffu, acc[4 + j], lane & 15);
-    x[j] = lane < 16 ? acc[j] : hi;
+    // (a stale accumulator may hold anything, NaN included: select, do not multiply)
+    const float lo_s = __uint_as_float(v0[j]) + (nacc > 1 ? __uint_as_float(v1[j]) : 0.0f) + (nacc > 2 ? __uint_as_float(v2[j]) : 0.0f);
+    const float hi_s = __uint_as_float(v0[4 + j]) + (nacc > 1 ? __uint_as_float(v1[4 + j]) : 0.0f) + (nacc > 2 ? __uint_as_float(v2[4 + j]) : 0.0f);
+    const float got = __shfl_sync(0xffffffffu, hi_s, lane & 15);
+    x[j] = hi ? got : lo_s;
   }
 }
 
