@@ -119,6 +119,8 @@ SYMBOLS = {
     "dbn_rbm_fit_epoch": (C.c_int, [C.c_void_p, _P(RbmStepArgs), C.c_int, C.c_int]),
     "dbn_rbm_tc_epoch_plan": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "dbn_set_tc_epoch": (C.c_int, [C.c_int]),
+    "dbn_set_tc_finetune": (C.c_int, [C.c_int]),
+    "dbn_mlp_tc_epoch_plan": (C.c_int, [C.c_int, C.c_int, _P(C.c_int32), C.c_int, C.c_int, C.c_int]),
     "dbn_rbm_tc_epoch_plan_info": (C.c_int, [C.c_int, C.c_int, C.c_int, _P(C.c_int32), C.c_int]),
     "dbn_rbm_persistent_plan": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "dbn_rbm_fit_epoch_persistent": (C.c_int, [C.c_void_p, _P(RbmStepArgs), C.c_void_p, C.c_int, C.c_int]),

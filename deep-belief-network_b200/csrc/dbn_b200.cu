@@ -8,6 +8,7 @@
 #include "misc_kernels.cuh"
 #include "rbm_persistent.cuh"
 #include "rbm_tc_epoch.cuh"
+#include "mlp_tc_epoch.cuh"
 #include "dp_kernels.cuh"
 
 using namespace dbn;
@@ -133,6 +134,8 @@ struct MlpWorkspace {
   dbn_mat delta[DBN_MAX_LAYERS];      // delta_1..delta_L
   dbn_mat Z, dO;                      // head scores/outputs, head delta (fp32)
   dbn_mat dOb;                        // bf16 copy of the head delta (BF16 mode: operand of the head-gradient contraction)
+  TeCtl* ctl;                         // tensor-core modes: control block + split-K scratch of the persistent fine-tune kernel
+  float* scratch;
 };
 size_t mlp_ws_layout(int precision, int Bmax, int n_in, const int32_t* dims, int L, int n_out, char* base,
                      MlpWorkspace* ws) {
@@ -152,6 +155,17 @@ size_t mlp_ws_layout(int precision, int Bmax, int n_in, const int32_t* dims, int
   w.Z = carve(n_out, DBN_F32, false);
   w.dO = carve(n_out, DBN_F32, false);
   w.dOb = is_tc(precision) ? carve(n_out, dt, false) : null_mat();
+  w.ctl = nullptr;
+  w.scratch = nullptr;
+  if (is_tc(precision)) {
+    w.ctl = reinterpret_cast<TeCtl*>(base ? base + off : nullptr);
+    off = align_up(off + sizeof(TeCtl), 1024);
+    MtPlan pl;
+    if (mt_plan(n_in, dims, L, n_out, Bmax, &pl) && pl.scratch_bytes > 0) {
+      w.scratch = reinterpret_cast<float*>(base ? base + off : nullptr);
+      off = align_up(off + pl.scratch_bytes, 1024);
+    }
+  }
   if (ws) *ws = w;
   return off;
 }
@@ -871,8 +885,106 @@ int dbn_mlp_train_step(void* stream, const dbn_mlp_step_args* a) {
   return DBN_OK;
 }
 
+// Whole iteration (every mini-batch of one pass) in ONE cooperative launch of mlp_tc_epoch_kernel when the network fits its
+// phase plan (tensor-core modes, <= 4 hidden layers, head <= 16 wide, mini-batches of 16..256 rows, no dropout, no optional
+// outputs); *done = 0: not applicable, the caller runs the tiled path.
+static int mlp_fit_epoch_tc(cudaStream_t st, const dbn_mlp_step_args* t, int n_rows, int batch_size, int* done) {
+  *done = 0;
+  const int L = t->n_layers;
+  const int B = t->ws_rows > 0 ? t->ws_rows : std::min(batch_size, n_rows);
+  if (mt_enabled_flag() != 1 || !is_tc(t->precision) || n_rows <= 0 || L < 1 || L > MT_MAX_LAYERS) return DBN_OK;
+  if (B < std::min(batch_size, n_rows) || (n_rows > B && B != batch_size)) return DBN_OK;
+  if (t->keep_p < 1.0f || t->out.ptr || t->raw_grads[0].ptr) return DBN_OK;
+  if (t->act != DBN_ACT_SIGMOID && t->act != DBN_ACT_RELU) return DBN_OK;
+  if (t->head != DBN_HEAD_SOFTMAX && t->head != DBN_HEAD_LINEAR) return DBN_OK;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) {
+    (void)cudaGetLastError();
+    return DBN_OK;
+  }
+  MtPlan pl;
+  if (!mt_plan(t->n_in, t->dims, L, t->n_out, B, &pl)) return DBN_OK;
+  if (pl.grid > mt_max_coresident()) return DBN_OK;
+  if (t->workspace_bytes < dbn_mlp_workspace_bytes(t->precision, B, t->n_in, t->dims, L, t->n_out)) return DBN_OK;
+  if (!t->Y || !t->Wo || !t->bo || t->ldwo != t->dims[L - 1] || (reinterpret_cast<uintptr_t>(t->Wo) & 15) != 0) return DBN_OK;
+  if (!umma_operand_ok(t->X, t->n_in)) return DBN_OK;
+  for (int l = 0; l < L; ++l)
+    if (!umma_operand_ok(t->Wb[l], l == 0 ? t->n_in : t->dims[l - 1]) || t->Wb[l].dtype != t->X.dtype || !t->W[l] || !t->c[l]) return DBN_OK;
+  MlpWorkspace ws;
+  mlp_ws_layout(t->precision, B, t->n_in, t->dims, L, t->n_out, static_cast<char*>(t->workspace), &ws);
+  if (pl.scratch_bytes > 0 && ws.scratch == nullptr) return DBN_OK;
+  static MtArgs a;   // (5 KB: built in place; the launch copies it)
+  memset(&a, 0, sizeof(a));
+  memcpy(a.ph, pl.ph, sizeof(a.ph));
+  a.n_phases = pl.n_phases;
+  a.L = L; a.n_in = t->n_in; a.n_out = t->n_out; a.B = B; a.act = t->act; a.head = t->head; a.dtype = t->X.dtype;
+  a.n_rows = n_rows; a.row0 = t->row0; a.scale = -t->lr_over_bs; a.decay = t->decay;
+  a.X = t->X; a.dOb = ws.dOb;
+  for (int l = 0; l < L; ++l) {
+    a.dims[l] = t->dims[l];
+    a.a[l] = ws.act[l]; a.d[l] = ws.delta[l]; a.Wb[l] = t->Wb[l];
+    a.W[l] = t->W[l]; a.ldw[l] = t->ldw[l]; a.c[l] = t->c[l];
+  }
+  a.Wo = t->Wo; a.ldwo = t->ldwo; a.bo = t->bo; a.Y = t->Y; a.ldy = t->ldy; a.loss_rows = t->loss_rows;
+  a.off_bars = pl.off_bars; a.smem_bytes = pl.smem_bytes; a.wo_bytes = pl.wo_bytes;
+  a.ctl = ws.ctl; a.scratch = ws.scratch; a.trace = nullptr;
+  const uint64_t xrows = (uint64_t)t->row0 + (uint64_t)n_rows;
+  for (int l = 0; l < L; ++l) {
+    const dbn_mat in = l == 0 ? t->X : ws.act[l - 1];
+    const uint64_t in_rows = l == 0 ? xrows : (uint64_t)B;
+    const int Kin = l == 0 ? t->n_in : t->dims[l - 1];
+    const int ks = ceil_div(Kin, 64);
+    DBN_TRY(make_operand_map(&a.tm_in3[l], in, in_rows, ks, pl.f_rb[l], ks));
+    DBN_TRY(make_operand_map(&a.tm_w3[l], t->Wb[l], t->dims[l], ks, pl.f_w[l], ks));
+    DBN_TRY(te_make_map2(&a.tm_in2[l], in, in.ld, in_rows, 256));
+    DBN_TRY(te_make_map2(&a.tm_d2[l], ws.delta[l], ws.delta[l].ld, B, 256));
+    if (l >= 1) {   // delta_l and W_l feed the contraction that produces delta_{l-1}
+      DBN_TRY(make_operand_map(&a.tm_d3[l], ws.delta[l], B, ceil_div(t->dims[l], 64), pl.b_rb[l - 1], pl.b_kc[l - 1]));
+      DBN_TRY(te_make_map2(&a.tm_w2[l], t->Wb[l], t->Wb[l].ld, t->dims[l], std::min(pl.b_kc[l - 1] * 64, 256)));
+    }
+  }
+  DBN_TRY(te_make_map2(&a.tm_in2[L], ws.act[L - 1], ws.act[L - 1].ld, B, 256));
+  DBN_TRY(te_make_map2(&a.tm_d2[L], ws.dOb, ws.dOb.ld, B, 256));
+  static std::atomic<uint64_t> attr_set{0};
+  if (first_use_on_device(attr_set))
+    DBN_CUDA_OK(cudaFuncSetAttribute(mlp_tc_epoch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TE_SMEM_MAX));
+  DBN_CUDA_OK(cudaMemsetAsync(ws.ctl, 0, sizeof(TeCtl), st));
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(pl.grid);
+  cfg.blockDim = dim3(TE_THREADS);
+  cfg.dynamicSmemBytes = pl.smem_bytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  DBN_CUDA_OK(cudaLaunchKernelEx(&cfg, mlp_tc_epoch_kernel, a));
+  DBN_LAUNCH_CHECK();
+  *done = 1;
+  return DBN_OK;
+}
+
+int dbn_mlp_tc_epoch_plan(int precision, int n_in, const int32_t* dims, int n_layers, int n_out, int batch_size) {
+  MtPlan pl;
+  if (!dims || !is_tc(precision) || mt_enabled_flag() != 1 || !mt_plan(n_in, dims, n_layers, n_out, batch_size, &pl)) return 0;
+  return pl.grid;
+}
+int dbn_set_tc_finetune(int enabled) {
+  const int prev = mt_enabled_flag();
+  mt_enabled_flag() = enabled ? 1 : 0;
+  return prev;
+}
+
 int dbn_mlp_fit_epoch(void* stream, const dbn_mlp_step_args* tmpl, int n_rows, int batch_size) {
   DBN_REQUIRE(tmpl && n_rows >= 0 && batch_size > 0, "bad argument");
+  {
+    DBN_NEED_DEVICE();
+    int done = 0;
+    DBN_TRY(mlp_fit_epoch_tc(as_stream(stream), tmpl, n_rows, batch_size, &done));
+    if (done) return DBN_OK;
+  }
   for (int s = 0; s < n_rows; s += batch_size) {
     dbn_mlp_step_args a = *tmpl;
     a.B = std::min(batch_size, n_rows - s);

@@ -1087,6 +1087,11 @@ class MlpIterRunner:
         self.graph = None
         self.launches_per_iter = 0
         self.iters_run = 0
+        # tensor-core modes without dropout: dbn_mlp_fit_epoch is ONE cooperative launch of the persistent fine-tune
+        # kernel (csrc/mlp_tc_epoch.cuh) -- nothing to capture
+        dims = (C.c_int32 * len(mlp.dims))(*mlp.dims)
+        self.tc_epoch = (mlp.prec in TC_PRECS and dropout_p == 0 and
+                         lib.dbn_mlp_tc_epoch_plan(mlp.prec, mlp.n_in, dims, len(mlp.dims), mlp.n_out, min(self.bs, n)) > 0)
 
     def _enqueue(self):
         lib = self.mlp.lib
@@ -1105,7 +1110,7 @@ class MlpIterRunner:
             for m, w in zip(self.masks, self.widths):
                 m.copy_(torch.from_numpy(np.ascontiguousarray(flat[:, o:o + w])))
                 o += w
-        if _use_graphs() and self.iters_run >= 1:   # iteration 1 eager (warm-up), iteration 2 captured, then replays
+        if _use_graphs() and self.iters_run >= 1 and not self.tc_epoch:   # iteration 1 eager (warm-up), iteration 2 captured, then replays
             if self.graph is None:
                 torch.cuda.current_stream().synchronize()
                 self.graph = torch.cuda.CUDAGraph()

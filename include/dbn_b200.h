@@ -441,6 +441,16 @@ int dbn_mlp_train_step(void* stream, const dbn_mlp_step_args* args);
 /* One iteration's mini-batch loop (dbn/models.py:439-465). loss_rows (if set) is [n_rows]. */
 int dbn_mlp_fit_epoch(void* stream, const dbn_mlp_step_args* tmpl, int n_rows, int batch_size);
 
+/* Tensor-core modes: dbn_mlp_fit_epoch runs the whole iteration as ONE cooperative launch of the persistent fine-tune
+ * kernel (csrc/mlp_tc_epoch.cuh: a phase program F_0..F_{L-1} | HEAD | B_l + U_{l+2} .. | U_1 + U_0 per mini-batch, grid
+ * barriers between phases) when the network fits its plan -- <= 4 hidden layers, head <= 16 wide, mini-batches of 16..256
+ * rows, no dropout, no optional outputs, stream not being captured -- and as the loop of dbn_mlp_train_step otherwise.
+ * Replaces the mini-batch loop of dbn/models.py:439-465.  Returns the number of CTAs of the plan, 0 when it does not fit
+ * (or DBN_B200_TC_FINETUNE=0): callers then capture the iteration in a CUDA graph as before. */
+int dbn_mlp_tc_epoch_plan(int precision, int n_in, const int32_t* dims, int n_layers, int n_out, int batch_size);
+/* Switch it on / off at run time; returns the previous setting (parity tests run the same iteration through both paths). */
+int dbn_set_tc_finetune(int enabled);
+
 /* ---- small helpers the host loops need -------------------------------------------------------- */
 /* dst[i, :] = src[idx[i], :] with optional dtype conversion and dropout on the input
  * (permutation + batch_generator of the reference: dbn/models.py:106-107, dbn/utils.py:11-13).

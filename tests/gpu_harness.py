@@ -221,3 +221,33 @@ def tc_epoch_plan(V, H, B):
     names = ["ctas", "hid_rows", "hid_units", "hid_tiles", "vis_rows", "vis_units", "ksplit", "kc_slabs", "vis_tiles",
              "dw_width", "dw_tiles", "smem", "vk_early", "p1_in_act", "scratch", "kv_slabs"]
     return {names[i]: int(out[i]) for i in range(min(m, 16))}
+
+
+def run_mlp_epoch(layers, Wo, bo, X, Y, act, head, precision, batch_size, lr=0.1, l2=1.0, tc=True, iters=1):
+    """`iters` passes of dbn_mlp_fit_epoch over the rows of X in their stored order (no shuffle, no dropout), either as
+    ONE persistent launch per pass (tc=True, csrc/mlp_tc_epoch.cuh) or as the tiled launches per mini-batch.  Returns
+    the trained parameters, the per-row losses of the last pass and the number of kernels the library launched."""
+    import torch
+    l = lib()
+    dev = torch.device("cuda")
+    n = X.shape[0]
+    rbms = [E.DeviceRbm(W, np.zeros(W.shape[1]), c, act, precision, dev) for (W, c) in layers]
+    mlp = E.DeviceMlp(rbms, Wo, bo, act, head, precision, dev)
+    Xop = stage_operand(X, precision)
+    Yd = _t(Y, torch.float32)
+    ws = mlp.make_workspace(min(batch_size, n))
+    loss = torch.zeros(n, device="cuda")
+    a = mlp.step_args(Xop, Yd, lr / batch_size, 1.0 - lr * l2 / n, 1.0, ws, 0, None, loss, None)
+    prev = l.dbn_set_tc_finetune(1 if tc else 0)
+    try:
+        before = l.dbn_launch_count()
+        for _ in range(iters):
+            L.check(l.dbn_mlp_fit_epoch(E.stream_ptr(), C.byref(a), n, batch_size))
+        torch.cuda.synchronize()
+        launches = int(l.dbn_launch_count() - before)
+    finally:
+        l.dbn_set_tc_finetune(prev)
+    res = {"layers": [(r.export()[0], r.export()[2]) for r in rbms], "loss": loss.double().cpu().numpy(), "launches": launches}
+    res["Wo"], res["bo"] = mlp.export_head()
+    res["shadows"] = [r.Wb[:, :r.V].float().double().cpu().numpy() for r in rbms]
+    return res

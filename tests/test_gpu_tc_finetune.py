@@ -1,0 +1,99 @@
+"""Parity of the persistent fine-tune kernel (csrc/mlp_tc_epoch.cuh: one cooperative launch per back-propagation
+iteration, reference loop dbn/models.py:439-465) against the float64 oracle and against the tiled path."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from gpu_harness import lib, relF, run_mlp_epoch, shadow_round  # noqa: E402
+from oracle import dbn_oracle as orc  # noqa: E402
+
+
+def _net(rng, n_in, hs, n_out):
+    layers, prev = [], n_in
+    for h in hs:
+        layers.append((rng.standard_normal((h, prev)) / np.sqrt(prev), rng.standard_normal(h) * 0.1))
+        prev = h
+    return layers, rng.standard_normal((n_out, prev)) / np.sqrt(prev), rng.standard_normal(n_out) * 0.1
+
+
+def _oracle_epoch(layers, Wo, bo, X, Y, act, head, lr, l2, bs, precision):
+    """dbn/models.py:439-465 in float64.  The device contracts the 16-bit shadows of the hidden weights, so the oracle
+    takes its gradients at the weights rounded the same way and applies them to the un-rounded masters.  Also returns
+    the yardsticks of tests/test_gpu_parity.py::test_finetune_step_against_oracle summed over the mini-batches: the size
+    of the terms each weight / bias change is a signed sum of (lr/bs x || |delta|^T |a| ||, lr/bs x || sum |delta| ||)."""
+    lay = [[W.copy(), c.copy()] for (W, c) in layers]
+    Wo, bo = Wo.copy(), bo.copy()
+    n = X.shape[0]
+    losses = np.zeros(n)
+    nl = len(lay) + 1
+    scale_w, scale_b = np.zeros(nl), np.zeros(nl)
+    for s in range(0, n, bs):
+        q = [(shadow_round(W, precision), c) for (W, c) in lay]
+        gW, gb, out, acts, deltas = orc.finetune_grads(q, Wo, bo, X[s:s + bs], Y[s:s + bs], None, act, head)
+        losses[s:s + bs] = orc.sample_loss(out, Y[s:s + bs], head).sum(axis=1) / (Y.shape[1] if head == "softmax" else 1)
+        decay = 1.0 - lr * l2 / n
+        for l in range(nl):
+            scale_w[l] += lr / bs * np.linalg.norm(np.abs(deltas[l]).T @ np.abs(acts[l]))
+            scale_b[l] += lr / bs * np.linalg.norm(np.abs(deltas[l]).sum(axis=0))
+        for l in range(len(lay)):
+            lay[l][0] = decay * lay[l][0] - lr / bs * gW[l]
+            lay[l][1] = lay[l][1] - lr / bs * gb[l]
+        Wo = decay * Wo - lr / bs * gW[-1]
+        bo = bo - lr / bs * gb[-1]
+    return lay, Wo, bo, losses, scale_w, scale_b
+
+
+CASES = [
+    (784, [500, 500, 2000], 10, 256, 512 + 96, "sigmoid", "softmax"),   # config 3 (short last mini-batch, split-K backward)
+    (64, [256, 256], 10, 32, 96, "relu", "softmax"),                    # config 1 widths
+    (96, [128], 3, 64, 128, "sigmoid", "linear"),                       # one hidden layer, regression head
+    (200, [136, 72, 104, 64], 5, 128, 256, "sigmoid", "softmax"),       # four hidden layers, ragged widths
+]
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp16"])
+@pytest.mark.parametrize("n_in,hs,n_out,bs,n,act,head", CASES)
+def test_iteration_against_oracle(precision, n_in, hs, n_out, bs, n, act, head):
+    import ctypes as C
+    dims = (C.c_int32 * len(hs))(*hs)
+    assert lib().dbn_mlp_tc_epoch_plan(1, n_in, dims, len(hs), n_out, min(bs, n)) > 0, "network expected to fit the plan"
+    rng = np.random.default_rng(n_in + n_out + len(hs))
+    layers, Wo, bo = _net(rng, n_in, hs, n_out)
+    X = rng.integers(0, 17, (n, n_in)) / 16.0
+    Y = np.eye(n_out)[rng.integers(0, n_out, n)] if head == "softmax" else rng.standard_normal((n, n_out))
+    lr, l2 = 0.1, 1.0
+    lay, Wo2, bo2, losses, scale_w, scale_b = _oracle_epoch(layers, Wo, bo, X, Y, act, head, lr, l2, bs, precision)
+    res = run_mlp_epoch(layers, Wo, bo, X, Y, act, head, precision, bs, lr=lr, l2=l2, tc=True)
+    assert res["launches"] <= 2, "the iteration must be one persistent launch"
+    # same bound as the single-step test of the tiled path: 2e-3 per contraction, compounding through the chain
+    # (depth), four times the margin for relu's gate flips; measured against the size of the summed terms
+    depth = len(hs) + 1
+    gate = 4.0 if act == "relu" else 1.0
+    tol = 2e-3 * depth * gate
+    for l in range(len(hs)):
+        assert np.linalg.norm(res["layers"][l][0] - lay[l][0]) < tol * scale_w[l] + 2e-6 * np.linalg.norm(lay[l][0]), "layer %d weights" % l
+        assert np.linalg.norm(res["layers"][l][1] - lay[l][1]) < tol * scale_b[l] + 1e-6, "layer %d bias" % l
+        assert np.array_equal(res["shadows"][l], shadow_round(res["layers"][l][0], precision)), "shadow must be the rounded master"
+    assert np.linalg.norm(res["Wo"] - Wo2) < tol * scale_w[-1] + 1e-6 and np.linalg.norm(res["bo"] - bo2) < tol * scale_b[-1] + 1e-6
+    assert np.max(np.abs(res["loss"] - losses)) < tol * 10 * max(1.0, np.max(np.abs(losses)))
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp16"])
+@pytest.mark.parametrize("n_in,hs,n_out,bs,n,act,head", CASES[:2])
+def test_iteration_matches_tiled_path(precision, n_in, hs, n_out, bs, n, act, head):
+    rng = np.random.default_rng(5)
+    layers, Wo, bo = _net(rng, n_in, hs, n_out)
+    X = rng.integers(0, 17, (n, n_in)) / 16.0
+    Y = np.eye(n_out)[rng.integers(0, n_out, n)]
+    r1 = run_mlp_epoch(layers, Wo, bo, X, Y, act, head, precision, bs, tc=True, iters=2)
+    r0 = run_mlp_epoch(layers, Wo, bo, X, Y, act, head, precision, bs, tc=False, iters=2)
+    assert r1["launches"] <= 4 and r0["launches"] > 8
+    gate = 4.0 if act == "relu" else 1.0
+    for l in range(len(hs)):
+        assert relF(r1["layers"][l][0] - layers[l][0], r0["layers"][l][0] - layers[l][0]) < 2e-3 * gate
+        assert relF(r1["layers"][l][1] - layers[l][1], r0["layers"][l][1] - layers[l][1]) < 2e-3 * gate
+    assert relF(r1["Wo"] - Wo, r0["Wo"] - Wo) < 2e-3 * gate
+    r2 = run_mlp_epoch(layers, Wo, bo, X, Y, act, head, precision, bs, tc=True, iters=2)
+    for l in range(len(hs)):
+        assert np.array_equal(r1["layers"][l][0], r2["layers"][l][0]), "deterministic"
