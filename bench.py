@@ -521,6 +521,9 @@ def bench_c2(c, steps, warmup, with_e2e=True):
     return rec
 
 
+C3_TC_TRAFFIC = None   # ncu dram__bytes_read.sum + dram__bytes_write.sum of one mlp_tc_epoch_kernel launch (profiles/r02_c3_tc_epoch_full.txt)
+
+
 def bench_c3(c, steps, warmup, with_e2e=True):
     import ctypes as C
     import torch
@@ -542,34 +545,50 @@ def bench_c3(c, steps, warmup, with_e2e=True):
                       precision, dev)
     runner = E.MlpIterRunner(mlp, Xd, Yd, C2_BS, 0.1, 1.0, 0.0, 77)
     ms, clocks, eager = timed(c, runner.run, steps, warmup)
-    launches = eager + steps * runner.launches_per_iter * (1 if E._use_graphs() else 0)
     P = [v * h for v, h in zip(C2_DIMS[:-1], C2_DIMS[1:])] + [2000 * 10]
     flops_per_step = (2.0 * sum(P) + 2.0 * sum(P[1:]) + 2.0 * sum(P)) * C2_ROWS
-    # dominant kernel alone: the weight-gradient contraction + decayed SGD update of the widest layer
-    # (2000 x 501 accumulator, K = 256 rows), timed back to back inside a CUDA graph
-    l3 = layers[2]
-    Ad = torch.zeros(C2_BS, E.bf16_pitch(2000), dtype=E.OP_DTYPE[E.PREC_IDS[precision]], device=dev)
-    Bd = torch.zeros(C2_BS, E.bf16_pitch(500), dtype=E.OP_DTYPE[E.PREC_IDS[precision]], device=dev)
-    Ad[:, :2000] = 0.01
-    Bd[:, :501] = 1.0
-    ops = L.Operands()
-    ops.A, ops.B, ops.transA, ops.transB, ops.K = E.mat(Ad), E.mat(Bd), 1, 1, C2_BS
-    u = L.UpdateEpilogue()
-    scratchW = torch.zeros_like(l3.W)
-    scratchc = torch.zeros_like(l3.c)
-    scratchWb = torch.zeros_like(l3.Wb) if l3.Wb is not None else None
-    u.W, u.ldw, u.Wb = scratchW.data_ptr(), 500, E.mat(scratchWb)
-    u.vecM, u.decay, u.scale = scratchc.data_ptr(), 0.999, -1e-4
-    prec = E.PREC_IDS[precision]
+    launches = eager + steps * runner.launches_per_iter * (1 if (E._use_graphs() and not runner.tc_epoch) else 0)
+    if runner.tc_epoch:
+        # dominant kernel: mlp_tc_epoch_kernel, ONE cooperative launch per iteration (csrc/mlp_tc_epoch.cuh), timed alone
+        def one():
+            L.check(lib.dbn_mlp_fit_epoch(E.stream_ptr(), C.byref(runner.args), runner.n, runner.bs))
+        dom_ms = time_alone(one, 5)
+        dom_tf = flops_per_step / (dom_ms * 1e-3) / 1e12
+        n_mb = -(-C2_ROWS // C2_BS)
+        roof = {"bound": "tensor", "kernel": "mlp_tc_epoch_kernel: persistent tcgen05 back-propagation iteration (784-[500,500,2000]-10, %d mini-batches "
+                                             "of %d rows in one cooperative launch; 7 phases per mini-batch, grid barrier between phases)" % (n_mb, C2_BS),
+                "achieved": dom_tf, "peak": c.pk["bf16_burst"], "unit": "TFLOP/s", "frac": dom_tf / c.pk["bf16_burst"],
+                "kernel_ms": dom_ms, "us_per_minibatch": 1e3 * dom_ms / n_mb, "peak_source": c.pk["source"] + " bf16 burst (kernel timed alone)",
+                "algorithmic_flops_per_launch": flops_per_step, "traffic": C3_TC_TRAFFIC,
+                "traffic_source": "ncu dram__bytes_read+write of this launch, profiles/r02_c3_tc_epoch_full.txt (algorithmic: the iteration's input "
+                                  "rows once + every weight matrix in and out; activations and deltas stay in L2)",
+                "note": "latency-bound by construction at batch 256: seven dependent phases per mini-batch separated by grid barriers"}
+    else:
+        # dominant kernel alone: the weight-gradient contraction + decayed SGD update of the widest layer
+        # (2000 x 501 accumulator, K = 256 rows), timed back to back inside a CUDA graph
+        l3 = layers[2]
+        Ad = torch.zeros(C2_BS, E.bf16_pitch(2000), dtype=E.OP_DTYPE[E.PREC_IDS[precision]], device=dev)
+        Bd = torch.zeros(C2_BS, E.bf16_pitch(500), dtype=E.OP_DTYPE[E.PREC_IDS[precision]], device=dev)
+        Ad[:, :2000] = 0.01
+        Bd[:, :501] = 1.0
+        ops = L.Operands()
+        ops.A, ops.B, ops.transA, ops.transB, ops.K = E.mat(Ad), E.mat(Bd), 1, 1, C2_BS
+        u = L.UpdateEpilogue()
+        scratchW = torch.zeros_like(l3.W)
+        scratchc = torch.zeros_like(l3.c)
+        scratchWb = torch.zeros_like(l3.Wb) if l3.Wb is not None else None
+        u.W, u.ldw, u.Wb = scratchW.data_ptr(), 500, E.mat(scratchWb)
+        u.vecM, u.decay, u.scale = scratchc.data_ptr(), 0.999, -1e-4
+        prec = E.PREC_IDS[precision]
 
-    def dom():
-        L.check(lib.dbn_gemm_update(E.stream_ptr(), prec, 2000, 500, 0, 1, C.byref(ops), 1, C.byref(u)))
-    dom_ms = time_alone(dom, 200, graph_batch=50 if E._use_graphs() else 0)
-    dom_tf = 2.0 * C2_BS * 2000 * 501 / (dom_ms * 1e-3) / 1e12
-    roof = {"bound": "tensor", "kernel": "weight-gradient contraction + decayed SGD update of layer 3 (2000x501, K=256)",
-            "achieved": dom_tf, "peak": c.pk["bf16_burst"], "unit": "TFLOP/s", "frac": dom_tf / c.pk["bf16_burst"],
-            "kernel_ms": dom_ms, "peak_source": c.pk["source"] + " bf16 burst", "traffic": None,
-            "note": "latency-bound at batch 256 (0.5 GFLOP per launch); step_roofline is the figure of merit"}
+        def dom():
+            L.check(lib.dbn_gemm_update(E.stream_ptr(), prec, 2000, 500, 0, 1, C.byref(ops), 1, C.byref(u)))
+        dom_ms = time_alone(dom, 200, graph_batch=50 if E._use_graphs() else 0)
+        dom_tf = 2.0 * C2_BS * 2000 * 501 / (dom_ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "weight-gradient contraction + decayed SGD update of layer 3 (2000x501, K=256)",
+                "achieved": dom_tf, "peak": c.pk["bf16_burst"], "unit": "TFLOP/s", "frac": dom_tf / c.pk["bf16_burst"],
+                "kernel_ms": dom_ms, "peak_source": c.pk["source"] + " bf16 burst", "traffic": None,
+                "note": "latency-bound at batch 256 (0.5 GFLOP per launch); step_roofline is the figure of merit"}
     rec = {"metric": "backprop samples/sec", "value": C2_ROWS * steps / (ms * 1e-3), "unit": "samples/s", "steps": steps,
            "warmup": warmup, "ms_per_step": ms / steps, "config": workload_config("c3", c.world), "clocks": clocks,
            "gpu_launches": int(launches), "launches_per_minibatch": runner.launches_per_iter / max(1, -(-C2_ROWS // C2_BS)),

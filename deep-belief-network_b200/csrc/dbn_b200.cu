@@ -927,7 +927,7 @@ static int mlp_fit_epoch_tc(cudaStream_t st, const dbn_mlp_step_args* t, int n_r
   }
   a.Wo = t->Wo; a.ldwo = t->ldwo; a.bo = t->bo; a.Y = t->Y; a.ldy = t->ldy; a.loss_rows = t->loss_rows;
   a.off_bars = pl.off_bars; a.smem_bytes = pl.smem_bytes; a.wo_bytes = pl.wo_bytes;
-  a.ctl = ws.ctl; a.scratch = ws.scratch; a.trace = nullptr;
+  a.ctl = ws.ctl; a.scratch = ws.scratch; a.trace = umma_trace_ptr();
   const uint64_t xrows = (uint64_t)t->row0 + (uint64_t)n_rows;
   for (int l = 0; l < L; ++l) {
     const dbn_mat in = l == 0 ? t->X : ws.act[l - 1];

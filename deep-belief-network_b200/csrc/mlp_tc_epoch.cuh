@@ -72,6 +72,15 @@ struct MtArgs {
   long long* trace;
 };
 
+// debug trace (dbn_debug_set_trace): [cta][step < 8][phase < 13][8] clock64 stamps: 0 operands of the first tile landed (issuer 0),
+// 1 its accumulator ready (epilogue thread 0), 2 last tile's epilogue done, 3 CTA done, 4 arrived, 5 barrier passed,
+// 6 second tile's accumulator ready
+constexpr int MT_TRACE_STEPS = 8, MT_TRACE_SLOTS = MT_MAX_PHASES * 8;
+__device__ __forceinline__ void mt_trace(const MtArgs& a, int step, int p, int slot) {
+  if (a.trace != nullptr && step < MT_TRACE_STEPS)
+    a.trace[((size_t)blockIdx.x * MT_TRACE_STEPS + step) * MT_TRACE_SLOTS + p * 8 + slot] = clock64();
+}
+
 // activation derivative evaluated on the stored activation (dbn/activations.py:38, :58)
 __device__ __forceinline__ float mt_prime(int act, float g) { return act == DBN_ACT_SIGMOID ? g * (1.0f - g) : (g > 0.0f ? 1.0f : 0.0f); }
 
@@ -318,6 +327,7 @@ __global__ void __launch_bounds__(TE_THREADS, 1) mlp_tc_epoch_kernel(const __gri
             if (g.kind == MT_NONE || bid >= g.n_tiles) continue;
             te_mbar_wait(a.ctl, bar(MT_B_LD0 + gi), n_ld[gi] & 1u);
             ++n_ld[gi];
+            if (w == 0 && gi == 0) mt_trace(a, s, p, 0);
             if (n_task > 0) te_mbar_wait(a.ctl, bar(MT_B_TFREE), (n_task - 1) & 1u);   // the previous tile's accumulators are drained
             tc_fence_after();
             const int l = g.layer;
@@ -420,6 +430,7 @@ __global__ void __launch_bounds__(TE_THREADS, 1) mlp_tc_epoch_kernel(const __gri
             te_mbar_wait(a.ctl, bar(MT_B_ACC), n_acc & 1u);
             ++n_acc;
             tc_fence_after();
+            if (tid_e == 0) mt_trace(a, s, p, gi == 0 ? 1 : 6);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const int ch = wg + 4 * i;
@@ -470,6 +481,7 @@ __global__ void __launch_bounds__(TE_THREADS, 1) mlp_tc_epoch_kernel(const __gri
             te_mbar_wait(a.ctl, bar(MT_B_ACC), n_acc & 1u);
             ++n_acc;
             tc_fence_after();
+            if (tid_e == 0) mt_trace(a, s, p, gi == 0 ? 1 : 6);
             if (split) {
               // partial tile -> L2 scratch; once all partials are there every CTA of the split finishes 16-row groups
               const int tile = rbk * g.nt_cols + cb;
@@ -540,12 +552,16 @@ __global__ void __launch_bounds__(TE_THREADS, 1) mlp_tc_epoch_kernel(const __gri
           __syncwarp();
           if (lane == 0) mbar_arrive(bar(MT_B_TFREE));   // this warp has drained its share of the accumulators
         }
+        if (tid_e == 0) mt_trace(a, s, p, 2);
         if (s + 1 == steps && p == np - 1) break;
         asm volatile("bar.sync 1, %0;" ::"n"(TE_EPI_THREADS) : "memory");
         if (tid_e == 0) {
+          mt_trace(a, s, p, 3);
           te_grid_arrive(a.ctl, 0);
+          mt_trace(a, s, p, 4);
           ++n_bar;
           te_grid_wait(a.ctl, n_bar * gridDim.x);
+          mt_trace(a, s, p, 5);
           if (p + 1 < np) mt_issue_loads(a, s, p + 1, sbase, bar_base);
           else mt_issue_loads(a, s + 1, 0, sbase, bar_base);
         }
