@@ -652,7 +652,7 @@ inline bool mt_plan(int n_in, const int32_t* dims, int L, int n_out, int B, MtPl
         if (!w) continue;
         const long ab = (long)rb * 128 * kc, bb = (long)ceil_div(kc * 64, 256) * std::min(kc * 64, 256) * 128;
         if (ab + bb > slot_max) continue;
-        const long cost = ab + bb + (S > 1 ? 16384 : 0);
+        const long cost = ab + bb + (S > 1 ? 98304 : 0);   // the exchange of a split costs about as much as fetching 96 KB
         if (best < 0 || cost < best) {
           best = cost;
           MtGroup& g = bwd[l];
