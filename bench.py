@@ -521,7 +521,7 @@ def bench_c2(c, steps, warmup, with_e2e=True):
     return rec
 
 
-C3_TC_TRAFFIC = None   # ncu dram__bytes_read.sum + dram__bytes_write.sum of one mlp_tc_epoch_kernel launch (profiles/r02_c3_tc_epoch_full.txt)
+C3_TC_TRAFFIC = 122.5e6   # (algorithmic: 99.8 MB of staged input rows + 2.4 MB of targets + ~13 MB of weights in and out)  -- ncu dram__bytes_read.sum + dram__bytes_write.sum of one mlp_tc_epoch_kernel launch (profiles/r02_c3_tc_epoch_full.txt)
 
 
 def bench_c3(c, steps, warmup, with_e2e=True):

@@ -155,6 +155,12 @@ __device__ __forceinline__ void mt_head_phase(const MtArgs& a, int s, int valid,
   float acc[MT_MAX_OUT];
 #pragma unroll
   for (int c = 0; c < MT_MAX_OUT; ++c) acc[c] = 0.0f;
+  // the target and the head bias do not depend on the scores: requested first, their DRAM / L2 latency hides behind them
+  float y_pre = 0.0f, bo_pre = 0.0f;
+  if (part == 0 && row_ok && lane < C) {
+    y_pre = a.Y[(size_t)(a.row0 + s * a.B + row) * a.ldy + lane];
+    bo_pre = __ldcg(a.bo + lane);
+  }
   if (row_ok) {
     for (int k = (part * 32 + lane) * 8; k < K; k += 2048) {   // (K % 8 == 0: plan)
       const uint4 t = __ldcg(reinterpret_cast<const uint4*>(arow + k));
@@ -192,9 +198,9 @@ __device__ __forceinline__ void mt_head_phase(const MtArgs& a, int s, int valid,
     if (lv) {
 #pragma unroll
       for (int q = 0; q < 8; ++q) z += partial[r_in][q][lane];
-      z += __ldcg(a.bo + lane);
+      z += bo_pre;
     }
-    const float y = lv ? a.Y[(size_t)(a.row0 + s * a.B + row) * a.ldy + lane] : 0.0f;
+    const float y = lv ? y_pre : 0.0f;
     float o_val = z, loss = 0.0f;
     if (a.head == DBN_HEAD_SOFTMAX) {
       float mx = lv ? z : -INFINITY;
