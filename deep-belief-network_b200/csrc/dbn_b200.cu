@@ -521,7 +521,10 @@ static int rbm_fit_epoch_tc(cudaStream_t st, const dbn_rbm_step_args* t, int n_r
   attr[0].val.cooperative = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  DBN_CUDA_OK(cudaLaunchKernelEx(&cfg, rbm_tc_epoch_kernel, a));
+  if (cudaLaunchKernelEx(&cfg, rbm_tc_epoch_kernel, a) != cudaSuccess) {
+    (void)cudaGetLastError();   // e.g. the grid cannot be co-resident right now (another context on the GPU): tiled path
+    return DBN_OK;
+  }
   DBN_LAUNCH_CHECK();
   *done = 1;
   return DBN_OK;
@@ -960,7 +963,10 @@ static int mlp_fit_epoch_tc(cudaStream_t st, const dbn_mlp_step_args* t, int n_r
   attr[0].val.cooperative = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  DBN_CUDA_OK(cudaLaunchKernelEx(&cfg, mlp_tc_epoch_kernel, a));
+  if (cudaLaunchKernelEx(&cfg, mlp_tc_epoch_kernel, a) != cudaSuccess) {
+    (void)cudaGetLastError();   // e.g. the grid cannot be co-resident right now: tiled path
+    return DBN_OK;
+  }
   DBN_LAUNCH_CHECK();
   *done = 1;
   return DBN_OK;

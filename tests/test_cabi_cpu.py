@@ -86,3 +86,30 @@ def test_invalid_arguments_are_rejected_before_any_launch():
     lib = G.lib()
     assert lib.dbn_rbm_fit_epoch(None, None, 10, 4) == L.ERR_INVALID_ARG
     assert lib.dbn_philox_uniforms_host(0, 0, 0, 0, 1, 1, None) == L.ERR_INVALID_ARG
+
+
+def test_persistent_kernel_plans_are_pure_host_functions():
+    """The tile plans of the two persistent tcgen05 kernels (csrc/rbm_tc_epoch.cuh, csrc/mlp_tc_epoch.cuh) are computed on
+    the host: every phase fits the 148 SMs of a B200 and 227 KB of shared memory; shapes outside the plan report 0."""
+    import ctypes as C
+    lib = L.load()
+    out = (C.c_int32 * 16)()
+    for (V, H, B) in [(784, 500, 256), (500, 500, 256), (500, 2000, 256), (256, 256, 32), (64, 128, 16)]:
+        m = lib.dbn_rbm_tc_epoch_plan_info(V, H, B, out, 16)
+        assert m >= 16, (V, H, B)
+        ctas, hid_tiles, vis_tiles, dw_tiles, smem = out[0], out[3], out[8], out[10], out[11]
+        assert 0 < ctas <= 148 and max(hid_tiles, vis_tiles, dw_tiles) == ctas and 0 < smem <= 232448
+        assert out[1] in (32, 64) and out[2] % 8 == 0 and out[5] % 8 == 0 and out[9] % 8 == 0 and out[9] <= 128
+        assert lib.dbn_rbm_tc_epoch_plan(L.PREC_BF16, V, H, B) == ctas and lib.dbn_rbm_tc_epoch_plan(L.PREC_FP32, V, H, B) == 0
+    assert lib.dbn_rbm_tc_epoch_plan_info(4096, 4096, 256, out, 16) == 0      # config 5: CTA-pair kernels
+    assert lib.dbn_rbm_tc_epoch_plan_info(784, 500, 512, out, 16) == 0        # mini-batch beyond one tile of the dW contraction
+    assert lib.dbn_rbm_tc_epoch_plan_info(13, 100, 16, out, 16) == 0          # config 4: FP32 cluster kernel
+    dims = (C.c_int32 * 3)(500, 500, 2000)
+    assert 0 < lib.dbn_mlp_tc_epoch_plan(L.PREC_BF16, 784, dims, 3, 10, 256) <= 148
+    assert lib.dbn_mlp_tc_epoch_plan(L.PREC_FP32, 784, dims, 3, 10, 256) == 0
+    assert lib.dbn_mlp_tc_epoch_plan(L.PREC_BF16, 784, dims, 3, 100, 256) == 0   # wide head: tiled path
+    five = (C.c_int32 * 5)(128, 128, 128, 128, 128)
+    assert lib.dbn_mlp_tc_epoch_plan(L.PREC_BF16, 784, five, 5, 10, 256) == 0     # more than 4 hidden layers
+    prev = lib.dbn_set_tc_finetune(0)
+    assert lib.dbn_mlp_tc_epoch_plan(L.PREC_BF16, 784, dims, 3, 10, 256) == 0
+    lib.dbn_set_tc_finetune(prev)
