@@ -13,7 +13,7 @@ import warnings
 import numpy as np
 
 _LIB = None        # None = not tried, False = unavailable
-_THREADS = max(1, min(8, os.cpu_count() or 1))   # helper threads of the finishing pass (log / sqrt of the accepted pairs)
+_THREADS = max(1, min(8, (os.cpu_count() or 2) - 1))   # worker threads (the calling thread produces the MT19937 words meanwhile)
 
 
 def _raw(fn, rs_state, n):

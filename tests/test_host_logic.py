@@ -196,6 +196,29 @@ def test_legacy_randn_is_np_random_randn_bit_for_bit():
         assert tail_ref[0] == tail_got[0] and np.array_equal(tail_ref[1], tail_got[1]) and np.array_equal(tail_ref[2], tail_got[2])
 
 
+def test_legacy_randn_parallel_path_is_bit_exact_too():
+    """Half a million draws and more take the fully threaded path of csrc/host_rng.c (rejection pass on worker threads,
+    only the MT19937 recurrence sequential): same values and same generator state as np.random.randn, for even / odd
+    lengths, with and without a cached Gaussian, ending inside and at the edge of a chunk."""
+    from dbn_b200 import _hostrng as R
+    assert R.available()
+    for seed, pre, shapes in ((3, 0, [(1 << 19,), (1025, 1031)]), (11, 1, [((1 << 19) + 1,), (700, 1500), (5,)]),
+                              (42, 2, [(2048, 2049)])):
+        np.random.seed(seed)
+        if pre:
+            np.random.randn(pre)
+        ref = [np.random.randn(*s) for s in shapes]
+        tail_ref = (np.random.random_sample(), np.random.randn(3), np.random.get_state()[2])
+        np.random.seed(seed)
+        if pre:
+            np.random.randn(pre)
+        got = [R.legacy_randn(*s) for s in shapes]
+        tail_got = (np.random.random_sample(), np.random.randn(3), np.random.get_state()[2])
+        for a, b in zip(ref, got):
+            assert a.shape == b.shape and np.array_equal(a.view(np.uint64), b.view(np.uint64))
+        assert tail_ref[0] == tail_got[0] and np.array_equal(tail_ref[1], tail_got[1]) and tail_ref[2] == tail_got[2]
+
+
 def test_rbm_parameter_init_is_the_reference_stream():
     """BinaryRBM._draw_params consumes np.random exactly like dbn/models.py:55-69 (W, then c, then b)."""
     np.random.seed(11)
