@@ -87,3 +87,18 @@ def test_plan_falls_back():
     assert l.dbn_rbm_tc_epoch_plan(1, 4096, 4096, 256) == 0      # config 5: CTA-pair kernels
     assert l.dbn_rbm_tc_epoch_plan(0, 784, 500, 256) == 0        # strict FP32: SIMT / cluster kernel
     assert l.dbn_rbm_tc_epoch_plan(1, 784, 500, 256) > 0
+
+
+@pytest.mark.parametrize("V,H", [(784, 500), (500, 2000)])
+def test_full_size_epochs_are_reproducible(V, H):
+    """BASELINE config 2 at its full size (60000 rows = 235 mini-batches per launch, 940 grid barriers): two runs from
+    the same state give bit-identical parameters -- every hand-off of the kernel (L2 barrier, TMA refills of activations
+    other CTAs wrote, split-K scratch, fixed-point statistics) is ordered, none is a race that happens to work."""
+    rng = np.random.default_rng(V)
+    W, b, c = _layer(rng, V, H)
+    X = (rng.random((60000, V)) < 0.13).astype(np.float32)
+    runs = [run_rbm_epoch(W, b, c, X, 256, 1, "sigmoid", "fp16", seed=9, lr=0.01, tc_epoch=True, epochs=2) for _ in range(2)]
+    assert runs[0]["launches"] <= 4
+    for k in ("W", "b", "c", "Wb"):
+        assert np.array_equal(runs[0][k], runs[1][k]), k
+    assert np.all(np.isfinite(runs[0]["W"])) and np.linalg.norm(runs[0]["W"] - W) > 0
