@@ -13,6 +13,7 @@ import warnings
 import numpy as np
 
 _LIB = None        # None = not tried, False = unavailable
+_LIB_F32 = None    # dbn_host_legacy_randn_f32 of the same library
 _THREADS = max(1, min(8, (os.cpu_count() or 2) - 1))   # worker threads (the calling thread produces the MT19937 words meanwhile)
 
 
@@ -55,6 +56,12 @@ def _load():
                                C.c_size_t, C.c_int]
                 if _self_check(fn):
                     _LIB = fn
+                    global _LIB_F32
+                    f32 = C.CDLL(path).dbn_host_legacy_randn_f32
+                    f32.restype = C.c_int
+                    f32.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double), C.c_void_p,
+                                    C.c_size_t, C.c_double, C.c_int]
+                    _LIB_F32 = f32
                 else:
                     warnings.warn("dbn_b200: libdbn_hostrng.so does not reproduce np.random.randn here; using NumPy")
             except (OSError, AttributeError):
@@ -80,3 +87,25 @@ def legacy_randn(*shape):
         return np.random.randn(*shape)
     np.random.set_state(new_state)
     return out.reshape(shape) if shape else float(out[0])
+
+
+def legacy_randn_f32(out, divisor):
+    """out[...] = float32(np.random.randn(*out.shape) / divisor) with the same effect on the global np.random state:
+    initial weights in the form the device stores them, written straight into `out` (a C-contiguous float32 array,
+    typically pinned memory about to be uploaded) -- no float64 array of the layer's size on the way."""
+    assert out.dtype == np.float32 and out.flags.c_contiguous
+    n = int(out.size)
+    _load()
+    st = np.random.get_state() if (_LIB_F32 and n >= 4096) else None
+    if st is not None and st[0] == 'MT19937':
+        key = np.ascontiguousarray(st[1], dtype=np.uint32).copy()
+        pos, has_gauss, gauss = C.c_int(int(st[2])), C.c_int(int(st[3])), C.c_double(float(st[4]))
+        rc = _LIB_F32(key.ctypes.data, C.byref(pos), C.byref(has_gauss), C.byref(gauss), out.ctypes.data, n, float(divisor),
+                      _THREADS)
+        if rc == 0:
+            np.random.set_state(('MT19937', key, pos.value, has_gauss.value, gauss.value))
+            return out
+        if rc != -1:
+            raise RuntimeError("dbn_host_legacy_randn_f32 failed after consuming part of the stream")
+    out[...] = np.random.randn(*out.shape) / divisor
+    return out

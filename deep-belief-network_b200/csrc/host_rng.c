@@ -274,6 +274,8 @@ struct par_ctx {
   size_t base;           /* pairs accepted by earlier chunks */
   /* the call */
   double* out;           /* where pair 0 goes */
+  float* out32;          /* instead of `out`, when set: (float)(value / divisor) -- initial weights in the device's form */
+  double divisor;
   size_t want, full_pairs;
   double last[2];        /* the odd pair: first half, second half */
 };
@@ -315,8 +317,13 @@ static void* par_worker(void* arg) {
       const double f = sqrt(-2.0 * log(rr) / rr);
       const size_t g = off + i;
       if (g < cx->full_pairs) {
-        cx->out[2 * g] = f * j->px[sl][2 * i];
-        cx->out[2 * g + 1] = f * j->px[sl][2 * i + 1];
+        if (cx->out32) {
+          cx->out32[2 * g] = (float)(f * j->px[sl][2 * i] / cx->divisor);
+          cx->out32[2 * g + 1] = (float)(f * j->px[sl][2 * i + 1] / cx->divisor);
+        } else {
+          cx->out[2 * g] = f * j->px[sl][2 * i];
+          cx->out[2 * g + 1] = f * j->px[sl][2 * i + 1];
+        }
       } else {                                       /* the odd pair: its second half stays cached in the generator */
         cx->last[0] = f * j->px[sl][2 * i];
         cx->last[1] = f * j->px[sl][2 * i + 1];
@@ -327,7 +334,8 @@ static void* par_worker(void* arg) {
 }
 
 /* n >= PAR_MIN_N draws on nt >= 2 threads.  Returns 0 on success; -1 if nothing was consumed (no memory / threads). */
-static int randn_parallel(uint32_t* key, int* pos, int* has_gauss, double* gauss, double* out, size_t n, int nt) {
+static int randn_parallel(uint32_t* key, int* pos, int* has_gauss, double* gauss, double* out, size_t n, int nt,
+                          float* out32, double divisor) {
   size_t done = 0, full_pairs, want, base = 0;
   int odd, cur = 0, t, p = *pos, started = 0, in_flight = 0;
   uint32_t key_work[MT_N], snap_key[2][MT_N];
@@ -382,11 +390,16 @@ static int randn_parallel(uint32_t* key, int* pos, int* has_gauss, double* gauss
     return -1;
   }
   memcpy(key_work, key, sizeof(key_work));
-  if (*has_gauss) out[done++] = *gauss;
+  if (*has_gauss) {
+    if (out32) out32[done++] = (float)(*gauss / divisor);
+    else out[done++] = *gauss;
+  }
   full_pairs = (n - done) / 2;
   odd = (int)((n - done) & 1);
   want = full_pairs + (size_t)odd;
-  cx->out = out + done;
+  cx->out = out32 ? 0 : out + done;
+  cx->out32 = out32 ? out32 + done : 0;
+  cx->divisor = divisor;
   cx->want = want;
   cx->full_pairs = full_pairs;
   for (;;) {
@@ -425,7 +438,8 @@ static int randn_parallel(uint32_t* key, int* pos, int* has_gauss, double* gauss
           left -= take;
         }
         if (odd) {
-          out[n - 1] = cx->last[0];
+          if (out32) out32[n - 1] = (float)(cx->last[0] / divisor);
+          else out[n - 1] = cx->last[0];
           *gauss = cx->last[1];
           *has_gauss = 1;
         } else {
@@ -467,7 +481,7 @@ int dbn_host_legacy_randn(uint32_t* key, int* pos, int* has_gauss, double* gauss
   int odd, cur = 0;
   if (n == 0) return 0;
   if (n >= PAR_MIN_N && n_threads >= 2) {
-    if (randn_parallel(key, pos, has_gauss, gauss, out, n, n_threads) == 0) return 0;
+    if (randn_parallel(key, pos, has_gauss, gauss, out, n, n_threads, 0, 1.0) == 0) return 0;
   }
   r2[0] = (double*)malloc(2 * sizeof(double) * CHUNK_PAIRS + sizeof(pair_stream));
   if (!r2[0]) return -1;
@@ -509,5 +523,34 @@ int dbn_host_legacy_randn(uint32_t* key, int* pos, int* has_gauss, double* gauss
   }
   *pos = stream_pos(s);
   free(r2[0]);
+  return 0;
+}
+
+/* out32[i] = (float)(g_i / divisor) for the same n draws g_i (and the same final state) as dbn_host_legacy_randn: the
+ * initial weights `np.random.randn(h, v) / sqrt(v)` (dbn/models.py:55-57) in the form the device takes them, written
+ * straight into (pinned) memory -- no float64 array of the layer's size, no divide pass, no narrowing pass.  Each value
+ * goes through the same two roundings as NumPy's `(randn / s).astype(float32)`. */
+int dbn_host_legacy_randn_f32(uint32_t* key, int* pos, int* has_gauss, double* gauss, float* out32, size_t n, double divisor,
+                              int n_threads) {
+  size_t done = 0;
+  double* tmp;
+  if (n == 0) return 0;
+  if (!out32 || divisor == 0.0) return -1;
+  if (n >= PAR_MIN_N && n_threads >= 2 &&
+      randn_parallel(key, pos, has_gauss, gauss, 0, n, n_threads, out32, divisor) == 0)
+    return 0;
+  tmp = (double*)malloc((n < 65536 ? n : 65536) * sizeof(double));
+  if (!tmp) return -1;
+  while (done < n) {       /* small draws (or no threads): the sequential path, a cache-sized piece at a time */
+    const size_t m = n - done < 65536 ? n - done : 65536;
+    size_t i;
+    if (dbn_host_legacy_randn(key, pos, has_gauss, gauss, tmp, m, 1) != 0) {
+      free(tmp);
+      return done == 0 ? -1 : -2;       /* -2: the state has advanced */
+    }
+    for (i = 0; i < m; i++) out32[done + i] = (float)(tmp[i] / divisor);
+    done += m;
+  }
+  free(tmp);
   return 0;
 }

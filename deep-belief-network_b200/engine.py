@@ -135,6 +135,9 @@ class _PinnedPool:
                     idle = ev is None or ev.query()
                     if pick is None or (idle and not pick[1]) or (idle == pick[1] and buf.numel() < cls._free[pick[0]][0].numel()):
                         pick = (i, idle)
+            if pick is not None and not pick[1] and nbytes <= (1 << 20):
+                pick = None     # only busy candidates: a small buffer is cheaper to allocate than to wait for (its last
+                                # copy may sit behind a multi-gigabyte upload in the copy engine's queue)
             if pick is not None:
                 buf, ev = cls._free.pop(pick[0])
             else:
@@ -150,6 +153,35 @@ class _PinnedPool:
         with cls._lock:
             if len(cls._free) < 64:
                 cls._free.append((buf, ev))
+
+
+_POOLED = {}     # id(ndarray) -> (ndarray, pinned buffer): host arrays living in pooled pinned memory (pooled_f32)
+
+
+def pooled_f32(shape):
+    """Float32 ndarray of `shape` in pooled pinned memory, or None when too many are outstanding.  For host data that is
+    produced only to be uploaded (initial weights drawn straight in the device's form): the upload is one DMA from
+    where the values were written, and `release_pooled` hands the memory back once that copy has been queued."""
+    if len(_POOLED) >= 8:
+        return None
+    n = int(np.prod(shape))
+    buf, _ev = _PinnedPool.take(n * 4)
+    a = buf[:n * 4].view(torch.float32).view(*shape).numpy()
+    _POOLED[id(a)] = (a, buf)
+    return a
+
+
+def release_pooled(a, device=None):
+    """Give a pooled_f32 array back (after the copies that read it were queued on the upload stream); the array must not
+    be touched afterwards.  False if `a` is not one."""
+    ent = _POOLED.get(id(a)) if isinstance(a, np.ndarray) else None
+    if ent is None or ent[0] is not a:
+        return False
+    del _POOLED[id(a)]
+    ev = torch.cuda.Event()
+    ev.record(_upload_stream(device if device is not None else torch.device("cuda", torch.cuda.current_device())))
+    _PinnedPool.give(ent[1], ev)
+    return True
 
 
 _UPLOAD_STREAMS = {}
@@ -209,6 +241,61 @@ def upload_f32(arr, device):
     dev.record_stream(cur)        # allocated in the upload stream's pool, used on the compute stream
     return dev
 
+
+def is_pinned_f32(arr):
+    """Is this host array something the copy engine can read in place (float32, C-contiguous, page-locked)."""
+    return (isinstance(arr, np.ndarray) and arr.dtype == np.float32 and arr.flags.c_contiguous and arr.size > 0 and
+            torch.from_numpy(arr).is_pinned())
+
+
+def operand_upload_wanted(precision, n, cols):
+    """Should a dataset of n x cols host rows go up as 16-bit operands (upload_operand) rather than as fp32 rows: a
+    tensor-core precision, the host helper present, and enough bytes for the PCIe time to matter."""
+    from . import _hoststage
+    precision = PREC_IDS.get(precision, precision)
+    return (precision in TC_PRECS and n * cols >= (1 << 20) and os.environ.get("DBN_B200_OPERAND_UPLOAD", "1") != "0" and
+            _hoststage.available())
+
+
+def upload_operand(arr, device, precision):
+    """Host rows -> new device tensor in the OPERAND layout of a tensor-core precision ([n, bf16_pitch(cols)] 16-bit:
+    rounded row | ones column | zero padding), returned as its [n, cols] view.  Host threads round piece i+1 into pooled
+    pinned memory exactly as the device's staging kernel would (csrc/host_stage.c) while piece i is in flight on the
+    upload stream: half the PCIe bytes of upload_f32 -- the bound of an end-to-end fit of a large dataset -- and
+    bit-identical operands, since the tensor-core path reads the rows through this rounding anyway.  The source needs
+    no pinning (the threads read it with plain loads); like upload_f32 it does not wait for the compute stream."""
+    from . import _hoststage
+    arr = np.asarray(arr)
+    n, cols = int(arr.shape[0]), int(arr.shape[1])
+    dt = OP_DTYPE[PREC_IDS.get(precision, precision)]
+    kind = _hoststage.kind_of(dt)
+    pitch = bf16_pitch(cols)
+    up = _upload_stream(device)
+    cur = torch.cuda.current_stream(device)
+    with torch.cuda.stream(up):
+        dev = torch.empty(n, pitch, dtype=dt, device=device)
+    fast = arr.dtype == np.float32 and arr.flags.c_contiguous
+    rows_per = max(1, min(n, _OPERAND_PIECE // (2 * pitch)))
+    bufs = [_PinnedPool.take(rows_per * pitch * 2) for _ in range(min(3, (n + rows_per - 1) // rows_per))]
+    for i, s0 in enumerate(range(0, n, rows_per)):
+        buf, ev = bufs[i % len(bufs)]
+        if i >= len(bufs):
+            ev.synchronize()                          # the DMA that last read this buffer has finished
+        m = min(rows_per, n - s0)
+        stage = buf[:m * pitch * 2].view(dt).view(m, pitch)
+        src = arr[s0:s0 + m] if fast else np.ascontiguousarray(arr[s0:s0 + m], dtype=np.float32)
+        _hoststage.stage_rows(src, None, stage.data_ptr(), pitch, kind, True)
+        with torch.cuda.stream(up):
+            dev[s0:s0 + m].copy_(stage, non_blocking=True)
+            ev.record(up)
+    for buf, ev in bufs:
+        _PinnedPool.give(buf, ev)
+    cur.wait_stream(up)
+    dev.record_stream(cur)
+    return dev[:, :cols]
+
+
+_OPERAND_PIECE = 16 << 20   # bytes of 16-bit rows per piece of upload_operand
 
 _CAST_POOL = None
 
@@ -471,7 +558,11 @@ def fit_rbm_data_parallel(layer, X_host, n_epochs, batch_size, k, lr, seed, dp, 
             reason = str(e)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)   # all ranks take the same path
         if int(ok.item()) == 1:
-            Xl = upload_f32(X_host[rank * nl:(rank + 1) * nl], dev)
+            mine = X_host[rank * nl:(rank + 1) * nl]
+            if verbose is None and not is_pinned_f32(mine) and operand_upload_wanted(layer.prec, nl, V):
+                Xl = upload_operand(mine, dev, layer.prec)     # rounded on the host: half the PCIe bytes
+            else:
+                Xl = upload_f32(mine, dev)
             runner = dp_peer.DpPeerRunner(layer, Xl, n, batch_size, k, lr, seed, group.member)
         else:
             if group is not None:

@@ -26,7 +26,7 @@ from scipy.stats import truncnorm
 from sklearn.base import BaseEstimator, ClassifierMixin, RegressorMixin, TransformerMixin
 
 from . import engine as E
-from ._hostrng import legacy_randn
+from ._hostrng import legacy_randn, legacy_randn_f32
 from .activations import ReLUActivationFunction, SigmoidActivationFunction
 
 
@@ -45,6 +45,21 @@ def _to_device_f32(X):
     if t.is_pinned():
         return t.to(_device(), non_blocking=True)
     return t.to(_device())
+
+
+def _to_device_rows(X, precision_of_first_layer, quiet):
+    """The dataset a pre-training run reads, on the device.  When its only consumer is a tensor-core layer (which reads
+    the rows through a 16-bit rounding anyway) and nothing else needs the un-rounded values (the verbose
+    reconstruction error does), the rows are rounded on the host and go up as 16-bit operands: same numbers, half the
+    PCIe bytes (engine.upload_operand), and a pageable source needs no driver staging.  Otherwise fp32 rows; a caller who
+    page-locked a float32 dataset gets the single DMA straight from it (at 55 GB/s that beats rounding 2 GB on eight
+    host threads: tools/e2e_c5_probe.py)."""
+    X = np.asarray(X)
+    if quiet and X.ndim == 2 and X.shape[0] > 0 and not E.is_pinned_f32(X):
+        prec = precision_of_first_layer(int(X.shape[1]))
+        if E.operand_upload_wanted(prec, int(X.shape[0]), int(X.shape[1])):
+            return E.upload_operand(X, _device(), prec)
+    return _to_device_f32(X)
 
 
 def _resident(n, v, h):
@@ -162,10 +177,18 @@ class BinaryRBM(BaseEstimator, TransformerMixin, BaseModel):
         self.rng = rng
 
     # ---- parameter initialisation: same draws, same order as dbn/models.py:55-69 ----
-    def _draw_params(self, n_visible):
+    def _draw_params(self, n_visible, for_upload=False):
+        """Initial parameters (dbn/models.py:55-69).  for_upload: the weights are about to be uploaded and trained, so
+        nobody will read them on the host -- a large sigmoid layer is then drawn straight as the fp32 the device stores,
+        into pooled pinned memory (same np.random draws, each value rounded as the upload would round it): no float64
+        array of the layer's size, no divide pass, no narrowing pass on the critical path of the fit."""
         h, s = self.n_hidden_units, np.sqrt(n_visible)
         if self.activation_function == 'sigmoid':   # legacy_randn == np.random.randn, bit for bit (see _hostrng.py)
-            W = legacy_randn(h, n_visible) / s
+            W = E.pooled_f32((h, n_visible)) if (for_upload and h * n_visible >= (1 << 20)) else None
+            if W is not None:
+                legacy_randn_f32(W, s)
+            else:
+                W = legacy_randn(h, n_visible) / s
             c = legacy_randn(h) / s
             b = legacy_randn(n_visible) / s
             return W, c, b, SigmoidActivationFunction
@@ -178,8 +201,20 @@ class BinaryRBM(BaseEstimator, TransformerMixin, BaseModel):
         self.n_visible_units = n_visible
         self.W, self.c, self.b, self._activation_function_class = drawn if drawn is not None else self._draw_params(n_visible)
 
+    def _upload_initial(self):
+        """The freshly initialised layer on the device.  Weights that were drawn into pooled pinned memory
+        (_draw_params(for_upload=True)) are handed back once their upload is queued; `W` is then unset until the fitted
+        parameters are adopted."""
+        layer = self._device_layer()
+        if E.release_pooled(self.W):
+            self.W = None
+        return layer
+
     def _resolved_precision(self):
-        return E.resolve_precision(self.precision, self.n_visible_units, self.n_hidden_units, self.batch_size,
+        return self._precision_for(self.n_visible_units)
+
+    def _precision_for(self, n_visible):
+        return E.resolve_precision(self.precision, n_visible, self.n_hidden_units, self.batch_size,
                                    activation=self.activation_function, phase="pretrain")
 
     def _device_layer(self, precision=None):
@@ -209,7 +244,7 @@ class BinaryRBM(BaseEstimator, TransformerMixin, BaseModel):
         self._init_params(int(Xd.shape[1]), draws.get() if draws is not None else None)
         if self.optimization_algorithm != 'sgd':
             raise ValueError("Invalid optimization algorithm.")
-        layer = self._device_layer()
+        layer = self._upload_initial()
         if draws is not None:
             seed = draws.get()
         else:
@@ -226,7 +261,7 @@ class BinaryRBM(BaseEstimator, TransformerMixin, BaseModel):
     def _draw_jobs(self, n, n_features):
         """The np.random draws of one fit, in sequential order (generator for _DrawAhead): parameters, Philox key,
         one double shuffle per epoch."""
-        yield self._draw_params(n_features)
+        yield self._draw_params(n_features, for_upload=(n > 0 and self.n_epochs > 0))
         yield _draw_seed()
         for _ in range(self.n_epochs if n > 0 else 0):
             yield E.epoch_order(n)
@@ -259,6 +294,7 @@ class BinaryRBM(BaseEstimator, TransformerMixin, BaseModel):
                 draws = _DrawAhead(self._draw_jobs(n, v))      # drawn while the rows upload
                 W, c, b, _cls = draws.get()
                 layer = E.DeviceRbm(W, b, c, self.activation_function, precision, dev)
+                E.release_pooled(W, dev)
                 seed = draws.get()
                 seed_t.fill_(seed - (1 << 64) if seed >= (1 << 63) else seed)
             else:
@@ -291,7 +327,7 @@ class BinaryRBM(BaseEstimator, TransformerMixin, BaseModel):
         self._init_params(int(X.shape[1]), draws.get() if draws is not None else None)
         if self.optimization_algorithm != 'sgd':
             raise ValueError("Invalid optimization algorithm.")
-        layer = self._device_layer()
+        layer = self._upload_initial()
         seed = draws.get() if draws is not None else _draw_seed()
         runner = E.HostRbmEpochRunner(layer, X, self.batch_size, self.contrastive_divergence_iter, self.learning_rate, seed)
         import torch
@@ -319,7 +355,7 @@ class BinaryRBM(BaseEstimator, TransformerMixin, BaseModel):
             if X.ndim == 2 and X.shape[0] * self.n_hidden_units >= (1 << 16):
                 draws = _DrawAhead(self._draw_jobs(int(X.shape[0]), int(X.shape[1])))
         try:
-            self._fit_device(_to_device_f32(X), draws=draws)
+            self._fit_device(_to_device_rows(X, self._precision_for, not self.verbose), draws=draws)
         finally:
             if draws is not None:
                 draws.close()
@@ -404,7 +440,7 @@ class UnsupervisedDBN(BaseEstimator, TransformerMixin, BaseModel):
         """The np.random draws of one greedy pre-training run, in sequential order (generator for _DrawAhead)."""
         v = n_features
         for rbm in self.rbm_layers:
-            yield rbm._draw_params(v)
+            yield rbm._draw_params(v, for_upload=(n > 0 and rbm.n_epochs > 0))
             yield _draw_seed()
             for _ in range(rbm.n_epochs if n > 0 else 0):
                 yield E.epoch_order(n)
@@ -440,7 +476,10 @@ class UnsupervisedDBN(BaseEstimator, TransformerMixin, BaseModel):
         """Pre-train every layer on the previous layer's features (dbn/models.py:248-276)."""
         if self._out_of_core(np.shape(X)):
             return self._fit_host(X)
-        return self._fit_device(_to_device_f32(X))
+        first = lambda v: E.resolve_precision(self.precision, v, self.hidden_layers_structure[0], self.batch_size,
+                                              activation=self.activation_function, phase="pretrain")
+        quiet = not self.verbose and self.rbm_class is BinaryRBM and len(self.hidden_layers_structure) > 0
+        return self._fit_device(_to_device_rows(X, first, quiet))
 
     def _transform_device(self, Xd):
         for rbm in self.rbm_layers:

@@ -35,7 +35,7 @@ def test_host_helper_library_exports_its_header():
     """include/dbn_hostrng.h <-> libdbn_hostrng.so (host-side C helper, no CUDA)."""
     src = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "dbn_hostrng.h")).read(), flags=re.S)
     declared = set(re.findall(r"\b(dbn_[a-z0-9_]+)\s*\(", src))
-    assert declared == {"dbn_host_legacy_randn"}
+    assert declared == {"dbn_host_legacy_randn", "dbn_host_legacy_randn_f32", "dbn_host_stage_rows"}
     lib = C.CDLL(os.path.join(ROOT, "deep-belief-network_b200", "libdbn_hostrng.so"))
     for name in declared:
         assert hasattr(lib, name)

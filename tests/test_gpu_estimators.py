@@ -408,3 +408,66 @@ def test_out_of_core_supervised_fit_equals_the_resident_fit(kind, precision, dro
     assert np.array_equal(res.W, ooc.W) and np.array_equal(res.b, ooc.b)
     monkeypatch.delenv("DBN_B200_RESIDENT_BYTES")
     assert np.array_equal(np.asarray(res.predict(X[:20])), np.asarray(ooc.predict(X[:20])))
+
+
+@pytest.mark.parametrize("act,precision", [("sigmoid", "auto"), ("relu", "auto"), ("sigmoid", "bf16")])
+def test_operand_upload_equals_the_fp32_upload(act, precision, monkeypatch):
+    """engine.upload_operand: the dataset of a tensor-core fit is rounded to the 16-bit operand type on the HOST
+    (csrc/host_stage.c) and goes up as operand rows -- half the PCIe bytes.  The rounding is the device staging
+    kernel's, so the trained parameters must be BIT-IDENTICAL to the fp32 upload, on data that is NOT exactly
+    representable in 16 bits, through BinaryRBM.fit and the stacked fit, with the upload split into many pieces."""
+    from dbn_b200 import engine as E
+    rng = np.random.default_rng(5)
+    N, V, hs, bs = 2100 + 37, 520, [192, 128], 128
+    X = rng.random((N, V)).astype(np.float32) ** 3
+    X64 = X.astype(np.float64)                   # a float64 caller goes through the same rounding (f64 -> f32 -> 16 bit)
+    monkeypatch.setattr(E, "_OPERAND_PIECE", 300 * 1024)
+    calls = []
+    real = E.upload_operand
+    monkeypatch.setattr(E, "upload_operand", lambda *a, **k: (calls.append(E.PREC_IDS.get(a[2], a[2])), real(*a, **k))[1])
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("DBN_B200_OPERAND_UPLOAD", mode)
+        np.random.seed(21)
+        r = BinaryRBM(n_hidden_units=hs[0], activation_function=act, learning_rate=0.02, n_epochs=2, batch_size=bs,
+                      verbose=False, precision=precision).fit(X if mode == "1" else X64)
+        np.random.seed(22)
+        d = UnsupervisedDBN(hidden_layers_structure=hs, activation_function=act, learning_rate_rbm=0.02, n_epochs_rbm=2,
+                            batch_size=bs, verbose=False, precision=precision).fit(X64 if mode == "1" else X)
+        out[mode] = (r, d)
+    want = {"sigmoid": E.L.PREC_F16, "relu": E.L.PREC_BF16}[act] if precision == "auto" else E.L.PREC_BF16
+    assert calls == [want, want], "the 16-bit upload must have run (twice) in mode 1 only"
+    (r1, d1), (r0, d0) = out["1"], out["0"]
+    assert np.array_equal(r1.W, r0.W) and np.array_equal(r1.b, r0.b) and np.array_equal(r1.c, r0.c)
+    for a, b in zip(d1.rbm_layers, d0.rbm_layers):
+        assert np.array_equal(a.W, b.W) and np.array_equal(a.b, b.b) and np.array_equal(a.c, b.c)
+    assert np.linalg.norm(r1.W) > 0 and np.all(np.isfinite(r1.W))
+
+
+def test_weights_drawn_in_device_form_equal_the_float64_draw(monkeypatch):
+    """A large sigmoid layer's initial weights are drawn by the helper thread straight as fp32 into pooled pinned memory
+    (csrc/host_rng.c dbn_host_legacy_randn_f32: no float64 array, no divide pass, no narrowing pass before the upload).
+    Same np.random stream, same rounding: the fit must be bit-identical to the sequential float64 draw, and the
+    stream must be left where the reference leaves it."""
+    from dbn_b200 import engine as E
+    rng = np.random.default_rng(8)
+    N, V, hs, bs = 512 + 19, 1000, [1100, 1000], 128
+    X = (rng.random((N, V)) < 0.2).astype(np.float32)
+    out = {}
+    for ahead in ("1", "0"):
+        monkeypatch.setenv("DBN_B200_DRAW_AHEAD", ahead)
+        np.random.seed(31)
+        r = BinaryRBM(n_hidden_units=hs[0], learning_rate=0.02, n_epochs=1, batch_size=bs, verbose=False).fit(X)
+        d = UnsupervisedDBN(hidden_layers_structure=hs, learning_rate_rbm=0.02, n_epochs_rbm=2, batch_size=bs, verbose=False).fit(X)
+        out[ahead] = (r, d, np.random.randn(3))
+        assert not E._POOLED, "every pooled array must have been handed back"
+    (r1, d1, t1), (r0, d0, t0) = out["1"], out["0"]
+    assert np.array_equal(t1, t0)
+    assert np.array_equal(r1.W, r0.W) and np.array_equal(r1.b, r0.b) and np.array_equal(r1.c, r0.c)
+    for a, b in zip(d1.rbm_layers, d0.rbm_layers):
+        assert np.array_equal(a.W, b.W) and np.array_equal(a.b, b.b) and np.array_equal(a.c, b.c)
+    # zero epochs: the float64 draw goes through the device (fp32) and comes back un-trained
+    np.random.seed(31)
+    z = BinaryRBM(n_hidden_units=hs[0], n_epochs=0, batch_size=bs, verbose=False).fit(X)
+    np.random.seed(31)
+    assert z.W.dtype == np.float64 and np.array_equal(z.W, (np.random.randn(hs[0], V) / np.sqrt(V)).astype(np.float32))

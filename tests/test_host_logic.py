@@ -230,3 +230,62 @@ def test_rbm_parameter_init_is_the_reference_stream():
     m = BinaryRBM(n_hidden_units=h)
     m._init_params(v)
     assert np.array_equal(m.W, W) and np.array_equal(m.c, c) and np.array_equal(m.b, b)
+
+
+@pytest.mark.parametrize("scalar", [0, 256])
+def test_host_stage_rows_rounds_like_the_device_cast(scalar):
+    """csrc/host_stage.c: gathered rows in the operand layout ([cast(X[rows[i]]) | 1 | 0...]) with the device's rounding
+    -- bf16 nearest-even, fp16 nearest-even saturating at +-65504 (dbn_common.cuh mat_store) -- checked bit for bit
+    against torch's CPU casts on ties, subnormals, overflow, infinities and random bit patterns, for the vector
+    (AVX2 / F16C) and the portable scalar conversions, on one thread and several."""
+    import torch
+    from dbn_b200 import _hoststage as hs
+    if not hs.available():
+        pytest.skip("libdbn_hostrng.so not built")
+    rng = np.random.default_rng(0)
+    n, cols = 1200, 203
+    X = rng.standard_normal((n, cols)).astype(np.float32)
+    special = np.array([0.0, -0.0, 1.0, 65504.0, 65519.0, 65520.0, 70000.0, -70000.0, 1e38, -1e38, np.inf, -np.inf, 2.0 ** -14,
+                        2.0 ** -24, 2.0 ** -25, 2.0 ** -25 * 1.0001, 2.0 ** -26, 6.1e-5, 5.96e-8, 3e-8, 1 + 2.0 ** -11,
+                        1 + 2.0 ** -10 + 2.0 ** -11, 1 + 2.0 ** -8, 1 + 2.0 ** -7 + 2.0 ** -8, 3.3895313892515355e38], dtype=np.float32)
+    X[0, :len(special)] = special
+    bits = (rng.integers(0, 1 << 32, (40, cols), dtype=np.uint64).astype(np.uint32)).view(np.float32)
+    bits[np.isnan(bits)] = 1.0
+    X[1:41] = bits
+    X[41:81] = bits * np.float32(1e-6)
+    rows = rng.permutation(n)[:1000]
+    ldo = (cols + 1 + 63) // 64 * 64
+    for kind, dt, it in ((hs.BF16, torch.bfloat16, torch.int16), (hs.F16, torch.float16, torch.int16), (hs.F32, torch.float32, torch.int32)):
+        src = torch.from_numpy(X[rows])
+        ref = (src.clamp(-65504.0, 65504.0) if dt == torch.float16 else src).to(dt)
+        for threads in (1, 5):
+            out = torch.full((len(rows), ldo), 7, dtype=dt)
+            hs.stage_rows(X, rows, out.data_ptr(), ldo, kind | scalar, True, threads=threads)
+            assert torch.equal(out[:, :cols].contiguous().view(it), ref.contiguous().view(it)), (kind, threads)
+            assert bool((out[:, cols] == 1).all()) and bool((out[:, cols + 1:] == 0).all())
+        plain = torch.full((n, cols), 7, dtype=dt)      # no gather, no ones column, no padding
+        hs.stage_rows(X, None, plain.data_ptr(), cols, kind | scalar, False)
+        full = torch.from_numpy(X)
+        assert torch.equal(plain.view(it), (full.clamp(-65504.0, 65504.0) if dt == torch.float16 else full).to(dt).view(it))
+
+
+def test_legacy_randn_f32_is_the_narrowed_scaled_draw():
+    """csrc/host_rng.c dbn_host_legacy_randn_f32: `(np.random.randn(h, v) / sqrt(v)).astype(float32)` (the initial
+    weights, dbn/models.py:55-57, as the device stores them) without the float64 array -- values and generator state bit
+    for bit, on the threaded path (>= 2^19 draws) and the sequential one, with and without a cached Gaussian."""
+    from dbn_b200 import _hostrng as hr
+    if not hr.available():
+        pytest.skip("libdbn_hostrng.so not built")
+    for shape, pre in (((700, 801), 0), ((1031, 517), 3), ((50, 100), 1), ((3,), 0)):
+        s = np.sqrt(shape[-1])
+        np.random.seed(77)
+        np.random.randn(pre)                      # odd `pre` leaves a cached Gaussian behind
+        ref = (np.random.randn(*shape) / s).astype(np.float32)
+        tail_ref = np.random.randn(5)
+        np.random.seed(77)
+        np.random.randn(pre)
+        out = np.full(shape, 7, dtype=np.float32)
+        hr.legacy_randn_f32(out, s)
+        tail_got = np.random.randn(5)
+        assert np.array_equal(out.view(np.uint32), ref.view(np.uint32)), shape
+        assert np.array_equal(tail_ref, tail_got), shape
