@@ -398,6 +398,17 @@ class DeviceRbm:
             self.Wb = torch.zeros(self.H, bf16_pitch(self.V), dtype=OP_DTYPE[self.prec], device=device)
         return self
 
+    def clone_as(self, precision):
+        """Independent copy of this layer on the device, in `precision` (fp32 masters copied device to device, the 16-bit
+        shadow rounded afresh): how a pre-trained layer enters the fine-tune without a round trip through the host."""
+        act = next(k for k, v in ACT_IDS.items() if v == self.act)
+        o = DeviceRbm.blank(self.H, self.V, act, precision, self.device)
+        o.W.copy_(self.W)
+        o.b.copy_(self.b)
+        o.c.copy_(self.c)
+        o.refresh_shadow()
+        return o
+
     def move_shadow(self, Wb):
         """Keep the bf16 shadow in caller-provided memory (a peer-visible arena) from now on."""
         assert self.prec in TC_PRECS and tuple(Wb.shape) == (self.H, bf16_pitch(self.V)) and Wb.dtype == OP_DTYPE[self.prec]

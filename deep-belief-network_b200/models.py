@@ -184,7 +184,7 @@ class BinaryRBM(BaseEstimator, TransformerMixin, BaseModel):
         array of the layer's size, no divide pass, no narrowing pass on the critical path of the fit."""
         h, s = self.n_hidden_units, np.sqrt(n_visible)
         if self.activation_function == 'sigmoid':   # legacy_randn == np.random.randn, bit for bit (see _hostrng.py)
-            W = E.pooled_f32((h, n_visible)) if (for_upload and h * n_visible >= (1 << 20)) else None
+            W = E.pooled_f32((h, n_visible)) if (for_upload and h * n_visible >= (1 << 17)) else None
             if W is not None:
                 legacy_randn_f32(W, s)
             else:
@@ -261,7 +261,7 @@ class BinaryRBM(BaseEstimator, TransformerMixin, BaseModel):
     def _draw_jobs(self, n, n_features):
         """The np.random draws of one fit, in sequential order (generator for _DrawAhead): parameters, Philox key,
         one double shuffle per epoch."""
-        yield self._draw_params(n_features, for_upload=(n > 0 and self.n_epochs > 0))
+        yield self._draw_params(n_features, for_upload=True)   # read back from the device even when nothing trains
         yield _draw_seed()
         for _ in range(self.n_epochs if n > 0 else 0):
             yield E.epoch_order(n)
@@ -440,7 +440,7 @@ class UnsupervisedDBN(BaseEstimator, TransformerMixin, BaseModel):
         """The np.random draws of one greedy pre-training run, in sequential order (generator for _DrawAhead)."""
         v = n_features
         for rbm in self.rbm_layers:
-            yield rbm._draw_params(v, for_upload=(n > 0 and rbm.n_epochs > 0))
+            yield rbm._draw_params(v, for_upload=True)
             yield _draw_seed()
             for _ in range(rbm.n_epochs if n > 0 else 0):
                 yield E.epoch_order(n)
@@ -568,8 +568,14 @@ class AbstractSupervisedDBN(BaseEstimator, BaseModel):
 
     def _device_mlp(self, precision):
         dev = _device()
-        layers = [E.DeviceRbm(r.W, r.b, r.c, r.activation_function, precision, dev)
-                  for r in self.unsupervised_dbn.rbm_layers]
+        layers = []
+        for r in self.unsupervised_dbn.rbm_layers:
+            # a layer that was just pre-trained is still on the device (BinaryRBM._adopt): copy it there instead of
+            # narrowing and uploading its float64 host arrays again
+            hit = next((l for (sig, l) in r.__dict__.get("_dev_cache", {}).values()
+                        if sig == _signature(r.W, r.b, r.c)), None)
+            layers.append(hit.clone_as(precision) if hit is not None else
+                          E.DeviceRbm(r.W, r.b, r.c, r.activation_function, precision, dev))
         return E.DeviceMlp(layers, self.W, self.b, self.unsupervised_dbn.activation_function, self._head,
                            precision, dev)
 
