@@ -370,5 +370,9 @@ def run_epoch_lockstep(runners, order):
 
 
 def peer_path_wanted(layer, world):
-    return (layer.prec in E.TC_PRECS and layer.H % world == 0 and world <= L.MAX_PEERS and
+    return peer_path_wanted_for(layer.prec, layer.H, world)
+
+
+def peer_path_wanted_for(prec, H, world):
+    return (E.PREC_IDS.get(prec, prec) in E.TC_PRECS and H % world == 0 and world <= L.MAX_PEERS and
             os.environ.get("DBN_B200_DP_P2P", "1") != "0")

@@ -542,7 +542,24 @@ class DeviceRbm:
             torch.cuda.current_stream().synchronize()
 
 
-def fit_rbm_data_parallel(layer, X_host, n_epochs, batch_size, k, lr, seed, dp, next_order, verbose=None):
+def dp_begin_upload(X_host, precision, H, dp, device, quiet=True):
+    """Start the upload of this rank's share of the dataset BEFORE the initial parameters exist: rank 0 spends ~20 ms
+    drawing a 4096 x 4096 layer and the other ranks wait for its broadcast -- the rows cross PCIe meanwhile.  Returns
+    the device tensor fit_rbm_data_parallel takes as `Xl` (the rank's 1/world of the rows when the peer-memory path is
+    the one that will run), or None."""
+    from . import dp_peer
+    rank, world = dp
+    n, V = int(X_host.shape[0]), int(X_host.shape[1])
+    if n == 0 or n % world or not dp_peer.peer_path_wanted_for(precision, H, world):
+        return None
+    nl = n // world
+    mine = X_host[rank * nl:(rank + 1) * nl]
+    if quiet and not is_pinned_f32(mine) and operand_upload_wanted(precision, nl, V):
+        return upload_operand(mine, device, precision)     # rounded on the host: half the PCIe bytes
+    return upload_f32(mine, device)
+
+
+def fit_rbm_data_parallel(layer, X_host, n_epochs, batch_size, k, lr, seed, dp, next_order, verbose=None, Xl=None):
     """Data-parallel BinaryRBM._stochastic_gradient_descent (dbn/models.py:96-122) of one layer whose parameters are
     already identical on every rank.  X_host: the whole dataset on the host (float32 [n, V], the same on every rank);
     next_order(): on rank 0 returns the next epoch's row order (the reference's double shuffle), ignored elsewhere --
@@ -569,11 +586,8 @@ def fit_rbm_data_parallel(layer, X_host, n_epochs, batch_size, k, lr, seed, dp, 
             reason = str(e)
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)   # all ranks take the same path
         if int(ok.item()) == 1:
-            mine = X_host[rank * nl:(rank + 1) * nl]
-            if verbose is None and not is_pinned_f32(mine) and operand_upload_wanted(layer.prec, nl, V):
-                Xl = upload_operand(mine, dev, layer.prec)     # rounded on the host: half the PCIe bytes
-            else:
-                Xl = upload_f32(mine, dev)
+            if Xl is None or int(Xl.shape[0]) != nl:
+                Xl = dp_begin_upload(X_host, layer.prec, layer.H, dp, dev, quiet=verbose is None)
             runner = dp_peer.DpPeerRunner(layer, Xl, n, batch_size, k, lr, seed, group.member)
         else:
             if group is not None:

@@ -289,6 +289,8 @@ class BinaryRBM(BaseEstimator, TransformerMixin, BaseModel):
         precision = self._resolved_precision()
         draws = None
         seed_t = torch.zeros(1, dtype=torch.int64, device=dev)
+        # this rank's rows start crossing PCIe now, under rank 0's parameter draws and the broadcast everyone waits for
+        Xl = E.dp_begin_upload(X, precision, self.n_hidden_units, dp, dev, quiet=not self.verbose)
         try:
             if rank == 0:
                 draws = _DrawAhead(self._draw_jobs(n, v))      # drawn while the rows upload
@@ -310,7 +312,8 @@ class BinaryRBM(BaseEstimator, TransformerMixin, BaseModel):
             elif self.verbose:
                 cb = lambda it, err: None
             E.fit_rbm_data_parallel(layer, X, self.n_epochs, self.batch_size, self.contrastive_divergence_iter,
-                                    self.learning_rate, seed, dp, (draws.get if draws is not None else None), verbose=cb)
+                                    self.learning_rate, seed, dp, (draws.get if draws is not None else None), verbose=cb,
+                                    Xl=Xl)
         finally:
             if draws is not None:
                 draws.close()
