@@ -136,6 +136,7 @@ struct MlpWorkspace {
   dbn_mat dOb;                        // bf16 copy of the head delta (BF16 mode: operand of the head-gradient contraction)
   TeCtl* ctl;                         // tensor-core modes: control block + split-K scratch of the persistent fine-tune kernel
   float* scratch;
+  dbn_mat a0b;                        // tensor-core modes: second masked-input buffer (the persistent kernel masks one step ahead)
 };
 size_t mlp_ws_layout(int precision, int Bmax, int n_in, const int32_t* dims, int L, int n_out, char* base,
                      MlpWorkspace* ws) {
@@ -165,6 +166,9 @@ size_t mlp_ws_layout(int precision, int Bmax, int n_in, const int32_t* dims, int
       w.scratch = reinterpret_cast<float*>(base ? base + off : nullptr);
       off = align_up(off + pl.scratch_bytes, 1024);
     }
+    w.a0b = carve(n_in, dt, true);
+  } else {
+    w.a0b = null_mat();
   }
   if (ws) *ws = w;
   return off;
@@ -754,6 +758,7 @@ int dbn_mlp_workspace_init(void* stream, int precision, int Bmax, int n_in, cons
   DBN_CUDA_OK(cudaMemsetAsync(workspace, 0, bytes, as_stream(stream)));
   if (is_tc(precision)) {
     DBN_TRY(dbn_fill_ones_column(stream, &ws.a0, Bmax, n_in));
+    DBN_TRY(dbn_fill_ones_column(stream, &ws.a0b, Bmax, n_in));
     for (int l = 0; l < n_layers; ++l) DBN_TRY(dbn_fill_ones_column(stream, &ws.act[l], Bmax, dims[l]));
   }
   return DBN_OK;
@@ -889,15 +894,15 @@ int dbn_mlp_train_step(void* stream, const dbn_mlp_step_args* a) {
 }
 
 // Whole iteration (every mini-batch of one pass) in ONE cooperative launch of mlp_tc_epoch_kernel when the network fits its
-// phase plan (tensor-core modes, <= 4 hidden layers, head <= 16 wide, mini-batches of 16..256 rows, no dropout, no optional
-// outputs); *done = 0: not applicable, the caller runs the tiled path.
+// phase plan (tensor-core modes, <= 4 hidden layers, head <= 16 wide, mini-batches of 16..256 rows, no optional outputs;
+// dropout by Philox or injected masks included); *done = 0: not applicable, the caller runs the tiled path.
 static int mlp_fit_epoch_tc(cudaStream_t st, const dbn_mlp_step_args* t, int n_rows, int batch_size, int* done) {
   *done = 0;
   const int L = t->n_layers;
   const int B = t->ws_rows > 0 ? t->ws_rows : std::min(batch_size, n_rows);
   if (mt_enabled_flag() != 1 || !is_tc(t->precision) || n_rows <= 0 || L < 1 || L > MT_MAX_LAYERS) return DBN_OK;
   if (B < std::min(batch_size, n_rows) || (n_rows > B && B != batch_size)) return DBN_OK;
-  if (t->keep_p < 1.0f || t->out.ptr || t->raw_grads[0].ptr) return DBN_OK;
+  if (t->out.ptr || t->raw_grads[0].ptr) return DBN_OK;
   if (t->act != DBN_ACT_SIGMOID && t->act != DBN_ACT_RELU) return DBN_OK;
   if (t->head != DBN_HEAD_SOFTMAX && t->head != DBN_HEAD_LINEAR) return DBN_OK;
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
@@ -944,6 +949,19 @@ static int mlp_fit_epoch_tc(cudaStream_t st, const dbn_mlp_step_args* t, int n_r
     if (l >= 1) {   // delta_l and W_l feed the contraction that produces delta_{l-1}
       DBN_TRY(make_operand_map(&a.tm_d3[l], ws.delta[l], B, ceil_div(t->dims[l], 64), pl.b_rb[l - 1], pl.b_kc[l - 1]));
       DBN_TRY(te_make_map2(&a.tm_w2[l], t->Wb[l], t->Wb[l].ld, t->dims[l], std::min(pl.b_kc[l - 1] * 64, 256)));
+    }
+  }
+  if (t->keep_p < 1.0f) {   // dropout: layer 0 reads the masked copy of its mini-batch (double-buffered, written one phase ahead)
+    a.drop = 1;
+    a.keep_p = t->keep_p;
+    a.rng = t->rng;
+    for (int j = 0; j <= L; ++j) a.masks[j] = t->masks[j];
+    a.a0[0] = ws.a0;
+    a.a0[1] = ws.a0b;
+    const int ks0 = ceil_div(t->n_in, 64);
+    for (int i = 0; i < 2; ++i) {
+      DBN_TRY(make_operand_map(&a.tm_a0_3[i], a.a0[i], B, ks0, pl.f_rb[0], ks0));
+      DBN_TRY(te_make_map2(&a.tm_a0_2[i], a.a0[i], a.a0[i].ld, B, 256));
     }
   }
   DBN_TRY(te_make_map2(&a.tm_in2[L], ws.act[L - 1], ws.act[L - 1].ld, B, 256));

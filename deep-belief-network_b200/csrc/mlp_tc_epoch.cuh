@@ -70,6 +70,15 @@ struct MtArgs {
   TeCtl* ctl;
   float* scratch;
   long long* trace;
+  // dropout (dbn/models.py:401-411), drop != 0: the input of step s is masked into a0[s & 1] one phase ahead (every CTA a
+  // share of the rows), the hidden activations in the forward epilogue; masks[j].ptr != null: injected masks (rows of
+  // the iteration, != 0 keeps), else Philox keyed like the tiled path (stream + j, global row, column)
+  int drop;
+  float keep_p;
+  dbn_rng rng;
+  dbn_mat masks[MT_MAX_LAYERS + 1];
+  dbn_mat a0[2];
+  CUtensorMap tm_a0_3[2], tm_a0_2[2];     // a0[i] as FWD A / UPD B of layer 0
 };
 
 // debug trace (dbn_debug_set_trace): [cta][step < 8][phase < 13][8] clock64 stamps: 0 operands of the first tile landed (issuer 0),
@@ -125,7 +134,8 @@ __device__ __forceinline__ void mt_issue_loads(const MtArgs& a, int s, int p, ui
     mbar_expect_tx(bar, g.a_bytes + g.b_bytes);
     if (g.kind == MT_FWD) {
       const int rbk = bid / g.nt_cols, cb = bid % g.nt_cols;
-      tma_load_3d(sbase + g.off_a, &a.tm_in3[l], bar, 0, (l == 0 ? a.row0 + s * a.B : 0) + rbk * g.rb, 0);
+      if (l == 0 && a.drop) tma_load_3d(sbase + g.off_a, &a.tm_a0_3[s & 1], bar, 0, rbk * g.rb, 0);
+      else tma_load_3d(sbase + g.off_a, &a.tm_in3[l], bar, 0, (l == 0 ? a.row0 + s * a.B : 0) + rbk * g.rb, 0);
       tma_load_3d(sbase + g.off_b, &a.tm_w3[l], bar, 0, cb * g.width, 0);
     } else if (g.kind == MT_BWD) {
       const int kc = bid % g.ksplit, cb = (bid / g.ksplit) % g.nt_cols, rbk = bid / (g.ksplit * g.nt_cols);
@@ -136,10 +146,35 @@ __device__ __forceinline__ void mt_issue_loads(const MtArgs& a, int s, int p, ui
     } else {
       const int mb = bid / g.nt_cols, nb = bid % g.nt_cols;
       tma_load_2d(sbase + g.off_a, &a.tm_d2[l], bar, mb * 64, 0);
+      const bool masked = l == 0 && a.drop;
       for (int ch = 0; ch < g.n_chunks; ++ch)
-        tma_load_2d(sbase + g.off_b + (uint32_t)(ch * TE_BOX_BYTES), &a.tm_in2[l], bar, nb * g.width + ch * 64,
-                    l == 0 ? a.row0 + s * a.B : 0);
+        tma_load_2d(sbase + g.off_b + (uint32_t)(ch * TE_BOX_BYTES), masked ? &a.tm_a0_2[s & 1] : &a.tm_in2[l], bar,
+                    nb * g.width + ch * 64, (l == 0 && !masked) ? a.row0 + s * a.B : 0);
     }
+  }
+}
+
+// input_data *= Binomial(1, p) (dbn/models.py:401-403) for mini-batch s, into a0[s & 1]: every CTA's epilogue threads take
+// a share of the quads; rows past the end of the dataset are zero (they are operands of the dW contraction)
+__device__ __forceinline__ void mt_mask_input(const MtArgs& a, int s, int tid_e, uint32_t epoch) {
+  const int valid = min(a.B, a.n_rows - s * a.B);
+  const int quads = (a.n_in + 3) >> 2;
+  dbn_rng r = a.rng;
+  r.row0 += (uint32_t)(s * a.B);
+  const dbn_mat& dst = a.a0[s & 1];
+  const bool inj = a.masks[0].ptr != nullptr;
+  for (int q = (int)blockIdx.x * TE_EPI_THREADS + tid_e; q < a.B * quads; q += (int)gridDim.x * TE_EPI_THREADS) {
+    const int row = q / quads, c = (q - row * quads) << 2, nv = min(4, a.n_in - c);
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (row < valid) {
+      float u[4] = {0.f, 0.f, 0.f, 0.f};
+      mat_load4(a.X, a.row0 + s * a.B + row, c, v, nv);
+      if (inj) mat_load4(a.masks[0], s * a.B + row, c, u, nv);
+      else rng_uniform4(r, epoch, row, c, u);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = (inj ? (u[j] != 0.0f) : (u[j] < a.keep_p)) ? v[j] : 0.0f;
+    }
+    mat_store4(dst, row, c, v, nv);
   }
 }
 
@@ -292,6 +327,12 @@ __global__ void __launch_bounds__(TE_THREADS, 1) mlp_tc_epoch_kernel(const __gri
       asm volatile("prefetch.tensormap [%0];" ::"l"(&a.tm_d2[l]) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&a.tm_in2[l]) : "memory");
     }
+    if (a.drop) {
+      for (int i = 0; i < 2; ++i) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&a.tm_a0_3[i]) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&a.tm_a0_2[i]) : "memory");
+      }
+    }
     mbar_init(bar(MT_B_LD0), 1);
     mbar_init(bar(MT_B_LD1), 1);
     mbar_init(bar(MT_B_ACC), TE_NISS);
@@ -395,6 +436,17 @@ __global__ void __launch_bounds__(TE_THREADS, 1) mlp_tc_epoch_kernel(const __gri
     const int coff = (lane >> 4) * 4;
     const uint32_t tq = tmem_base + ((uint32_t)(q * 32) << 16);
     unsigned n_acc = 0, n_bar = 0, n_ld0 = 0;
+    const uint32_t epoch = a.rng.epoch + (a.rng.epoch_ptr ? *a.rng.epoch_ptr : 0u);
+    if (a.drop) {       // the first mini-batch's masked input must exist before anybody's first tile is requested
+      mt_mask_input(a, 0, tid_e, epoch);
+      asm volatile("bar.sync 1, %0;" ::"n"(TE_EPI_THREADS) : "memory");
+      if (tid_e == 0) {
+        te_grid_arrive(a.ctl, 0);
+        ++n_bar;
+        te_grid_wait(a.ctl, n_bar * gridDim.x);
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(TE_EPI_THREADS) : "memory");
+    }
     if (tid_e == 0) mt_issue_loads(a, 0, 0, sbase, bar_base);
     for (int s = 0; s < steps; ++s) {
       const int valid = min(a.B, a.n_rows - s * a.B);
@@ -549,6 +601,20 @@ __global__ void __launch_bounds__(TE_THREADS, 1) mlp_tc_epoch_kernel(const __gri
                     if (fwd) x[j] = row_ok ? apply_act<true>(a.act, acc[j] + pre[i][j]) : 0.0f;
                     else x[j] = row_ok ? acc[j] * mt_prime(a.act, pre[i][j]) : 0.0f;
                   }
+                  if (fwd && a.drop && row_ok && n0 < N) {      // input_data *= Binomial(1, p): dbn/models.py:408-411
+                    float u[4] = {1.f, 1.f, 1.f, 1.f};
+                    const bool inj = a.masks[l + 1].ptr != nullptr;
+                    if (inj) {
+                      mat_load4(a.masks[l + 1], s * a.B + grow, n0, u, min(4, N - n0));
+                    } else {
+                      dbn_rng r = a.rng;
+                      r.stream += (uint32_t)(l + 1);
+                      r.row0 += (uint32_t)(s * a.B);
+                      rng_uniform4(r, epoch, grow, n0, u);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) x[j] = (inj ? (u[j] != 0.0f) : (u[j] < a.keep_p)) ? x[j] : 0.0f;
+                  }
                   if (lane_ok && n0 < N) te_store4_h(fwd ? a.a[l] : a.d[l], grow, n0, N, x);
                 }
               }
@@ -560,6 +626,7 @@ __global__ void __launch_bounds__(TE_THREADS, 1) mlp_tc_epoch_kernel(const __gri
         }
         if (tid_e == 0) mt_trace(a, s, p, 2);
         if (s + 1 == steps && p == np - 1) break;
+        if (a.drop && p == np - 1) mt_mask_input(a, s + 1, tid_e, epoch);   // next mini-batch's input, into the other buffer
         asm volatile("bar.sync 1, %0;" ::"n"(TE_EPI_THREADS) : "memory");
         if (tid_e == 0) {
           mt_trace(a, s, p, 3);

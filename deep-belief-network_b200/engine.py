@@ -1203,10 +1203,10 @@ class MlpIterRunner:
         self.graph = None
         self.launches_per_iter = 0
         self.iters_run = 0
-        # tensor-core modes without dropout: dbn_mlp_fit_epoch is ONE cooperative launch of the persistent fine-tune
-        # kernel (csrc/mlp_tc_epoch.cuh) -- nothing to capture
+        # tensor-core modes: dbn_mlp_fit_epoch is ONE cooperative launch of the persistent fine-tune kernel
+        # (csrc/mlp_tc_epoch.cuh; dropout by Philox or injected masks included) -- nothing to capture
         dims = (C.c_int32 * len(mlp.dims))(*mlp.dims)
-        self.tc_epoch = (mlp.prec in TC_PRECS and dropout_p == 0 and
+        self.tc_epoch = (mlp.prec in TC_PRECS and
                          lib.dbn_mlp_tc_epoch_plan(mlp.prec, mlp.n_in, dims, len(mlp.dims), mlp.n_out, min(self.bs, n)) > 0)
 
     def _enqueue(self):

@@ -444,7 +444,8 @@ int dbn_mlp_fit_epoch(void* stream, const dbn_mlp_step_args* tmpl, int n_rows, i
 /* Tensor-core modes: dbn_mlp_fit_epoch runs the whole iteration as ONE cooperative launch of the persistent fine-tune
  * kernel (csrc/mlp_tc_epoch.cuh: a phase program F_0..F_{L-1} | HEAD | B_l + U_{l+2} .. | U_1 + U_0 per mini-batch, grid
  * barriers between phases) when the network fits its plan -- <= 4 hidden layers, head <= 16 wide, mini-batches of 16..256
- * rows, no dropout, no optional outputs, stream not being captured -- and as the loop of dbn_mlp_train_step otherwise.
+ * rows, no optional outputs, stream not being captured (dropout by Philox or injected masks is handled inside the kernel)
+ * -- and as the loop of dbn_mlp_train_step otherwise.
  * Replaces the mini-batch loop of dbn/models.py:439-465.  Returns the number of CTAs of the plan, 0 when it does not fit
  * (or DBN_B200_TC_FINETUNE=0): callers then capture the iteration in a CUDA graph as before. */
 int dbn_mlp_tc_epoch_plan(int precision, int n_in, const int32_t* dims, int n_layers, int n_out, int batch_size);

@@ -223,8 +223,10 @@ def tc_epoch_plan(V, H, B):
     return {names[i]: int(out[i]) for i in range(min(m, 16))}
 
 
-def run_mlp_epoch(layers, Wo, bo, X, Y, act, head, precision, batch_size, lr=0.1, l2=1.0, tc=True, iters=1):
-    """`iters` passes of dbn_mlp_fit_epoch over the rows of X in their stored order (no shuffle, no dropout), either as
+def run_mlp_epoch(layers, Wo, bo, X, Y, act, head, precision, batch_size, lr=0.1, l2=1.0, tc=True, iters=1, keep_p=1.0,
+                  masks=None, seed=0):
+    """`iters` passes of dbn_mlp_fit_epoch over the rows of X in their stored order (no shuffle; dropout when keep_p < 1:
+    Philox keyed by `seed`, or the injected `masks` = [n x n_in, n x h_1, ...] of zeros / ones), either as
     ONE persistent launch per pass (tc=True, csrc/mlp_tc_epoch.cuh) or as the tiled launches per mini-batch.  Returns
     the trained parameters, the per-row losses of the last pass and the number of kernels the library launched."""
     import torch
@@ -237,12 +239,15 @@ def run_mlp_epoch(layers, Wo, bo, X, Y, act, head, precision, batch_size, lr=0.1
     Yd = _t(Y, torch.float32)
     ws = mlp.make_workspace(min(batch_size, n))
     loss = torch.zeros(n, device="cuda")
-    a = mlp.step_args(Xop, Yd, lr / batch_size, 1.0 - lr * l2 / n, 1.0, ws, 0, None, loss, None)
+    iter_ctr = torch.zeros(1, dtype=torch.int32, device="cuda")
+    masks_d = [_t(m, torch.float32) for m in masks] if masks is not None else None   # injected dropout masks, rows of X
+    a = mlp.step_args(Xop, Yd, lr / batch_size, 1.0 - lr * l2 / n, keep_p, ws, seed, iter_ctr, loss, masks_d)
     prev = l.dbn_set_tc_finetune(1 if tc else 0)
     try:
         before = l.dbn_launch_count()
         for _ in range(iters):
             L.check(l.dbn_mlp_fit_epoch(E.stream_ptr(), C.byref(a), n, batch_size))
+            iter_ctr.add_(1)
         torch.cuda.synchronize()
         launches = int(l.dbn_launch_count() - before)
     finally:

@@ -17,7 +17,7 @@ def _net(rng, n_in, hs, n_out):
     return layers, rng.standard_normal((n_out, prev)) / np.sqrt(prev), rng.standard_normal(n_out) * 0.1
 
 
-def _oracle_epoch(layers, Wo, bo, X, Y, act, head, lr, l2, bs, precision):
+def _oracle_epoch(layers, Wo, bo, X, Y, act, head, lr, l2, bs, precision, masks=None):
     """dbn/models.py:439-465 in float64.  The device contracts the 16-bit shadows of the hidden weights, so the oracle
     takes its gradients at the weights rounded the same way and applies them to the un-rounded masters.  Also returns
     the yardsticks of tests/test_gpu_parity.py::test_finetune_step_against_oracle summed over the mini-batches: the size
@@ -30,7 +30,8 @@ def _oracle_epoch(layers, Wo, bo, X, Y, act, head, lr, l2, bs, precision):
     scale_w, scale_b = np.zeros(nl), np.zeros(nl)
     for s in range(0, n, bs):
         q = [(shadow_round(W, precision), c) for (W, c) in lay]
-        gW, gb, out, acts, deltas = orc.finetune_grads(q, Wo, bo, X[s:s + bs], Y[s:s + bs], None, act, head)
+        mk = [m[s:s + bs] for m in masks] if masks is not None else None
+        gW, gb, out, acts, deltas = orc.finetune_grads(q, Wo, bo, X[s:s + bs], Y[s:s + bs], mk, act, head)
         losses[s:s + bs] = orc.sample_loss(out, Y[s:s + bs], head).sum(axis=1) / (Y.shape[1] if head == "softmax" else 1)
         decay = 1.0 - lr * l2 / n
         for l in range(nl):
@@ -119,3 +120,59 @@ def test_full_size_iteration_is_reproducible_and_equals_the_tiled_path():
         assert relF(r1["layers"][l][0] - layers[l][0], r0["layers"][l][0] - layers[l][0]) < 5e-2
     assert np.array_equal(r1["Wo"], r2["Wo"]) and np.array_equal(r1["loss"], r2["loss"])
     assert relF(r1["Wo"] - Wo, r0["Wo"] - Wo) < 5e-2 and np.max(np.abs(r1["loss"] - r0["loss"])) < 0.1
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp16"])
+@pytest.mark.parametrize("n_in,hs,n_out,bs,n,act,head", [CASES[0], CASES[1], CASES[3]])
+def test_dropout_iteration_against_oracle(precision, n_in, hs, n_out, bs, n, act, head):
+    """Dropout inside the persistent kernel (dbn/models.py:401-411: the input and every hidden activation are multiplied
+    by Binomial(1, p) masks, no rescale; the derivative sees the masked activation).  With INJECTED masks -- the form the
+    numpy-replay mode uses -- the iteration is checked against the float64 oracle on the same masks: the masked input is
+    produced one phase ahead into a double buffer by all CTAs, the hidden masks are applied in the forward epilogue."""
+    rng = np.random.default_rng(n_in + 7 * len(hs))
+    layers, Wo, bo = _net(rng, n_in, hs, n_out)
+    X = rng.integers(0, 17, (n, n_in)) / 16.0
+    Y = np.eye(n_out)[rng.integers(0, n_out, n)] if head == "softmax" else rng.standard_normal((n, n_out))
+    masks = [(rng.random((n, w)) < 0.8).astype(np.float64) for w in [n_in] + hs]
+    lr, l2 = 0.1, 1.0
+    lay, Wo2, bo2, losses, scale_w, scale_b = _oracle_epoch(layers, Wo, bo, X, Y, act, head, lr, l2, bs, precision, masks)
+    res = run_mlp_epoch(layers, Wo, bo, X, Y, act, head, precision, bs, lr=lr, l2=l2, tc=True, keep_p=0.8, masks=masks)
+    assert res["launches"] <= 2, "the iteration must be one persistent launch"
+    depth = len(hs) + 1
+    gate = 4.0 if act == "relu" else 1.0
+    tol = 2e-3 * depth * gate
+    for l in range(len(hs)):
+        assert np.linalg.norm(res["layers"][l][0] - lay[l][0]) < tol * scale_w[l] + 2e-6 * np.linalg.norm(lay[l][0]), "layer %d weights" % l
+        assert np.linalg.norm(res["layers"][l][1] - lay[l][1]) < tol * scale_b[l] + 1e-6, "layer %d bias" % l
+    assert np.linalg.norm(res["Wo"] - Wo2) < tol * scale_w[-1] + 1e-6 and np.linalg.norm(res["bo"] - bo2) < tol * scale_b[-1] + 1e-6
+    assert np.max(np.abs(res["loss"] - losses)) < tol * 10 * max(1.0, np.max(np.abs(losses)))
+    # and the masks matter: without them the result is somewhere else
+    plain = run_mlp_epoch(layers, Wo, bo, X, Y, act, head, precision, bs, lr=lr, l2=l2, tc=True)
+    assert np.linalg.norm(plain["Wo"] - res["Wo"]) > 10 * tol * scale_w[-1] * 0.01
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp16"])
+@pytest.mark.parametrize("n_in,hs,n_out,bs,n,act,head", CASES[:2])
+def test_philox_dropout_matches_the_tiled_path(precision, n_in, hs, n_out, bs, n, act, head):
+    """Philox dropout: the persistent kernel draws the SAME masks as the tiled path (stream = layer, counter = global row
+    and column, epoch = iteration), so two iterations agree with the tiled launches to rounding, short last batch
+    included, and a different seed gives a different model."""
+    rng = np.random.default_rng(11)
+    layers, Wo, bo = _net(rng, n_in, hs, n_out)
+    X = rng.integers(0, 17, (n, n_in)) / 16.0
+    Y = np.eye(n_out)[rng.integers(0, n_out, n)]
+    kw = dict(lr=0.05, iters=2, keep_p=0.75, seed=0x1234567890ABCDEF)
+    r1 = run_mlp_epoch(layers, Wo, bo, X, Y, act, head, precision, bs, tc=True, **kw)
+    r0 = run_mlp_epoch(layers, Wo, bo, X, Y, act, head, precision, bs, tc=False, **kw)
+    assert r1["launches"] <= 4 and r0["launches"] > 8
+    gate = 4.0 if act == "relu" else 1.0
+    for l in range(len(hs)):
+        assert relF(r1["layers"][l][0] - layers[l][0], r0["layers"][l][0] - layers[l][0]) < 2e-3 * gate
+        assert relF(r1["layers"][l][1] - layers[l][1], r0["layers"][l][1] - layers[l][1]) < 2e-3 * gate
+    assert relF(r1["Wo"] - Wo, r0["Wo"] - Wo) < 2e-3 * gate
+    assert np.max(np.abs(r1["loss"] - r0["loss"])) < 2e-2
+    r2 = run_mlp_epoch(layers, Wo, bo, X, Y, act, head, precision, bs, tc=True, **kw)
+    assert all(np.array_equal(r1["layers"][l][0], r2["layers"][l][0]) for l in range(len(hs))), "deterministic"
+    kw["seed"] = 99
+    r3 = run_mlp_epoch(layers, Wo, bo, X, Y, act, head, precision, bs, tc=True, **kw)
+    assert relF(r3["Wo"] - Wo, r1["Wo"] - Wo) > 1e-2
