@@ -399,7 +399,8 @@ def time_alone(fn, reps, graph_batch=0):
 
 def e2e_measure(c, e2e_step, rows, steps, h2d, d2h, api):
     import torch
-    e2e_step()  # warm-up (module load, allocator)
+    for _ in range(2):
+        e2e_step()  # warm-up (module load, allocator, pinned staging pool: the second fit still grows the pools)
     barrier(c)
     t0 = time.perf_counter()
     for _ in range(steps):
@@ -516,7 +517,7 @@ def bench_c2(c, steps, warmup, with_e2e=True):
             m.fit(Xh.numpy())
             return m
         d2h = sum((v * h + v + h) * 4 for v, h in zip(C2_DIMS[:-1], C2_DIMS[1:]))
-        rec["e2e"] = e2e_measure(c, e2e_step, C2_ROWS, 5, Xh.numel() * 4, d2h,
+        rec["e2e"] = e2e_measure(c, e2e_step, C2_ROWS, 10, Xh.numel() * 4, d2h,
                                  "UnsupervisedDBN.fit(X_host), one epoch per layer per call; H2D of X and D2H of W,b,c per call")
     return rec
 
@@ -602,7 +603,7 @@ def bench_c3(c, steps, warmup, with_e2e=True):
             m.fit(Xh.numpy(), y)
             return m
         d2h = sum((v * h + h) * 4 for v, h in zip(C2_DIMS[:-1], C2_DIMS[1:])) + 2000 * 10 * 4
-        rec["e2e"] = e2e_measure(c, e2e_step, C2_ROWS, 5, Xh.numel() * 4 + C2_ROWS * 8, d2h,
+        rec["e2e"] = e2e_measure(c, e2e_step, C2_ROWS, 10, Xh.numel() * 4 + C2_ROWS * 8, d2h,
                                  "SupervisedDBNClassification.fit(X_host, y) with n_epochs_rbm=0, one back-prop iteration per call")
     return rec
 
@@ -720,7 +721,7 @@ def bench_c5(c, steps, warmup, with_e2e=True):
             m.fit(Xh.numpy())
             return m
         h2d = Xh.numel() * 4 // world
-        rec["e2e"] = e2e_measure(c, e2e_step, n_rows, 3, h2d, (C5_V * C5_H + C5_V + C5_H) * 4,
+        rec["e2e"] = e2e_measure(c, e2e_step, n_rows, 5, h2d, (C5_V * C5_H + C5_V + C5_H) * 4,
                                  "BinaryRBM.fit(X_host), one epoch of %d rows per call; each rank uploads its 1/%d of X, "
                                  "every rank exports W,b,c" % (n_rows, world))
     return rec

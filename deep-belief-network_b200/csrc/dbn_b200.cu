@@ -10,6 +10,7 @@
 #include "rbm_tc_epoch.cuh"
 #include "mlp_tc_epoch.cuh"
 #include "dp_kernels.cuh"
+#include <memory>
 
 using namespace dbn;
 
@@ -921,7 +922,8 @@ static int mlp_fit_epoch_tc(cudaStream_t st, const dbn_mlp_step_args* t, int n_r
   MlpWorkspace ws;
   mlp_ws_layout(t->precision, B, t->n_in, t->dims, L, t->n_out, static_cast<char*>(t->workspace), &ws);
   if (pl.scratch_bytes > 0 && ws.scratch == nullptr) return DBN_OK;
-  static MtArgs a;   // (5 KB: built in place; the launch copies it)
+  std::unique_ptr<MtArgs> args(new MtArgs);   // (7 KB; the launch copies it.  Not a static: two host threads may fit two models)
+  MtArgs& a = *args;
   memset(&a, 0, sizeof(a));
   memcpy(a.ph, pl.ph, sizeof(a.ph));
   a.n_phases = pl.n_phases;
