@@ -15,13 +15,18 @@ import numpy as np
 _LIB = None        # None = not tried, False = unavailable
 _LIB_F32 = None    # dbn_host_legacy_randn_f32 of the same library
 _THREADS = max(1, min(8, (os.cpu_count() or 2) - 1))   # worker threads (the calling thread produces the MT19937 words meanwhile)
+_PAR_MIN = int(os.environ.get("DBN_B200_RANDN_PAR_MIN", 1 << 18))   # draws from which the threads pay for their start-up (tools/randn_probe.py)
+
+
+def _threads_for(n):
+    return _THREADS if n >= _PAR_MIN else 1
 
 
 def _raw(fn, rs_state, n):
     key = np.ascontiguousarray(rs_state[1], dtype=np.uint32).copy()
     pos, has_gauss, gauss = C.c_int(int(rs_state[2])), C.c_int(int(rs_state[3])), C.c_double(float(rs_state[4]))
     out = np.empty(n, dtype=np.float64)
-    rc = fn(key.ctypes.data, C.byref(pos), C.byref(has_gauss), C.byref(gauss), out.ctypes.data, n, _THREADS)
+    rc = fn(key.ctypes.data, C.byref(pos), C.byref(has_gauss), C.byref(gauss), out.ctypes.data, n, _threads_for(n))
     if rc != 0:
         return None, None
     return out, ('MT19937', key, pos.value, has_gauss.value, gauss.value)
@@ -101,7 +106,7 @@ def legacy_randn_f32(out, divisor):
         key = np.ascontiguousarray(st[1], dtype=np.uint32).copy()
         pos, has_gauss, gauss = C.c_int(int(st[2])), C.c_int(int(st[3])), C.c_double(float(st[4]))
         rc = _LIB_F32(key.ctypes.data, C.byref(pos), C.byref(has_gauss), C.byref(gauss), out.ctypes.data, n, float(divisor),
-                      _THREADS)
+                      _threads_for(n))
         if rc == 0:
             np.random.set_state(('MT19937', key, pos.value, has_gauss.value, gauss.value))
             return out

@@ -231,7 +231,7 @@ static void finish_join(finish_batch* fb) {
  * final state are those of the sequential algorithm: same operations per attempt and per pair, same order of outputs. */
 #include <string.h>
 
-#define PAR_MIN_N ((size_t)1 << 19)
+#define PAR_MIN_N ((size_t)1 << 17)   /* the binding passes n_threads = 1 below its own (measured) threshold */
 #define CHUNK_ATT ((size_t)1 << 18)
 #define PAR_MAX_T 16
 
