@@ -418,19 +418,21 @@ class UnsupervisedDBN(BaseEstimator, TransformerMixin, BaseModel):
         ahead = (self.rbm_class is BinaryRBM and self.rng == 'philox' and
                  os.environ.get("DBN_B200_DRAW_AHEAD", "1") != "0")
         if not ahead:
-            for rbm in self.rbm_layers:      # strictly sequential: layer l+1 sees layer l's final features
+            for i, rbm in enumerate(self.rbm_layers):      # strictly sequential: layer l+1 sees layer l's final features
                 layer = rbm._fit_device(data)
-                data = layer.transform(data)  # stays in HBM between layers
+                if i + 1 < len(self.rbm_layers):           # (the reference also transforms after the last layer, for nobody)
+                    data = layer.transform(data)           # stays in HBM between layers
         else:
             # same draws in the same order, made by a helper thread that runs ahead of the device; every
             # layer's launches are queued without waiting for the previous layer, parameters come back at the end
             draws = _DrawAhead(self._draw_jobs(int(Xd.shape[0]), int(Xd.shape[1])))
             try:
                 fitted = []
-                for rbm in self.rbm_layers:
+                for i, rbm in enumerate(self.rbm_layers):
                     layer = rbm._fit_device(data, draws=draws, defer_export=True)
                     fitted.append((rbm, layer))
-                    data = layer.transform(data)
+                    if i + 1 < len(self.rbm_layers):
+                        data = layer.transform(data)
                 for rbm, layer in fitted:
                     rbm._adopt(layer)
             finally:
