@@ -416,7 +416,9 @@ def test_operand_upload_equals_the_fp32_upload(act, precision, monkeypatch):
     (csrc/host_stage.c) and goes up as operand rows -- half the PCIe bytes.  The rounding is the device staging
     kernel's, so the trained parameters must be BIT-IDENTICAL to the fp32 upload, on data that is NOT exactly
     representable in 16 bits, through BinaryRBM.fit and the stacked fit, with the upload split into many pieces."""
-    from dbn_b200 import engine as E
+    from dbn_b200 import engine as E, _hoststage
+    if not _hoststage.available():
+        pytest.skip("host staging helper not available (DBN_B200_HOST_STAGE=0 or libdbn_hostrng.so not built)")
     rng = np.random.default_rng(5)
     N, V, hs, bs = 2100 + 37, 520, [192, 128], 128
     X = rng.random((N, V)).astype(np.float32) ** 3

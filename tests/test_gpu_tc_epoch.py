@@ -84,9 +84,15 @@ def test_epoch_matches_tiled_path(precision, V, H, bs, n):
 
 def test_plan_falls_back():
     l = lib()
-    assert l.dbn_rbm_tc_epoch_plan(1, 4096, 4096, 256) == 0      # config 5: CTA-pair kernels
-    assert l.dbn_rbm_tc_epoch_plan(0, 784, 500, 256) == 0        # strict FP32: SIMT / cluster kernel
-    assert l.dbn_rbm_tc_epoch_plan(1, 784, 500, 256) > 0
+    prev = l.dbn_set_tc_epoch(1)      # (the suite may run with DBN_B200_TC_EPOCH=0: the switch is what is tested here)
+    try:
+        assert l.dbn_rbm_tc_epoch_plan(1, 4096, 4096, 256) == 0      # config 5: CTA-pair kernels
+        assert l.dbn_rbm_tc_epoch_plan(0, 784, 500, 256) == 0        # strict FP32: SIMT / cluster kernel
+        assert l.dbn_rbm_tc_epoch_plan(1, 784, 500, 256) > 0
+        l.dbn_set_tc_epoch(0)
+        assert l.dbn_rbm_tc_epoch_plan(1, 784, 500, 256) == 0
+    finally:
+        l.dbn_set_tc_epoch(prev)
 
 
 @pytest.mark.parametrize("V,H", [(784, 500), (500, 2000)])

@@ -58,7 +58,11 @@ CASES = [
 def test_iteration_against_oracle(precision, n_in, hs, n_out, bs, n, act, head):
     import ctypes as C
     dims = (C.c_int32 * len(hs))(*hs)
-    assert lib().dbn_mlp_tc_epoch_plan(1, n_in, dims, len(hs), n_out, min(bs, n)) > 0, "network expected to fit the plan"
+    prev = lib().dbn_set_tc_finetune(1)      # (the suite may run with DBN_B200_TC_FINETUNE=0)
+    try:
+        assert lib().dbn_mlp_tc_epoch_plan(1, n_in, dims, len(hs), n_out, min(bs, n)) > 0, "network expected to fit the plan"
+    finally:
+        lib().dbn_set_tc_finetune(prev)
     rng = np.random.default_rng(n_in + n_out + len(hs))
     layers, Wo, bo = _net(rng, n_in, hs, n_out)
     X = rng.integers(0, 17, (n, n_in)) / 16.0
