@@ -35,6 +35,12 @@ def _oracle_epoch(W, b, c, X, U, bs, k, act, lr, precision):
     (500, 2000, 256, 512, 1, "sigmoid"),     # config 2 layer 3: split-K visible phase
     (256, 256, 32, 96, 1, "relu"),           # config 1 layer 2 shape in a tensor-core mode
     (320, 200, 64, 192, 3, "sigmoid"),       # CD-3, ragged widths
+    (333, 257, 48, 48 * 3 + 7, 1, "sigmoid"),   # odd widths (not multiples of 8), odd batch, short last mini-batch
+    (72, 136, 64, 200, 2, "relu"),           # narrow layer, CD-2
+    (784, 500, 100, 250, 1, "sigmoid"),      # batch 100 (the reference's examples use 32 / 100-row batches)
+    (64, 128, 16, 40, 1, "sigmoid"),         # smallest shapes of the plan
+    (256, 256, 250, 250 + 13, 1, "sigmoid"), # mini-batch just under the 256-row tile
+    (1000, 1100, 128, 256, 1, "sigmoid"),    # wider than config 2 on both sides
 ])
 def test_epoch_against_oracle(precision, V, H, bs, n, k, act):
     assert tc_epoch_plan(V, H, min(bs, n)), "shape expected to fit the persistent kernel"

@@ -51,6 +51,12 @@ CASES = [
     (96, [128], 3, 64, 128, "sigmoid", "linear"),                       # one hidden layer, regression head
     (200, [136, 72, 104, 64], 5, 128, 256, "sigmoid", "softmax"),       # four hidden layers, ragged widths
 ]
+EDGE_CASES = [
+    (784, [500, 500, 2000], 10, 100, 250, "sigmoid", "softmax"),        # config 3 at batch 100 (short last mini-batch)
+    (64, [64], 1, 16, 40, "sigmoid", "linear"),                         # smallest network of the plan, one output
+    (32, [32, 32, 32, 32], 16, 16, 48, "relu", "softmax"),              # four minimal layers, widest head
+    (100, [200, 200], 3, 250, 250 + 9, "sigmoid", "softmax"),           # mini-batch just under the 256-row tile
+]
 
 
 @pytest.mark.parametrize("precision", ["bf16", "fp16"])
@@ -180,3 +186,10 @@ def test_philox_dropout_matches_the_tiled_path(precision, n_in, hs, n_out, bs, n
     kw["seed"] = 99
     r3 = run_mlp_epoch(layers, Wo, bo, X, Y, act, head, precision, bs, tc=True, **kw)
     assert relF(r3["Wo"] - Wo, r1["Wo"] - Wo) > 1e-2
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp16"])
+@pytest.mark.parametrize("n_in,hs,n_out,bs,n,act,head", EDGE_CASES)
+def test_edge_shapes_against_oracle(precision, n_in, hs, n_out, bs, n, act, head):
+    """The corners of the plan (odd batch sizes, minimal widths, four layers, one output, 16 outputs)."""
+    test_iteration_against_oracle(precision, n_in, hs, n_out, bs, n, act, head)
