@@ -197,16 +197,18 @@ __device__ __forceinline__ void mt_head_phase(const MtArgs& a, int s, int valid,
     bo_pre = __ldcg(a.bo + lane);
   }
   if (row_ok) {
-    for (int k = (part * 32 + lane) * 8; k < K; k += 2048) {   // (K % 8 == 0: plan)
-      const uint4 t = __ldcg(reinterpret_cast<const uint4*>(arow + k));
+    for (int k = (part * 32 + lane) * 8; k < K; k += 2048) {   // (K % 4 == 0: plan; a last chunk of 4 when K % 8 == 4)
+      const bool full = k + 8 <= K;
+      const uint4 t = __ldcg(reinterpret_cast<const uint4*>(arow + k));   // (the row pitch covers the whole chunk)
       float x[8];
       unpack16x2(A.dtype, t.x, x[0], x[1]); unpack16x2(A.dtype, t.y, x[2], x[3]);
       unpack16x2(A.dtype, t.z, x[4], x[5]); unpack16x2(A.dtype, t.w, x[6], x[7]);
+      if (!full) x[4] = x[5] = x[6] = x[7] = 0.0f;             // the ones column and the padding behind the last unit
 #pragma unroll
       for (int c = 0; c < MT_MAX_OUT; ++c) {
         if (c < C) {
           const float4 w0 = *reinterpret_cast<const float4*>(wo_s + (size_t)c * a.ldwo + k);
-          const float4 w1 = *reinterpret_cast<const float4*>(wo_s + (size_t)c * a.ldwo + k + 4);
+          const float4 w1 = full ? *reinterpret_cast<const float4*>(wo_s + (size_t)c * a.ldwo + k + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
           float sum = acc[c];
           sum = fmaf(x[0], w0.x, sum); sum = fmaf(x[1], w0.y, sum); sum = fmaf(x[2], w0.z, sum); sum = fmaf(x[3], w0.w, sum);
           sum = fmaf(x[4], w1.x, sum); sum = fmaf(x[5], w1.y, sum); sum = fmaf(x[6], w1.z, sum); sum = fmaf(x[7], w1.w, sum);
@@ -269,6 +271,7 @@ __device__ __forceinline__ void mt_head_phase(const MtArgs& a, int s, int valid,
   for (int c = 0; c < MT_MAX_OUT; ++c) d[c] = (c < C) ? dout[r_in][c] : 0.0f;
   const dbn_mat& D = a.d[a.L - 1];
   for (int k = (part * 32 + lane) * 8; k < K; k += 2048) {
+    const bool full = k + 8 <= K;
     float x[8], sm[8];
     if (row_ok) {
       const uint4 t = __ldcg(reinterpret_cast<const uint4*>(arow + k));
@@ -284,7 +287,7 @@ __device__ __forceinline__ void mt_head_phase(const MtArgs& a, int s, int valid,
     for (int c = 0; c < MT_MAX_OUT; ++c) {
       if (c < C) {
         const float4 w0 = *reinterpret_cast<const float4*>(wo_s + (size_t)c * a.ldwo + k);
-        const float4 w1 = *reinterpret_cast<const float4*>(wo_s + (size_t)c * a.ldwo + k + 4);
+        const float4 w1 = full ? *reinterpret_cast<const float4*>(wo_s + (size_t)c * a.ldwo + k + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
         sm[0] = fmaf(d[c], w0.x, sm[0]); sm[1] = fmaf(d[c], w0.y, sm[1]); sm[2] = fmaf(d[c], w0.z, sm[2]); sm[3] = fmaf(d[c], w0.w, sm[3]);
         sm[4] = fmaf(d[c], w1.x, sm[4]); sm[5] = fmaf(d[c], w1.y, sm[5]); sm[6] = fmaf(d[c], w1.z, sm[6]); sm[7] = fmaf(d[c], w1.w, sm[7]);
       }
@@ -294,7 +297,9 @@ __device__ __forceinline__ void mt_head_phase(const MtArgs& a, int s, int valid,
     uint4 pk;
     pk.x = pack16x2(D.dtype, sm[0], sm[1]); pk.y = pack16x2(D.dtype, sm[2], sm[3]);
     pk.z = pack16x2(D.dtype, sm[4], sm[5]); pk.w = pack16x2(D.dtype, sm[6], sm[7]);
-    *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(D.ptr) + (size_t)row * (size_t)D.ld + (size_t)k) = pk;
+    uint16_t* dst = reinterpret_cast<uint16_t*>(D.ptr) + (size_t)row * (size_t)D.ld + (size_t)k;
+    if (full) *reinterpret_cast<uint4*>(dst) = pk;
+    else *reinterpret_cast<uint2*>(dst) = make_uint2(pk.x, pk.y);   // the padding behind the last unit stays zero (K tail of the next contraction)
   }
 }
 
@@ -676,7 +681,7 @@ inline bool mt_plan(int n_in, const int32_t* dims, int L, int n_out, int B, MtPl
   for (int l = 0; l < L; ++l)
     if (dims[l] < 32) return false;
   const int HL = dims[L - 1];
-  if ((HL % 8) != 0) return false;                       // the head reads 8 activations per lane
+  if ((HL % 4) != 0) return false;                       // the head reads W_o rows as float4 (8 activations per lane, a last chunk of 4)
   const int G = TE_PLAN_CTAS;
   if ((B + 1) / 2 > G) return false;
   MtPlan P;

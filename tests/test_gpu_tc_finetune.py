@@ -56,6 +56,9 @@ EDGE_CASES = [
     (64, [64], 1, 16, 40, "sigmoid", "linear"),                         # smallest network of the plan, one output
     (32, [32, 32, 32, 32], 16, 16, 48, "relu", "softmax"),              # four minimal layers, widest head
     (100, [200, 200], 3, 250, 250 + 9, "sigmoid", "softmax"),           # mini-batch just under the 256-row tile
+    (784, [500, 500], 10, 256, 512 + 40, "sigmoid", "softmax"),         # last hidden layer 500 wide: 500 % 8 == 4, the head's last chunk is half
+    (784, [300], 10, 32, 96, "relu", "softmax"),                        # one 300-wide layer at the reference's default batch
+    (200, [100, 100], 2, 64, 128, "sigmoid", "linear"),                 # the reference's default structure [100, 100]
 ]
 
 
