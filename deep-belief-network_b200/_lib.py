@@ -99,6 +99,8 @@ SYMBOLS = {
     "dbn_last_error": (C.c_char_p, []),
     "dbn_device_count": (C.c_int, []),
     "dbn_launch_count": (C.c_uint64, []),
+    "dbn_set_tail_split": (C.c_int, [C.c_int]),
+    "dbn_tail_split_count": (C.c_uint64, []),
     "dbn_struct_size": (C.c_size_t, [C.c_int]),
     "dbn_debug_set_trace": (C.c_int, [C.c_void_p]),
     "dbn_set_sm_reserve": (C.c_int, [C.c_int]),

@@ -218,6 +218,12 @@ int dbn_abi_version(void) { return DBN_B200_ABI_VERSION; }
 const char* dbn_last_error(void) { return last_error_ref().c_str(); }
 int dbn_device_count(void) { return device_count_cached(); }
 uint64_t dbn_launch_count(void) { return launch_counter().load(); }
+uint64_t dbn_tail_split_count(void) { return ts_counter().load(); }
+int dbn_set_tail_split(int enabled) {
+  const int prev = ts_enabled_flag();
+  ts_enabled_flag() = enabled ? 1 : 0;
+  return prev;
+}
 int dbn_set_sm_reserve(int n_sms) {
   DBN_REQUIRE(n_sms >= 0 && n_sms <= 64, "reserve out of range");
   umma_sm_reserve() = n_sms;

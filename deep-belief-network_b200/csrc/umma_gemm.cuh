@@ -29,6 +29,7 @@
 #pragma once
 #include <cuda.h>
 #include <cooperative_groups.h>
+#include <mutex>
 
 #include "epilogue.cuh"
 
@@ -56,6 +57,12 @@ struct UmmaGemmParams {
   int own_start, own_rows;   // peer scatter: row blocks [own_start, own_start + own_rows) belong to this rank and are visited last
   int split, fs_per;   // split-K kernel: cluster size and fat stages per CTA
   long long* trace;  // debug: per-CTA phase timestamps (dbn_debug_set_trace), normally NULL
+  // CTA-pair kernel, tail split: tiles [0, n_whole) are contracted whole; every later tile by TWO clusters, the fat
+  // stages [0, ts_T0) and [ts_T0, T) of the pass list -- the second one parks its accumulator in ts_part and raises
+  // ts_flag, the first one adds it before the fused epilogue (n_whole == tiles_m * tiles_n: no split)
+  int n_whole, ts_T0;
+  float* ts_part;           // [tile - n_whole][cta][128 rows][BN] fp32
+  unsigned int* ts_flag;    // [tile - n_whole][cta][epilogue warp]
 };
 
 // debug trace slots per CTA: 0 entry (globaltimer ns), 1..6 clock64 at: entry, setup done, first operands
@@ -487,6 +494,26 @@ __device__ __forceinline__ uint32_t make_idesc_2sm(int bn, int transA, int trans
          ((uint32_t)transB << 16) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 }
 
+// Work unit u of the CTA-pair kernel -> tile, range of fat stages, role (0 whole tile, 1 first half + epilogue, 2 second
+// half: partial only).  A grid of few tiles quantises badly over the 74 SM pairs (4096 x 4096: 256 tiles = 3 full waves
+// and a fourth one 46 % full); when the last wave is at most half full, its tiles are split in two along K so that
+// twice as many pairs share it: 3.5 tile times instead of 4.
+struct TsWork {
+  int tile, g0, g1, role;
+};
+__device__ __forceinline__ TsWork ts_work(const UmmaGemmParams& p, int u, int T) {
+  TsWork w;
+  if (u < p.n_whole) {
+    w.tile = u; w.g0 = 0; w.g1 = T; w.role = 0;
+  } else {
+    const int j = u - p.n_whole;
+    w.tile = p.n_whole + (j >> 1);
+    if (j & 1) { w.g0 = p.ts_T0; w.g1 = T; w.role = 2; }
+    else { w.g0 = 0; w.g1 = p.ts_T0; w.role = 1; }
+  }
+  return w;
+}
+
 template <int BN, int KS, class Epi>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UG_THREADS, 1)
 umma_gemm2_kernel(const __grid_constant__ UmmaGemmParams p, const __grid_constant__ Epi epi_args, int coreM, int coreN,
@@ -518,6 +545,9 @@ umma_gemm2_kernel(const __grid_constant__ UmmaGemmParams p, const __grid_constan
   const bool leader = cta == 0;
   const int n_tiles = p.tiles_m * p.tiles_n;     // tiles_m counts 256-row blocks here
   const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  const int n_units = p.n_whole + 2 * (n_tiles - p.n_whole);   // (tail split: see ts_work)
+  int T = 0;                                                   // fat stages of a whole tile
+  for (int pass = 0; pass < p.n_ops; ++pass) T += (p.nslab[pass] + KS - 1) / KS;
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < p.n_ops; ++i) {   // hide the descriptor fetch behind the barrier / TMEM setup
@@ -553,14 +583,17 @@ umma_gemm2_kernel(const __grid_constant__ UmmaGemmParams p, const __grid_constan
     // ===================== TMA producer (both CTAs) =====================
     if (lane == 0) {
       uint32_t it = 0;
-      for (int tile = cluster_id; tile < n_tiles; tile += n_clusters) {
+      for (int u = cluster_id; u < n_units; u += n_clusters) {
+        const TsWork w = ts_work(p, u, T);
         int mb, nb;
-        tile_coords(p, tile, mb, nb);
+        tile_coords(p, w.tile, mb, nb);
         const int m0 = mb * 256 + (int)cta * UG_BM;
         const int n0 = nb * BN + (int)cta * HB;
+        int g = 0;
         for (int pass = 0; pass < p.n_ops; ++pass) {
           const int nfs = (p.nslab[pass] + KS - 1) / KS;
-          for (int f = 0; f < nfs; ++f, ++it) {
+          for (int f = 0; f < nfs; ++f, ++g) {
+            if (g < w.g0 || g >= w.g1) continue;
             const int s = it % STAGES;
             const uint32_t ph = (it / STAGES) & 1u;
             mbar_wait(empty_bar(s), ph ^ 1u);
@@ -571,6 +604,7 @@ umma_gemm2_kernel(const __grid_constant__ UmmaGemmParams p, const __grid_constan
             else                 tma_load_3d_2sm(sa, &p.tmA[pass], full_bar(s), 0, p.rowA[pass] + slab0 * UG_BK, m0 / 64);
             if (!p.transB[pass]) tma_load_3d_2sm(sb, &p.tmB[pass], full_bar(s), 0, p.rowB[pass] + n0, slab0);
             else                 tma_load_3d_2sm(sb, &p.tmB[pass], full_bar(s), 0, p.rowB[pass] + slab0 * UG_BK, n0 / 64);
+            ++it;
           }
         }
       }
@@ -579,19 +613,22 @@ umma_gemm2_kernel(const __grid_constant__ UmmaGemmParams p, const __grid_constan
     // ===================== MMA issuer (leader CTA only) =====================
     if (leader && lane == 0) {
       uint32_t it = 0, tl = 0;
-      for (int tile = cluster_id; tile < n_tiles; tile += n_clusters, ++tl) {
+      for (int u = cluster_id; u < n_units; u += n_clusters, ++tl) {
+        const TsWork w = ts_work(p, u, T);
         const int as = tl & 1;
         const uint32_t aph = (tl >> 1) & 1u;
         mbar_wait(tempty_bar(as), aph ^ 1u);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
         uint32_t accumulate = 0;
+        int g = 0;
         for (int pass = 0; pass < p.n_ops; ++pass) {
           const int nslab = p.nslab[pass];
           const int nfs = (nslab + KS - 1) / KS;
           const int tA = p.transA[pass], tB = p.transB[pass];
           const uint32_t idesc = make_idesc_2sm(BN, tA, tB, pass == 1, p.fmtA[pass], p.fmtB[pass]);
-          for (int f = 0; f < nfs; ++f, ++it) {
+          for (int f = 0; f < nfs; ++f, ++g) {
+            if (g < w.g0 || g >= w.g1) continue;
             const int s = it % STAGES;
             const uint32_t ph = (it / STAGES) & 1u;
             mbar_wait(full_bar(s), ph);
@@ -613,6 +650,7 @@ umma_gemm2_kernel(const __grid_constant__ UmmaGemmParams p, const __grid_constan
               }
             }
             tc_commit_2sm(empty_bar(s));   // frees this stage in BOTH CTAs
+            ++it;
           }
         }
         tc_commit_2sm(tfull_bar(as));      // both CTAs' epilogues may drain their half
@@ -624,13 +662,25 @@ umma_gemm2_kernel(const __grid_constant__ UmmaGemmParams p, const __grid_constan
     uint32_t epoch = 0;
     if constexpr (!Epi::kIsUpdate) epoch = epi_args.e.rng.epoch + (epi_args.e.rng.epoch_ptr ? *epi_args.e.rng.epoch_ptr : 0u);
     uint32_t tl = 0;
-    for (int tile = cluster_id; tile < n_tiles; tile += n_clusters, ++tl) {
+    for (int u = cluster_id; u < n_units; u += n_clusters, ++tl) {
+      const TsWork w = ts_work(p, u, T);
       int mb, nb;
-      tile_coords(p, tile, mb, nb);
+      tile_coords(p, w.tile, mb, nb);
       const int as = tl & 1;
       const uint32_t aph = (tl >> 1) & 1u;
       mbar_wait(tfull_bar(as), aph);
       tc_fence_after();
+      // tail split: this thread's row of the parked partial, this warp's flag (same cta / warp / lane in both clusters)
+      // (the partial is stored the way the warp holds it -- [chunk][quad of columns][lane] float4 -- so that every store /
+      // load instruction of a warp covers 512 contiguous bytes)
+      float4* part = nullptr;
+      unsigned int* flag = nullptr;
+      bool waited = w.role != 1;
+      if (w.role != 0) {
+        const size_t ws = ((size_t)(w.tile - p.n_whole) * 2 + cta) * UG_EPI_WARPS + (size_t)(warp - 2);
+        part = reinterpret_cast<float4*>(p.ts_part) + ws * (size_t)((BN / 32) / (UG_EPI_WARPS / 4) * 8 * 32) + lane;
+        flag = p.ts_flag + ws;
+      }
       const int m = mb * 256 + (int)cta * UG_BM + q * 32 + lane;
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
       constexpr int CH_PER_WARP = (BN / 32) / (UG_EPI_WARPS / 4);
@@ -646,8 +696,47 @@ umma_gemm2_kernel(const __grid_constant__ UmmaGemmParams p, const __grid_constan
         float acc[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(v[j]);
+        if (w.role == 2) {         // second half of a split tile: park the partial, no epilogue
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            __stcg(part + ((ch - ch0) * 8 + j) * 32, make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]));
+          continue;
+        }
+        if (w.role == 1) {
+          if (!waited) {           // the other half's accumulator must have been parked (first chunk only)
+            if (lane == 0) {
+              unsigned f = 0;
+              do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(f) : "l"(flag) : "memory");
+              } while (f == 0);
+            }
+            __syncwarp();
+            waited = true;
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 x = __ldcg(part + ((ch - ch0) * 8 + j) * 32);
+            acc[4 * j] += x.x; acc[4 * j + 1] += x.y; acc[4 * j + 2] += x.z; acc[4 * j + 3] += x.w;
+          }
+        }
         if (epi_args.scatter()) epi_args.apply_scatter(stage, m, n0, acc, coreM, coreN);
         else epi_args.apply(epoch, m, n0, acc, coreM, coreN, augM, augN);
+      }
+      if (w.role == 2) {           // publish the partial: every lane's stores, then the flag
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flag), "r"(1u) : "memory");
+      } else if (w.role == 1) {    // consumed: the flag is clear again for the next launch that uses this slot
+        __syncwarp();
+        if (lane == 0) {
+          if (!waited) {           // (a warp whose columns all lie beyond N never looked: the flag must be up before it is cleared)
+            unsigned f = 0;
+            do {
+              asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(f) : "l"(flag) : "memory");
+            } while (f == 0);
+          }
+          asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(flag), "r"(0u) : "memory");
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -1222,6 +1311,63 @@ inline long sk_cycles(int bn, int S, int per, bool upd) {
 
 constexpr int UG2_KS = 2;   // CTA-pair kernel: 2 slabs (K = 128) per stage, 64 KB per CTA, 3 stages
 
+// ---- tail split of the CTA-pair kernel (see ts_work) ----------------------------------------------------------
+// Scratch for the parked partials: TS_SLOTS launches may be in flight on different streams (a fine-tune step forks its
+// updates onto a second stream); a launch takes the next slot round-robin.  Allocated once per device, outside any
+// stream capture (a launch that meets a capturing stream before the first allocation simply does not split).
+constexpr int TS_SLOTS = 4, TS_MAX_TILES = 40;
+struct TsScratch {
+  float* part;
+  unsigned int* flag;
+  std::atomic<unsigned> next;
+};
+inline int& ts_enabled_flag() {   // DBN_B200_TAIL_SPLIT=0 contracts every tile whole; dbn_set_tail_split() overrides (tests, A/B runs)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DBN_B200_TAIL_SPLIT");
+    v = (e == nullptr || e[0] != '0') ? 1 : 0;
+  }
+  return v;
+}
+inline std::atomic<uint64_t>& ts_counter() {
+  static std::atomic<uint64_t> c{0};
+  return c;
+}
+inline TsScratch* ts_scratch(cudaStream_t st) {
+  static TsScratch sc[DBN_MAX_DEVICES];
+  static std::atomic<int> state[DBN_MAX_DEVICES];   // 0 not tried, 1 ready, 2 unavailable
+  const int dev = current_device();
+  int stt = state[dev].load(std::memory_order_acquire);
+  if (stt == 1) return &sc[dev];
+  if (stt == 2) return nullptr;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) {
+    (void)cudaGetLastError();
+    return nullptr;               // not now: allocate at the next eager launch
+  }
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  stt = state[dev].load(std::memory_order_acquire);
+  if (stt == 1) return &sc[dev];
+  if (stt == 2) return nullptr;
+  const size_t part_bytes = (size_t)TS_SLOTS * TS_MAX_TILES * 2 * UG_BM * 256 * sizeof(float);
+  const size_t flag_bytes = (size_t)TS_SLOTS * TS_MAX_TILES * 2 * UG_EPI_WARPS * sizeof(unsigned int);
+  void *a = nullptr, *b = nullptr;
+  if (cudaMalloc(&a, part_bytes) != cudaSuccess || cudaMalloc(&b, flag_bytes) != cudaSuccess ||
+      cudaMemset(b, 0, flag_bytes) != cudaSuccess) {
+    (void)cudaGetLastError();
+    if (a) cudaFree(a);
+    if (b) cudaFree(b);
+    state[dev].store(2, std::memory_order_release);
+    return nullptr;
+  }
+  sc[dev].part = static_cast<float*>(a);
+  sc[dev].flag = static_cast<unsigned int*>(b);
+  sc[dev].next.store(0);
+  state[dev].store(1, std::memory_order_release);
+  return &sc[dev];
+}
+
 template <int BN, class Epi>
 inline int umma_launch2(cudaStream_t st, UmmaGemmParams& p, const Epi& epi, int coreM, int coreN, int augM, int augN) {
   constexpr int STAGE_BYTES = UG2_KS * (UG_BM + BN / 2) * UG_BK * 2;
@@ -1239,6 +1385,21 @@ inline int umma_launch2(cudaStream_t st, UmmaGemmParams& p, const Epi& epi, int 
   epi.scatter_order(p);    // peer scatter: the tile order is the traffic pattern
   const int n_tiles = p.tiles_m * p.tiles_n;
   const int clusters = std::min(n_tiles, umma_num_sms() / 2);
+  // tail split: the last wave of tiles, when at most half full, is contracted by two clusters per tile (half of K each)
+  p.n_whole = n_tiles; p.ts_T0 = 0; p.ts_part = nullptr; p.ts_flag = nullptr;
+  int T = 0;
+  for (int i = 0; i < p.n_ops; ++i) T += ceil_div(p.nslab[i], UG2_KS);
+  const int tail = n_tiles % clusters;
+  if (ts_enabled_flag() == 1 && n_tiles > clusters && tail > 0 && 2 * tail <= clusters && tail <= TS_MAX_TILES && T >= 24) {   // (K >= 3072: below that the hand-over of the partial costs more than half a tile)
+    if (TsScratch* sc = ts_scratch(st)) {
+      const unsigned slot = sc->next.fetch_add(1) % TS_SLOTS;
+      p.n_whole = n_tiles - tail;
+      p.ts_T0 = T / 2;
+      p.ts_part = sc->part + (size_t)slot * TS_MAX_TILES * 2 * UG_BM * 256;
+      p.ts_flag = sc->flag + (size_t)slot * TS_MAX_TILES * 2 * UG_EPI_WARPS;
+      ts_counter().fetch_add(1);
+    }
+  }
   DBN_CUDA_OK(launch_pdl(umma_gemm2_kernel<BN, UG2_KS, Epi>, dim3(clusters * 2), dim3(UG_THREADS), SMEM, st, p, epi, coreM,
                          coreN, augM, augN));
   DBN_LAUNCH_CHECK();

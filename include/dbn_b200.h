@@ -192,6 +192,13 @@ const char* dbn_last_error(void);
 int dbn_device_count(void);
 /* Counts kernels launched by this library since load (bench.py's `gpu_launches`). */
 uint64_t dbn_launch_count(void);
+
+/* CTA-pair contraction (4096-wide layers): when the last wave of 256 x 256 tiles fills at most half of the SM pairs
+ * (256 tiles on 74 pairs: 3 waves and one 46 % full), each of its tiles is contracted by two pairs, half of K each, and
+ * the halves are summed before the fused epilogue (csrc/umma_gemm.cuh, ts_work).  dbn_set_tail_split(0) contracts every
+ * tile whole (also DBN_B200_TAIL_SPLIT=0); returns the previous setting.  dbn_tail_split_count: launches that split. */
+int dbn_set_tail_split(int enabled);
+uint64_t dbn_tail_split_count(void);
 /* Keep n_sms SMs free of the persistent contraction kernels (0 = use all; default).  Data-parallel
  * callers set this so the collective's kernels can run next to the contraction they overlap with. */
 int dbn_set_sm_reserve(int n_sms);

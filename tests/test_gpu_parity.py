@@ -552,3 +552,58 @@ def test_split_k_update_kernel_matches_numpy(M, N, K):
     assert np.max(np.abs(vM.cpu().numpy() - (vM0 + 0.01 * D[:M, N]))) < 1e-4 * max(1.0, np.abs(D[:M, N]).max())
     assert np.max(np.abs(vN.cpu().numpy() - (vN0 + 0.01 * D[M, :N]))) < 1e-4 * max(1.0, np.abs(D[M, :N]).max())
     assert ctas > 0
+
+
+@pytest.mark.parametrize("K,two_ops", [(1536, True), (3072, False), (4096, True)])
+def test_tail_split_of_the_cta_pair_contraction(K, two_ops):
+    """4096 x 4096 outputs are 256 CTA-pair tiles on 74 SM pairs: three full waves and a fourth one 46 % full.  The
+    tiles of that last wave are contracted by two pairs each (half of the K stages per pair; the second half parks its
+    fp32 accumulator in scratch, the first adds it before the fused epilogue).  Checked against float64 on the same
+    operands, against the unsplit launch (same sums in another order), with one and two operand pairs (dW = P0^T V0 -
+    Pk^T Vk: the split point then falls on / next to the boundary between the passes), launch after launch (the flags
+    must be clear again) -- and the counter proves the split ran."""
+    import ctypes as C
+    import torch
+    from dbn_b200 import _lib as L, engine as E
+    lib = G.lib()
+    M = N = 4096
+    rng = np.random.default_rng(K)
+
+    def operand(cols, binary):
+        t = torch.zeros(K, E.bf16_pitch(cols), dtype=torch.bfloat16, device="cuda")
+        x = (rng.random((K, cols)) < 0.5).astype(np.float32) if binary else rng.random((K, cols)).astype(np.float32)
+        t[:, :cols] = torch.as_tensor(x).cuda().to(torch.bfloat16)
+        return t
+
+    pairs = [(operand(M, False), operand(N, True))] + ([(operand(M, False), operand(N, False))] if two_ops else [])
+    ops = (L.Operands * 2)()
+    for o, (a, bm) in zip(ops, pairs):
+        o.A, o.B, o.transA, o.transB, o.K = E.mat(a), E.mat(bm), 1, 1, K
+    f = lambda t, c: t[:, :c].float().cpu().numpy().astype(np.float64)
+    ref = f(pairs[0][0], M).T @ f(pairs[0][1], N)
+    if two_ops:
+        ref = ref - f(pairs[1][0], M).T @ f(pairs[1][1], N)
+    scale = np.max(np.abs(f(pairs[0][0], M).T @ f(pairs[0][1], N)))
+
+    def run(split):
+        prev = lib.dbn_set_tail_split(1 if split else 0)
+        try:
+            raw = torch.full((M + 1, N + 8), -3.0, device="cuda")
+            u = L.UpdateEpilogue()
+            u.decay, u.scale, u.raw = 1.0, 1.0, E.mat(raw)
+            before = lib.dbn_tail_split_count()
+            L.check(lib.dbn_gemm_update(E.stream_ptr(), L.PREC_BF16, M, N, 0, 0, ops, len(pairs), C.byref(u)))
+            torch.cuda.synchronize()
+            return raw.cpu().numpy(), int(lib.dbn_tail_split_count() - before)
+        finally:
+            lib.dbn_set_tail_split(prev)
+
+    whole, n0 = run(False)
+    assert n0 == 0
+    for _ in range(3):                      # repeated launches reuse the scratch slots round-robin
+        got, n1 = run(True)
+        assert n1 == 1, "the launch was expected to split its last wave"
+        assert np.all(got[M:, :] == -3.0) and np.all(got[:, N:] == -3.0)
+        assert np.max(np.abs(got[:M, :N] - ref)) < 5e-5 * scale
+        assert np.max(np.abs(got[:M, :N] - whole[:M, :N])) < 2e-5 * scale
+    assert np.max(np.abs(whole[:M, :N] - ref)) < 5e-5 * scale
