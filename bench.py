@@ -362,9 +362,14 @@ def timed(c, fn, steps, warmup, finish=None):
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop()
     if c.world > 1:
-        t = torch.tensor([ms], device=c.dev)
-        c.dist.all_reduce(t, op=c.dist.ReduceOp.MAX)
-        ms = float(t.item())
+        # every rank's own time and median SM clock travel with the line: a straggler (a GPU held at low clocks, a
+        # starved host thread) shows up here instead of silently setting the max
+        mine = torch.tensor([ms, float(clocks.get("sm_mhz") or 0.0)], device=c.dev)
+        every = [torch.zeros_like(mine) for _ in range(c.world)]
+        c.dist.all_gather(every, mine)
+        clocks["ms_per_rank"] = [round(float(t[0].item()), 3) for t in every]
+        clocks["sm_mhz_per_rank"] = [float(t[1].item()) for t in every]
+        ms = max(clocks["ms_per_rank"] + [ms])
     return ms, clocks, int(c.lib.dbn_launch_count() - n0)
 
 
