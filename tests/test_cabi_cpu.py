@@ -113,3 +113,16 @@ def test_persistent_kernel_plans_are_pure_host_functions():
     prev = lib.dbn_set_tc_finetune(0)
     assert lib.dbn_mlp_tc_epoch_plan(L.PREC_BF16, 784, dims, 3, 10, 256) == 0
     lib.dbn_set_tc_finetune(prev)
+
+
+def test_scheduling_switches_are_host_state():
+    """dbn_set_tc_epoch / dbn_set_tc_finetune / dbn_set_tail_split flip process-wide host flags and return the previous
+    value (tests and A/B runs rely on restoring them); none of them needs a device."""
+    lib = L.load()
+    for name in ("dbn_set_tc_epoch", "dbn_set_tc_finetune", "dbn_set_tail_split"):
+        fn = getattr(lib, name)
+        prev = fn(0)
+        assert prev in (0, 1)
+        assert fn(1) == 0 and fn(prev) == 1
+        assert fn(prev) == prev
+    assert lib.dbn_tail_split_count() >= 0
